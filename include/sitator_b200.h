@@ -1,0 +1,135 @@
+/* sitator_b200 -- C ABI of the B200-native landmark-analysis path.
+ *
+ * Drop-in boundary for the native part of sitator's landmark analysis.  The reference's only
+ * native entry on this path is the Cython function
+ *     helpers._fill_landmark_vectors(self, sn, verts_np, site_vert_dists, frames, ...)
+ *         (/root/reference/sitator/landmark/helpers.pyx:12-124)
+ * plus the library calls its MCL clustering plugin makes on the landmark-vector matrix
+ *     (sitator/landmark/cluster/mcl.py:53-54, :81-89, :98-122; sitator/util/mcl.py:3-60;
+ *      sitator/util/DotProdClassifier.pyx:68-197)
+ * and the per-frame scans of SiteTrajectory / JumpAnalysis
+ *     (sitator/SiteTrajectory.py:205-232, :307-373; sitator/dynamics/JumpAnalysis.py:27-135).
+ * Each entry point below names the reference code it replaces.
+ *
+ * Conventions: plain C, no exceptions.  Every function returns 0 on success or a negative
+ * SITB_E_* code; sitb_last_error() gives the message for the calling thread.  Pointers named
+ * host_* are host memory, dev_* are device memory on the context's GPU (e.g. a
+ * torch tensor's data_ptr()).  Work is enqueued on the context's CUDA stream
+ * (sitb_set_stream); functions that return results to the host synchronise that stream.
+ * There is no CPU fallback: without a CUDA device sitb_create fails with SITB_E_CUDA.
+ */
+#ifndef SITATOR_B200_H
+#define SITATOR_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SITB_OK 0
+#define SITB_E_INVALID (-1)   /* bad argument */
+#define SITB_E_CUDA (-2)      /* CUDA runtime error (message has the cudaError string) */
+#define SITB_E_STATE (-3)     /* call sequence error (e.g. no frames uploaded) */
+#define SITB_E_LIMIT (-4)     /* a documented size limit was exceeded */
+
+/* error_code values of sitb_status, in the reference's raise order inside one frame */
+#define SITB_ERR_NONE 0
+#define SITB_ERR_STATIC_MOVED 1       /* helpers.pyx:76-80  StaticLatticeError(lattice_atoms=[index], frame) */
+#define SITB_ERR_STATIC_UNASSIGNED 2  /* helpers.pyx:87-92  StaticLatticeError(lattice_atoms=unassigned, frame) */
+#define SITB_ERR_ZERO_LANDMARK 3      /* helpers.pyx:116-118 ZeroLandmarkError(mobile_index=index, frame) */
+
+typedef struct sitb_ctx sitb_ctx;
+
+/* The landmark basis and the analysis parameters (LandmarkAnalysis.__init__, LandmarkAnalysis.py:95-130;
+ * SiteNetwork inputs, LandmarkAnalysis.py:179-202). */
+typedef struct sitb_network_desc {
+    int32_t n_atoms;       /* atoms per frame (sn.n_total) */
+    int32_t n_static;      /* sn.n_static  */
+    int32_t n_mobile;      /* sn.n_mobile  */
+    int32_t n_landmarks;   /* sn.n_sites = landmark dimension */
+    int32_t max_verts;     /* columns of verts (<= 8) */
+    const double* host_cellmat;      /* [3][3] = cell^T           (PBCCalculator.pyx:33) */
+    const double* host_cellmat_inv;  /* [3][3] inverse of cellmat (PBCCalculator.pyx:34); NULL: computed by adjugate */
+    const int32_t* host_static_idx;  /* [n_static] frame index of each static-lattice atom, ascending */
+    const int32_t* host_mobile_idx;  /* [n_mobile] */
+    const double* host_ideal_static; /* [n_static][3] sn.static_structure.positions */
+    const double* host_centers;      /* [n_landmarks][3] sn.centers */
+    const int32_t* host_verts;       /* [n_landmarks][max_verts] indexes into the static lattice, -1 padded (LandmarkAnalysis.py:195) */
+    double cutoff_midpoint;          /* LandmarkAnalysis.py:98 */
+    double cutoff_steepness;         /* LandmarkAnalysis.py:99 */
+    double cutoff_round_to_zero;     /* helpers.pyx:127-131 evaluated by the caller (libm log), or <= 0 to compute here */
+    double static_movement_threshold;/* LandmarkAnalysis.py:103 */
+    int32_t dynamic_lattice_mapping; /* LandmarkAnalysis.py:104 */
+    int32_t relaxed_lattice_checks;  /* LandmarkAnalysis.py:105 */
+} sitb_network_desc;
+
+typedef struct sitb_status {
+    int32_t error_code;   /* SITB_ERR_*: the first error in the reference's iteration order */
+    int32_t index;        /* lattice index (STATIC_MOVED) or mobile index (ZERO_LANDMARK) */
+    int64_t frame;        /* global frame index of that error */
+    int32_t zero_error;   /* 1 if a zero landmark vector occurred; zero_frame/zero_index locate the first */
+    int32_t zero_index;
+    int64_t zero_frame;
+    uint64_t n_zero_rows;        /* self.n_all_zero_lvecs (helpers.pyx:124) */
+    uint64_t n_duplicate_nearest;/* count of the warning at helpers.pyx:69-71 */
+    uint64_t n_list_overflow;    /* rows with more than 256 non-zero components (must be 0) */
+    uint64_t nnz;                /* non-zero landmark-vector components produced */
+    uint64_t n_float_ties;       /* cut-off tests that needed the double compare */
+} sitb_status;
+
+const char* sitb_last_error(void);
+int sitb_version(void);
+
+/* Context: device copies of the basis + precomputed tables (replaces LandmarkAnalysis.py:179, :191-202). */
+int sitb_create(const sitb_network_desc* desc, int device, sitb_ctx** out);
+void sitb_destroy(sitb_ctx* ctx);
+int sitb_set_stream(sitb_ctx* ctx, void* cuda_stream);
+int sitb_device_info(sitb_ctx* ctx, int32_t* n_sms, int32_t* cc_major, int32_t* cc_minor);
+
+/* site_vert_dists [L][V] (NaN padded, LandmarkAnalysis.py:196-202) and the squared cut-off table. */
+int sitb_get_tables(sitb_ctx* ctx, double* host_site_vert_dists, double* host_q_cutoff);
+
+/* Frames: copied once and kept resident for all passes, or borrowed from the caller's device buffer.
+ * frame0 = global index of the first frame (frame-sharded runs). */
+int sitb_upload_frames(sitb_ctx* ctx, const double* host_frames, int64_t n_frames, int64_t frame0);
+int sitb_borrow_frames(sitb_ctx* ctx, const double* dev_frames, int64_t n_frames, int64_t frame0);
+
+int sitb_reset_status(sitb_ctx* ctx);
+int sitb_get_status(sitb_ctx* ctx, sitb_status* out);
+
+/* helpers._fill_landmark_vectors (helpers.pyx:12-124) into a device matrix [(n*M)][L], float32 or float64. */
+int sitb_fill_dense(sitb_ctx* ctx, int64_t frame_begin, int64_t n, void* dev_out, int32_t out_is_f64);
+/* same for a list of (local) frame indices: rows i*M..i*M+M-1 of dev_out hold frame dev_frame_list[i] */
+int sitb_fill_dense_frames(sitb_ctx* ctx, const int64_t* dev_frame_list, int64_t n, void* dev_out, int32_t out_is_f64);
+
+/* cluster/mcl.py:53-54: seen_ntimes [L] (+=) and the un-normalised Gram sum_rows lv^T lv [L][L] (+=, upper
+ * triangle) by sparse outer products in FP64 -- the exact cross-check of the tensor-core SYRK. */
+int sitb_pass_stats(sitb_ctx* ctx, int64_t frame_begin, int64_t n, uint64_t* dev_seen, double* dev_gram_upper);
+
+/* Cluster centres (cluster/mcl.py:70-96): centres have disjoint supports, so they are given as a
+ * landmark -> cluster map (-1 none) and a landmark weight. */
+int sitb_set_centers(sitb_ctx* ctx, const int32_t* host_cluster_of_landmark, const float* host_weight,
+                     int32_t n_clusters);
+
+/* DotProdClassifier.predict (DotProdClassifier.pyx:129-197, predict_normed=False) fused with the fill.
+ * Any output pointer may be NULL.
+ *   dev_labels[n*M] int64 (-1 unassigned), dev_confs[n*M] float64,
+ *   dev_counts[C] += bincount(labels)                              (DotProdClassifier.pyx:92)
+ *   dev_best[C]   = max over rows of key(|centre.x|, first row)    (cluster/mcl.py:81-83)
+ *   dev_rep[C][L] += conf * lvec, dev_rep_w[C] += conf             (cluster/mcl.py:118-122)
+ *   dev_site_best[C] = max over rows of key(conf, first row)       (PBCCalculator.pyx:120-122 via LandmarkAnalysis.py:285)
+ * key = (float bits << 32) | (0xFFFFFFFF - global row). */
+int sitb_pass_assign(sitb_ctx* ctx, int64_t frame_begin, int64_t n, float threshold, int64_t* dev_labels,
+                     double* dev_confs, uint64_t* dev_counts, uint64_t* dev_best, double* dev_rep,
+                     double* dev_rep_w, uint64_t* dev_site_best);
+
+/* Reference-facing, host buffers in and out: what sitator/landmark/helpers.pyx:12 computes.
+ * frames [n_frames][n_atoms][3] float64 -> landmark vectors [n_frames*n_mobile][n_landmarks] float64. */
+int sitb_fill_landmark_vectors_host(sitb_ctx* ctx, const double* host_frames, int64_t n_frames,
+                                    double* host_landmark_vectors, sitb_status* status);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SITATOR_B200_H */

@@ -1,0 +1,404 @@
+// sitator_b200 -- C ABI (include/sitator_b200.h): context, frame residency, pass launchers.
+#include "../../include/sitator_b200.h"
+#include "sitb_fill.cuh"
+
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <vector>
+
+namespace sitb {
+cudaError_t launch_tables(const Cell& cell, const double* centers, const double* ideal, const int* verts_in, int L,
+                          int V, int Lpad, int S, double cutoff, double steep_log2e, double* svd_out,
+                          uint16_t* verts, float* qf, double* q64, double* acoef, cudaStream_t stream);
+}
+
+using namespace sitb;
+
+static thread_local char g_err[512] = "";
+
+static int fail(int code, const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+#define CK(call)                                                                                   \
+    do {                                                                                           \
+        cudaError_t e_ = (call);                                                                   \
+        if (e_ != cudaSuccess)                                                                     \
+            return fail(SITB_E_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+    } while (0)
+
+struct sitb_ctx {
+    int device = 0;
+    int n_sms = 0, cc_major = 0, cc_minor = 0;
+    int A = 0, S = 0, M = 0, L = 0, V = 0, Lpad = 0;
+    Cell cell;
+    double midpoint = 0, steepness = 0, cutoff = 0, static_thr = 0, bcoef = 0;
+    int dynamic = 0, relaxed = 0;
+    cudaStream_t stream = 0;
+    // device tables
+    int* d_static_idx = nullptr;
+    int* d_mobile_idx = nullptr;
+    double* d_ideal = nullptr;
+    double* d_centers = nullptr;
+    int* d_verts_in = nullptr;
+    double* d_svd = nullptr;
+    uint16_t* d_verts = nullptr;
+    float* d_qf = nullptr;
+    double* d_q64 = nullptr;
+    double* d_acoef = nullptr;
+    // centres
+    int* d_cid = nullptr;
+    float* d_cw = nullptr;
+    int n_clusters = 0;
+    // frames
+    const double* d_frames = nullptr;
+    double* d_frames_owned = nullptr;
+    size_t frames_capacity = 0;      // bytes
+    long long n_frames = 0, frame0 = 0;
+    // status
+    unsigned long long* d_status = nullptr;   // [2] error keys + [CNT_SLOTS] counters
+};
+
+static void free_ctx(sitb_ctx* c) {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    cudaFree(c->d_static_idx); cudaFree(c->d_mobile_idx); cudaFree(c->d_ideal); cudaFree(c->d_centers);
+    cudaFree(c->d_verts_in); cudaFree(c->d_svd); cudaFree(c->d_verts); cudaFree(c->d_qf); cudaFree(c->d_q64);
+    cudaFree(c->d_acoef); cudaFree(c->d_cid); cudaFree(c->d_cw); cudaFree(c->d_frames_owned); cudaFree(c->d_status);
+    delete c;
+}
+
+template <typename T>
+static cudaError_t upload(T** dst, const T* src, size_t n) {
+    cudaError_t e = cudaMalloc((void**)dst, sizeof(T) * (n ? n : 1));
+    if (e != cudaSuccess) return e;
+    if (n) e = cudaMemcpy(*dst, src, sizeof(T) * n, cudaMemcpyHostToDevice);
+    return e;
+}
+
+extern "C" const char* sitb_last_error(void) { return g_err; }
+extern "C" int sitb_version(void) { return 100; }
+
+extern "C" int sitb_create(const sitb_network_desc* d, int device, sitb_ctx** out) {
+    if (!d || !out) return fail(SITB_E_INVALID, "sitb_create: null argument");
+    *out = nullptr;
+    if (d->n_atoms <= 0 || d->n_static <= 0 || d->n_mobile <= 0 || d->n_landmarks <= 0 || d->max_verts <= 0)
+        return fail(SITB_E_INVALID, "sitb_create: sizes must be positive");
+    if (d->max_verts > 8) return fail(SITB_E_LIMIT, "sitb_create: max_verts %d > 8", d->max_verts);
+    if (d->n_static >= 65535) return fail(SITB_E_LIMIT, "sitb_create: n_static %d >= 65535", d->n_static);
+    if (d->n_landmarks >= 65535) return fail(SITB_E_LIMIT, "sitb_create: n_landmarks %d >= 65535", d->n_landmarks);
+    if (!d->host_cellmat || !d->host_static_idx || !d->host_mobile_idx || !d->host_ideal_static ||
+        !d->host_centers || !d->host_verts)
+        return fail(SITB_E_INVALID, "sitb_create: null table pointer");
+    for (int i = 0; i < d->n_static; ++i)
+        if (d->host_static_idx[i] < 0 || d->host_static_idx[i] >= d->n_atoms)
+            return fail(SITB_E_INVALID, "sitb_create: static_idx[%d] out of range", i);
+    for (int i = 0; i < d->n_mobile; ++i)
+        if (d->host_mobile_idx[i] < 0 || d->host_mobile_idx[i] >= d->n_atoms)
+            return fail(SITB_E_INVALID, "sitb_create: mobile_idx[%d] out of range", i);
+    for (int k = 0; k < d->n_landmarks; ++k) {
+        if (d->host_verts[(size_t)k * d->max_verts] < 0)
+            return fail(SITB_E_INVALID, "sitb_create: landmark %d has no vertices", k);
+        for (int h = 0; h < d->max_verts; ++h)
+            if (d->host_verts[(size_t)k * d->max_verts + h] >= d->n_static)
+                return fail(SITB_E_INVALID, "sitb_create: verts[%d][%d] out of range", k, h);
+    }
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+        return fail(SITB_E_CUDA, "sitb_create: no CUDA device (%s); this library has no CPU path",
+                    e != cudaSuccess ? cudaGetErrorString(e) : "count = 0");
+    if (device < 0 || device >= ndev) return fail(SITB_E_INVALID, "sitb_create: device %d of %d", device, ndev);
+    CK(cudaSetDevice(device));
+    sitb_ctx* c = new (std::nothrow) sitb_ctx();
+    if (!c) return fail(SITB_E_INVALID, "out of host memory");
+    c->device = device;
+    cudaDeviceProp prop;
+    e = cudaGetDeviceProperties(&prop, device);
+    if (e != cudaSuccess) { free_ctx(c); return fail(SITB_E_CUDA, "cudaGetDeviceProperties: %s", cudaGetErrorString(e)); }
+    c->n_sms = prop.multiProcessorCount; c->cc_major = prop.major; c->cc_minor = prop.minor;
+    c->A = d->n_atoms; c->S = d->n_static; c->M = d->n_mobile; c->L = d->n_landmarks; c->V = d->max_verts;
+    c->Lpad = (c->L + 31) & ~31;
+    // cell
+    for (int i = 0; i < 9; ++i) c->cell.c[i] = d->host_cellmat[i];
+    if (d->host_cellmat_inv) {
+        for (int i = 0; i < 9; ++i) c->cell.ci[i] = d->host_cellmat_inv[i];
+    } else {
+        const double* m = c->cell.c;
+        const double det = m[0] * (m[4] * m[8] - m[5] * m[7]) - m[1] * (m[3] * m[8] - m[5] * m[6]) +
+                           m[2] * (m[3] * m[7] - m[4] * m[6]);
+        if (det == 0.0) { free_ctx(c); return fail(SITB_E_INVALID, "sitb_create: singular cell"); }
+        double* o = c->cell.ci;
+        o[0] = (m[4] * m[8] - m[5] * m[7]) / det; o[1] = (m[2] * m[7] - m[1] * m[8]) / det; o[2] = (m[1] * m[5] - m[2] * m[4]) / det;
+        o[3] = (m[5] * m[6] - m[3] * m[8]) / det; o[4] = (m[0] * m[8] - m[2] * m[6]) / det; o[5] = (m[2] * m[3] - m[0] * m[5]) / det;
+        o[6] = (m[3] * m[7] - m[4] * m[6]) / det; o[7] = (m[1] * m[6] - m[0] * m[7]) / det; o[8] = (m[0] * m[4] - m[1] * m[3]) / det;
+    }
+    // centroid = sum over cell vectors of 0.5*cell (PBCCalculator.pyx:35): cell rows = cellmat columns
+    for (int k = 0; k < 3; ++k) {
+        // np.sum(0.5*cell, axis=0)[k] = ((0.5*cell[0][k] + 0.5*cell[1][k]) + 0.5*cell[2][k]); cell[i][k] = cellmat[k][i]
+        c->cell.cen[k] = (0.5 * c->cell.c[3 * k + 0] + 0.5 * c->cell.c[3 * k + 1]) + 0.5 * c->cell.c[3 * k + 2];
+    }
+    bool diag = true;
+    for (int i = 0; i < 3; ++i)
+        for (int j = 0; j < 3; ++j)
+            if (i != j && (c->cell.c[3 * i + j] != 0.0 || c->cell.ci[3 * i + j] != 0.0)) diag = false;
+    c->cell.diag = diag ? 1 : 0;
+    c->midpoint = d->cutoff_midpoint; c->steepness = d->cutoff_steepness;
+    c->cutoff = d->cutoff_round_to_zero > 0.0 ? d->cutoff_round_to_zero
+                                              : d->cutoff_midpoint + std::log((1.0 / 0.0001) - 1.0) / d->cutoff_steepness;
+    c->static_thr = d->static_movement_threshold;
+    c->dynamic = d->dynamic_lattice_mapping; c->relaxed = d->relaxed_lattice_checks;
+    const double log2e = 1.4426950408889634074;
+    const double steep_log2e = c->steepness * log2e;
+    c->bcoef = steep_log2e * c->midpoint;
+
+    const size_t LV = (size_t)c->L * c->V, LVp = (size_t)c->Lpad * c->V;
+#define CKC(call)                                                                          \
+    do {                                                                                   \
+        cudaError_t e2_ = (call);                                                          \
+        if (e2_ != cudaSuccess) {                                                          \
+            free_ctx(c);                                                                   \
+            return fail(SITB_E_CUDA, "%s failed: %s", #call, cudaGetErrorString(e2_));     \
+        }                                                                                  \
+    } while (0)
+    CKC(upload(&c->d_static_idx, d->host_static_idx, (size_t)c->S));
+    CKC(upload(&c->d_mobile_idx, d->host_mobile_idx, (size_t)c->M));
+    CKC(upload(&c->d_ideal, d->host_ideal_static, (size_t)c->S * 3));
+    CKC(upload(&c->d_centers, d->host_centers, (size_t)c->L * 3));
+    CKC(upload(&c->d_verts_in, d->host_verts, LV));
+    CKC(cudaMalloc((void**)&c->d_svd, sizeof(double) * LV));
+    CKC(cudaMalloc((void**)&c->d_verts, sizeof(uint16_t) * LVp));
+    CKC(cudaMalloc((void**)&c->d_qf, sizeof(float) * LVp));
+    CKC(cudaMalloc((void**)&c->d_q64, sizeof(double) * LVp));
+    CKC(cudaMalloc((void**)&c->d_acoef, sizeof(double) * LVp));
+    CKC(cudaMalloc((void**)&c->d_cid, sizeof(int) * (size_t)c->L));
+    CKC(cudaMalloc((void**)&c->d_cw, sizeof(float) * (size_t)c->L));
+    CKC(cudaMemset(c->d_cid, 0xFF, sizeof(int) * (size_t)c->L));
+    CKC(cudaMemset(c->d_cw, 0, sizeof(float) * (size_t)c->L));
+    CKC(cudaMalloc((void**)&c->d_status, sizeof(unsigned long long) * (2 + CNT_SLOTS)));
+    CKC(launch_tables(c->cell, c->d_centers, c->d_ideal, c->d_verts_in, c->L, c->V, c->Lpad, c->S, c->cutoff,
+                      steep_log2e, c->d_svd, c->d_verts, c->d_qf, c->d_q64, c->d_acoef, 0));
+    CKC(cudaDeviceSynchronize());
+#undef CKC
+    *out = c;
+    int rc = sitb_reset_status(c);
+    if (rc != SITB_OK) { free_ctx(c); *out = nullptr; return rc; }
+    return SITB_OK;
+}
+
+extern "C" void sitb_destroy(sitb_ctx* ctx) { free_ctx(ctx); }
+
+extern "C" int sitb_set_stream(sitb_ctx* c, void* s) {
+    if (!c) return fail(SITB_E_INVALID, "null context");
+    c->stream = (cudaStream_t)s;
+    return SITB_OK;
+}
+
+extern "C" int sitb_device_info(sitb_ctx* c, int32_t* n_sms, int32_t* major, int32_t* minor) {
+    if (!c) return fail(SITB_E_INVALID, "null context");
+    if (n_sms) *n_sms = c->n_sms;
+    if (major) *major = c->cc_major;
+    if (minor) *minor = c->cc_minor;
+    return SITB_OK;
+}
+
+extern "C" int sitb_get_tables(sitb_ctx* c, double* svd, double* q) {
+    if (!c) return fail(SITB_E_INVALID, "null context");
+    CK(cudaSetDevice(c->device));
+    const size_t LV = (size_t)c->L * c->V;
+    if (svd) CK(cudaMemcpy(svd, c->d_svd, sizeof(double) * LV, cudaMemcpyDeviceToHost));
+    if (q) {
+        std::vector<double> tmp((size_t)c->Lpad * c->V);
+        CK(cudaMemcpy(tmp.data(), c->d_q64, sizeof(double) * tmp.size(), cudaMemcpyDeviceToHost));
+        for (int k = 0; k < c->L; ++k)
+            for (int h = 0; h < c->V; ++h) q[(size_t)k * c->V + h] = tmp[(size_t)h * c->Lpad + k];
+    }
+    return SITB_OK;
+}
+
+extern "C" int sitb_upload_frames(sitb_ctx* c, const double* host, int64_t n, int64_t frame0) {
+    if (!c || !host || n <= 0) return fail(SITB_E_INVALID, "sitb_upload_frames: bad argument");
+    CK(cudaSetDevice(c->device));
+    const size_t bytes = sizeof(double) * (size_t)n * c->A * 3;
+    if (bytes > c->frames_capacity) {
+        cudaFree(c->d_frames_owned);
+        c->d_frames_owned = nullptr; c->frames_capacity = 0;
+        CK(cudaMalloc((void**)&c->d_frames_owned, bytes));
+        c->frames_capacity = bytes;
+    }
+    // pageable or pinned host memory both work; pinned (cudaHostRegister by the caller) is faster
+    CK(cudaMemcpyAsync(c->d_frames_owned, host, bytes, cudaMemcpyHostToDevice, c->stream));
+    c->d_frames = c->d_frames_owned; c->n_frames = n; c->frame0 = frame0;
+    return SITB_OK;
+}
+
+extern "C" int sitb_borrow_frames(sitb_ctx* c, const double* dev, int64_t n, int64_t frame0) {
+    if (!c || !dev || n <= 0) return fail(SITB_E_INVALID, "sitb_borrow_frames: bad argument");
+    c->d_frames = dev; c->n_frames = n; c->frame0 = frame0;
+    return SITB_OK;
+}
+
+extern "C" int sitb_reset_status(sitb_ctx* c) {
+    if (!c) return fail(SITB_E_INVALID, "null context");
+    CK(cudaSetDevice(c->device));
+    unsigned long long init[2 + CNT_SLOTS];
+    init[0] = init[1] = NO_ERROR_KEY;
+    for (int i = 0; i < CNT_SLOTS; ++i) init[2 + i] = 0ull;
+    CK(cudaMemcpyAsync(c->d_status, init, sizeof(init), cudaMemcpyHostToDevice, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    return SITB_OK;
+}
+
+extern "C" int sitb_get_status(sitb_ctx* c, sitb_status* out) {
+    if (!c || !out) return fail(SITB_E_INVALID, "sitb_get_status: null argument");
+    CK(cudaSetDevice(c->device));
+    unsigned long long h[2 + CNT_SLOTS];
+    CK(cudaMemcpyAsync(h, c->d_status, sizeof(h), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    memset(out, 0, sizeof(*out));
+    if (h[0] != NO_ERROR_KEY) {
+        out->error_code = (int32_t)((h[0] >> 20) & 0xF);
+        out->index = (int32_t)(h[0] & 0xFFFFF);
+        out->frame = (int64_t)(h[0] >> 24);
+    }
+    if (h[1] != NO_ERROR_KEY) {
+        out->zero_error = 1;
+        out->zero_index = (int32_t)(h[1] & 0xFFFFF);
+        out->zero_frame = (int64_t)(h[1] >> 24);
+    }
+    out->n_zero_rows = h[2 + CNT_ZERO_ROWS];
+    out->n_duplicate_nearest = h[2 + CNT_DUP_NEAREST];
+    out->n_list_overflow = h[2 + CNT_LIST_OVERFLOW];
+    out->nnz = h[2 + CNT_NNZ];
+    out->n_float_ties = h[2 + CNT_TIE_EXACT];
+    return SITB_OK;
+}
+
+static int base_params(sitb_ctx* c, int64_t begin, int64_t n, FillParams& p, const char* who) {
+    if (!c) return fail(SITB_E_INVALID, "%s: null context", who);
+    if (!c->d_frames) return fail(SITB_E_STATE, "%s: no frames resident (sitb_upload_frames / sitb_borrow_frames)", who);
+    if (begin < 0 || n < 0 || begin + n > c->n_frames)
+        return fail(SITB_E_INVALID, "%s: frame range [%lld, %lld) outside [0, %lld)", who, (long long)begin,
+                    (long long)(begin + n), (long long)c->n_frames);
+    if ((unsigned long long)(c->frame0 + c->n_frames) * (unsigned long long)c->M >= 0xFFFFFFFFull)
+        return fail(SITB_E_LIMIT, "%s: more than 2^32 landmark vectors", who);
+    memset(&p, 0, sizeof(p));
+    p.cell = c->cell;
+    p.frames = c->d_frames + (size_t)begin * c->A * 3;
+    p.frame_list = nullptr;
+    p.n_work = n;
+    p.frame0 = c->frame0 + begin;
+    p.A = c->A; p.S = c->S; p.M = c->M; p.L = c->L; p.V = c->V; p.Lpad = c->Lpad;
+    p.static_idx = c->d_static_idx; p.mobile_idx = c->d_mobile_idx; p.ideal = c->d_ideal;
+    p.verts = c->d_verts; p.qf = c->d_qf; p.q64 = c->d_q64; p.acoef = c->d_acoef;
+    p.bcoef = c->bcoef; p.static_thr = c->static_thr; p.dynamic = c->dynamic; p.relaxed = c->relaxed;
+    p.errkey = c->d_status; p.counters = c->d_status + 2;
+    p.cid = c->d_cid; p.cw = c->d_cw; p.n_clusters = c->n_clusters;
+    return SITB_OK;
+}
+
+extern "C" int sitb_fill_dense(sitb_ctx* c, int64_t begin, int64_t n, void* dev_out, int32_t is_f64) {
+    FillParams p;
+    int rc = base_params(c, begin, n, p, "sitb_fill_dense");
+    if (rc) return rc;
+    if (!dev_out) return fail(SITB_E_INVALID, "sitb_fill_dense: null output");
+    CK(cudaSetDevice(c->device));
+    p.dense_out = dev_out; p.dense_f64 = is_f64;
+    CK(launch_fill(p, MODE_DENSE, c->n_sms, c->stream));
+    return SITB_OK;
+}
+
+extern "C" int sitb_fill_dense_frames(sitb_ctx* c, const int64_t* dev_list, int64_t n, void* dev_out, int32_t is_f64) {
+    FillParams p;
+    int rc = base_params(c, 0, 0, p, "sitb_fill_dense_frames");
+    if (rc) return rc;
+    if (!dev_out || !dev_list) return fail(SITB_E_INVALID, "sitb_fill_dense_frames: null argument");
+    CK(cudaSetDevice(c->device));
+    p.frame_list = (const long long*)dev_list; p.n_work = n;
+    p.dense_out = dev_out; p.dense_f64 = is_f64;
+    p.errkey = nullptr; p.counters = nullptr;   // a re-evaluation of selected rows must not disturb the run's status
+    CK(launch_fill(p, MODE_DENSE, c->n_sms, c->stream));
+    return SITB_OK;
+}
+
+extern "C" int sitb_pass_stats(sitb_ctx* c, int64_t begin, int64_t n, uint64_t* dev_seen, double* dev_gram) {
+    FillParams p;
+    int rc = base_params(c, begin, n, p, "sitb_pass_stats");
+    if (rc) return rc;
+    if (!dev_seen || !dev_gram) return fail(SITB_E_INVALID, "sitb_pass_stats: null output");
+    CK(cudaSetDevice(c->device));
+    p.seen = (unsigned long long*)dev_seen; p.gram = dev_gram;
+    CK(launch_fill(p, MODE_STATS, c->n_sms, c->stream));
+    return SITB_OK;
+}
+
+extern "C" int sitb_set_centers(sitb_ctx* c, const int32_t* cid, const float* w, int32_t n_clusters) {
+    if (!c || !cid || !w) return fail(SITB_E_INVALID, "sitb_set_centers: null argument");
+    if (n_clusters < 0 || n_clusters > 32767) return fail(SITB_E_LIMIT, "sitb_set_centers: %d clusters (limit 32767)", n_clusters);
+    for (int k = 0; k < c->L; ++k)
+        if (cid[k] < -1 || cid[k] >= n_clusters) return fail(SITB_E_INVALID, "sitb_set_centers: cluster id %d of landmark %d out of range", cid[k], k);
+    CK(cudaSetDevice(c->device));
+    CK(cudaMemcpyAsync(c->d_cid, cid, sizeof(int) * (size_t)c->L, cudaMemcpyHostToDevice, c->stream));
+    CK(cudaMemcpyAsync(c->d_cw, w, sizeof(float) * (size_t)c->L, cudaMemcpyHostToDevice, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    c->n_clusters = n_clusters;
+    return SITB_OK;
+}
+
+extern "C" int sitb_pass_assign(sitb_ctx* c, int64_t begin, int64_t n, float thr, int64_t* labels, double* confs,
+                                uint64_t* counts, uint64_t* best, double* rep, double* rep_w, uint64_t* site_best) {
+    FillParams p;
+    int rc = base_params(c, begin, n, p, "sitb_pass_assign");
+    if (rc) return rc;
+    CK(cudaSetDevice(c->device));
+    p.assign_thr = thr;
+    p.labels = (long long*)labels; p.confs = confs; p.counts = (unsigned long long*)counts;
+    p.best = (unsigned long long*)best; p.rep = rep; p.rep_w = rep_w; p.site_best = (unsigned long long*)site_best;
+    CK(launch_fill(p, MODE_ASSIGN, c->n_sms, c->stream));
+    return SITB_OK;
+}
+
+extern "C" int sitb_fill_landmark_vectors_host(sitb_ctx* c, const double* host_frames, int64_t n_frames,
+                                               double* host_lv, sitb_status* status) {
+    if (!c || !host_frames || !host_lv || n_frames <= 0)
+        return fail(SITB_E_INVALID, "sitb_fill_landmark_vectors_host: bad argument");
+    CK(cudaSetDevice(c->device));
+    int rc = sitb_reset_status(c);
+    if (rc) return rc;
+    // stream the trajectory through the device in chunks: bounded device footprint for any n_frames
+    const size_t row_bytes = sizeof(double) * (size_t)c->M * c->L;           // per frame, output
+    const size_t in_bytes = sizeof(double) * (size_t)c->A * 3;               // per frame, input
+    long long chunk = (long long)((512ull << 20) / (row_bytes + in_bytes));
+    if (chunk < 1) chunk = 1;
+    if (chunk > n_frames) chunk = n_frames;
+    double* d_in = nullptr;
+    double* d_out = nullptr;
+    CK(cudaMalloc((void**)&d_in, in_bytes * (size_t)chunk));
+    cudaError_t e = cudaMalloc((void**)&d_out, row_bytes * (size_t)chunk);
+    if (e != cudaSuccess) { cudaFree(d_in); return fail(SITB_E_CUDA, "cudaMalloc: %s", cudaGetErrorString(e)); }
+    const double* saved_frames = c->d_frames; const long long saved_n = c->n_frames, saved_f0 = c->frame0;
+    rc = SITB_OK;
+    for (long long f0 = 0; f0 < n_frames && rc == SITB_OK; f0 += chunk) {
+        const long long n = (n_frames - f0 < chunk) ? (n_frames - f0) : chunk;
+        e = cudaMemcpyAsync(d_in, host_frames + (size_t)f0 * c->A * 3, in_bytes * (size_t)n, cudaMemcpyHostToDevice, c->stream);
+        if (e != cudaSuccess) { rc = fail(SITB_E_CUDA, "H2D: %s", cudaGetErrorString(e)); break; }
+        c->d_frames = d_in; c->n_frames = n; c->frame0 = f0;
+        rc = sitb_fill_dense(c, 0, n, d_out, 1);
+        if (rc) break;
+        e = cudaMemcpyAsync(host_lv + (size_t)f0 * c->M * c->L, d_out, row_bytes * (size_t)n, cudaMemcpyDeviceToHost, c->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+        if (e != cudaSuccess) { rc = fail(SITB_E_CUDA, "D2H: %s", cudaGetErrorString(e)); break; }
+    }
+    c->d_frames = saved_frames; c->n_frames = saved_n; c->frame0 = saved_f0;
+    cudaFree(d_in); cudaFree(d_out);
+    if (rc) return rc;
+    if (status) return sitb_get_status(c, status);
+    return SITB_OK;
+}

@@ -1,0 +1,252 @@
+"""Host-side driver of the device passes (thin: argument marshalling only).
+
+``LandmarkEngine`` owns one native context (``include/sitator_b200.h``) on one GPU: the landmark
+basis tables and a resident shard of frames.  Device buffers that cross the C ABI are torch CUDA
+tensors (torch is plumbing here: allocation, streams, and -- in ``landmark/`` -- the NCCL
+collectives); all arithmetic happens in ``csrc/``.
+"""
+import ctypes as C
+import math
+
+import numpy as np
+
+from . import _native
+
+
+def _torch():
+    import torch
+    return torch
+
+
+class EngineStatus(object):
+    """Python view of ``sitb_status``."""
+
+    def __init__(self, s):
+        self.error_code = int(s.error_code)
+        self.index = int(s.index)
+        self.frame = int(s.frame)
+        self.zero_error = bool(s.zero_error)
+        self.zero_index = int(s.zero_index)
+        self.zero_frame = int(s.zero_frame)
+        self.n_zero_rows = int(s.n_zero_rows)
+        self.n_duplicate_nearest = int(s.n_duplicate_nearest)
+        self.n_list_overflow = int(s.n_list_overflow)
+        self.nnz = int(s.nnz)
+        self.n_float_ties = int(s.n_float_ties)
+
+    def first_error(self, check_for_zeros):
+        """(code, frame, index) of the first error in the reference's iteration order, or None."""
+        cands = []
+        if self.error_code:
+            cands.append((self.frame, self.error_code, self.index))
+        if check_for_zeros and self.zero_error:
+            cands.append((self.zero_frame, 3, self.zero_index))
+        if not cands:
+            return None
+        frame, code, index = min(cands)
+        return code, frame, index
+
+
+def vertex_table(vertices):
+    """-1 padded (L, Vmax) int32 table of the landmark vertex lists (LandmarkAnalysis.py:194-195)."""
+    vmax = max(len(v) for v in vertices)
+    out = np.full((len(vertices), vmax), -1, dtype=np.int32)
+    for i, v in enumerate(vertices):
+        v = list(v)
+        out[i, :len(v)] = v
+    return out
+
+
+class LandmarkEngine(object):
+    def __init__(self, cell, static_idx, mobile_idx, n_atoms, ideal_static, centers, vertices,
+                 cutoff_midpoint=1.5, cutoff_steepness=30.0, static_movement_threshold=1.0,
+                 dynamic_lattice_mapping=False, relaxed_lattice_checks=False, device=None):
+        torch = _torch()
+        if not torch.cuda.is_available():
+            raise RuntimeError("sitator_b200 needs a CUDA device (B200, sm_100a); there is no CPU path")
+        self._lib = _native.load()
+        self.device = torch.device("cuda", torch.cuda.current_device() if device is None else int(device))
+        cell = np.ascontiguousarray(cell, dtype=np.float64).reshape(3, 3)
+        # PBCCalculator.__init__ (PBCCalculator.pyx:27-35): cellmat = cell^T, LAPACK inverse
+        self.cellmat = np.ascontiguousarray(cell.T)
+        self.cellmat_inv = np.ascontiguousarray(np.linalg.inv(self.cellmat))
+        self.cell_centroid = np.sum(0.5 * cell, axis=0)
+        self.static_idx = np.ascontiguousarray(static_idx, dtype=np.int32)
+        self.mobile_idx = np.ascontiguousarray(mobile_idx, dtype=np.int32)
+        self.ideal_static = np.ascontiguousarray(ideal_static, dtype=np.float64).reshape(-1, 3)
+        self.centers = np.ascontiguousarray(centers, dtype=np.float64).reshape(-1, 3)
+        self.verts = np.ascontiguousarray(vertex_table(vertices))
+        self.n_atoms = int(n_atoms)
+        self.S, self.M, self.L, self.V = len(self.static_idx), len(self.mobile_idx), len(self.centers), self.verts.shape[1]
+        if len(self.ideal_static) != self.S:
+            raise ValueError("ideal_static has %d rows for %d static atoms" % (len(self.ideal_static), self.S))
+        if len(vertices) != self.L:
+            raise ValueError("vertices/centers length mismatch")
+        # helpers.pyx:41-43,127-131 with libm log, exactly as the reference evaluates it
+        self.cutoff_round_to_zero = cutoff_midpoint + math.log((1 / 0.0001) - 1.) / cutoff_steepness
+        d = _native.NetworkDesc()
+        d.n_atoms, d.n_static, d.n_mobile, d.n_landmarks, d.max_verts = self.n_atoms, self.S, self.M, self.L, self.V
+        d.host_cellmat = self.cellmat.ctypes.data
+        d.host_cellmat_inv = self.cellmat_inv.ctypes.data
+        d.host_static_idx = self.static_idx.ctypes.data
+        d.host_mobile_idx = self.mobile_idx.ctypes.data
+        d.host_ideal_static = self.ideal_static.ctypes.data
+        d.host_centers = self.centers.ctypes.data
+        d.host_verts = self.verts.ctypes.data
+        d.cutoff_midpoint = float(cutoff_midpoint)
+        d.cutoff_steepness = float(cutoff_steepness)
+        d.cutoff_round_to_zero = float(self.cutoff_round_to_zero)
+        d.static_movement_threshold = float(static_movement_threshold)
+        d.dynamic_lattice_mapping = int(bool(dynamic_lattice_mapping))
+        d.relaxed_lattice_checks = int(bool(relaxed_lattice_checks))
+        self._ctx = C.c_void_p()
+        _native.check(self._lib.sitb_create(C.byref(d), self.device.index, C.byref(self._ctx)))
+        self._frames_keepalive = None
+        self.n_frames = 0
+        self.frame0 = 0
+        self.n_clusters = 0
+        n_sms, maj, mnr = C.c_int32(), C.c_int32(), C.c_int32()
+        _native.check(self._lib.sitb_device_info(self._ctx, C.byref(n_sms), C.byref(maj), C.byref(mnr)))
+        self.n_sms, self.compute_capability = n_sms.value, (maj.value, mnr.value)
+        self.use_current_stream()
+
+    @classmethod
+    def from_site_network(cls, sn, **kw):
+        cell = np.asarray(sn.structure.cell)
+        static_idx = np.where(sn.static_mask)[0]
+        mobile_idx = np.where(sn.mobile_mask)[0]
+        return cls(cell, static_idx, mobile_idx, sn.n_total, sn.static_structure.get_positions(),
+                   np.asarray(sn.centers), sn.vertices, **kw)
+
+    def close(self):
+        if getattr(self, "_ctx", None) is not None and self._ctx.value:
+            self._lib.sitb_destroy(self._ctx)
+            self._ctx = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- plumbing -------------------------------------------------------------------------
+    def use_current_stream(self):
+        torch = _torch()
+        s = torch.cuda.current_stream(self.device).cuda_stream
+        _native.check(self._lib.sitb_set_stream(self._ctx, C.c_void_p(s)))
+
+    def _empty(self, shape, dtype):
+        return _torch().empty(shape, dtype=dtype, device=self.device)
+
+    def _zeros(self, shape, dtype):
+        return _torch().zeros(shape, dtype=dtype, device=self.device)
+
+    @staticmethod
+    def _ptr(t):
+        return C.c_void_p(0 if t is None else t.data_ptr())
+
+    def tables(self):
+        svd = np.empty((self.L, self.V), dtype=np.float64)
+        q = np.empty((self.L, self.V), dtype=np.float64)
+        _native.check(self._lib.sitb_get_tables(self._ctx, svd.ctypes.data, q.ctypes.data))
+        return svd, q
+
+    def set_frames(self, frames, frame0=0):
+        """Make a shard of frames resident.  numpy float64 (F, A, 3) is copied to the device once;
+        a torch CUDA float64 tensor is borrowed in place."""
+        torch = _torch()
+        if isinstance(frames, torch.Tensor):
+            if frames.device != self.device or frames.dtype != torch.float64 or not frames.is_contiguous():
+                raise ValueError("device frames must be a contiguous float64 tensor on %s" % self.device)
+            if frames.shape[1:] != (self.n_atoms, 3):
+                raise ValueError("Wrong shape %s for frames." % (tuple(frames.shape),))
+            _native.check(self._lib.sitb_borrow_frames(self._ctx, self._ptr(frames), frames.shape[0], frame0))
+            self._frames_keepalive = frames
+        else:
+            frames = np.asarray(frames)
+            if frames.dtype != np.float64:
+                raise ValueError("frames must be float64 (the reference rejects other dtypes too)")
+            if frames.shape[1:] != (self.n_atoms, 3):
+                raise ValueError("Wrong shape %s for frames." % (frames.shape,))
+            frames = np.ascontiguousarray(frames)
+            _native.check(self._lib.sitb_upload_frames(self._ctx, frames.ctypes.data, frames.shape[0], frame0))
+            torch.cuda.current_stream(self.device).synchronize()
+            self._frames_keepalive = None
+        self.n_frames = int(frames.shape[0])
+        self.frame0 = int(frame0)
+
+    def reset_status(self):
+        _native.check(self._lib.sitb_reset_status(self._ctx))
+
+    def status(self):
+        s = _native.Status()
+        _native.check(self._lib.sitb_get_status(self._ctx, C.byref(s)))
+        return EngineStatus(s)
+
+    # ---- passes ---------------------------------------------------------------------------
+    def fill_dense(self, begin=0, n=None, dtype=None, out=None):
+        torch = _torch()
+        n = self.n_frames - begin if n is None else n
+        dtype = torch.float32 if dtype is None else dtype
+        if out is None:
+            out = self._empty((n * self.M, self.L), dtype)
+        _native.check(self._lib.sitb_fill_dense(self._ctx, begin, n, self._ptr(out), int(dtype == torch.float64)))
+        return out
+
+    def fill_frames(self, frame_indices, dtype=None):
+        """Landmark vectors of selected resident frames: (len(frame_indices)*M, L)."""
+        torch = _torch()
+        dtype = torch.float32 if dtype is None else dtype
+        idx = torch.as_tensor(np.asarray(frame_indices, dtype=np.int64), device=self.device)
+        out = self._empty((len(idx) * self.M, self.L), dtype)
+        _native.check(self._lib.sitb_fill_dense_frames(self._ctx, self._ptr(idx), len(idx), self._ptr(out),
+                                                       int(dtype == torch.float64)))
+        return out
+
+    def pass_stats(self, begin=0, n=None, seen=None, gram=None):
+        torch = _torch()
+        n = self.n_frames - begin if n is None else n
+        if seen is None:
+            seen = self._zeros((self.L,), torch.int64)
+        if gram is None:
+            gram = self._zeros((self.L, self.L), torch.float64)
+        _native.check(self._lib.sitb_pass_stats(self._ctx, begin, n, self._ptr(seen), self._ptr(gram)))
+        return seen, gram
+
+    def set_centers(self, cluster_of_landmark, weight, n_clusters):
+        cid = np.ascontiguousarray(cluster_of_landmark, dtype=np.int32)
+        w = np.ascontiguousarray(weight, dtype=np.float32)
+        assert cid.shape == (self.L,) and w.shape == (self.L,)
+        _native.check(self._lib.sitb_set_centers(self._ctx, cid.ctypes.data, w.ctypes.data, int(n_clusters)))
+        self.n_clusters = int(n_clusters)
+
+    def pass_assign(self, threshold, begin=0, n=None, labels=None, confs=None, counts=None, best=None,
+                    rep=None, rep_w=None, site_best=None):
+        n = self.n_frames - begin if n is None else n
+        _native.check(self._lib.sitb_pass_assign(
+            self._ctx, begin, n, float(threshold), self._ptr(labels), self._ptr(confs), self._ptr(counts),
+            self._ptr(best), self._ptr(rep), self._ptr(rep_w), self._ptr(site_best)))
+
+    def fill_landmark_vectors_host(self, frames):
+        """Host in, host out: the drop-in for ``helpers._fill_landmark_vectors`` (helpers.pyx:12)."""
+        frames = np.ascontiguousarray(frames, dtype=np.float64)
+        if frames.shape[1:] != (self.n_atoms, 3):
+            raise ValueError("Wrong shape %s for frames." % (frames.shape,))
+        out = np.empty((frames.shape[0] * self.M, self.L), dtype=np.float64)
+        s = _native.Status()
+        _native.check(self._lib.sitb_fill_landmark_vectors_host(
+            self._ctx, frames.ctypes.data, frames.shape[0], out.ctypes.data, C.byref(s)))
+        return out, EngineStatus(s)
+
+
+def unpack_key(keys):
+    """Split the (value bits << 32 | ~row) keys written by the assign pass: (float32 values, int64 rows)."""
+    keys = np.asarray(keys, dtype=np.uint64)
+    vals = (keys >> np.uint64(32)).astype(np.uint32).view(np.float32)
+    rows = (np.uint64(0xFFFFFFFF) - (keys & np.uint64(0xFFFFFFFF))).astype(np.int64)
+    return vals, rows
+
+
+def initial_key():
+    """Key of (value 0.0, row 0): what np.argmax gives when every |dot| is zero."""
+    return np.uint64(0xFFFFFFFF)

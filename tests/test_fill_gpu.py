@@ -1,0 +1,163 @@
+"""GPU parity: K1 (wrap + lattice check + landmark fill + assign) against the NumPy oracle."""
+import numpy as np
+import pytest
+
+from sitator_b200 import synthetic as syn
+from tests import _util as U
+
+pytestmark = pytest.mark.gpu
+
+
+def _oracle_lv(system, frames, **kw):
+    from oracle import landmark_oracle as orc
+    cnt = {}
+    lv, nzero, wrapped = orc.fill_landmark_vectors(
+        system.cell, system.static_pos, system.static_idx, system.mobile_idx, system.lm_centers,
+        system.lm_vertices, frames, check_for_zeros=False, counters=cnt, **kw)
+    return lv, nzero, cnt
+
+
+def _compare_lv(got, want):
+    got = np.asarray(got, dtype=np.float64)
+    assert got.shape == want.shape
+    assert np.array_equal(got != 0, want != 0), "support differs in %d components" % int(np.sum((got != 0) != (want != 0)))
+    nz = want != 0
+    rel = np.abs(got[nz] - want[nz]) / want[nz]
+    assert rel.max() < U.LV_RTOL, "max rel err %.3g" % rel.max()
+    return float(rel.max())
+
+
+@pytest.mark.parametrize("name,n_frames", [("toy_bcc", 300), ("llzo", 40), ("llzo_v4", 40)])
+def test_tables_and_dense_fill_match_oracle(name, n_frames):
+    import torch
+    from oracle import landmark_oracle as orc
+    system, cfg = syn.make_config(name)
+    frames = system.trajectory(n_frames)
+    eng = U.engine_for(system)
+    # Step 1 tables: bit-exact (LandmarkAnalysis.py:194-202)
+    pbc = orc.PBC(system.cell)
+    verts_np, svd = orc.vertex_tables(pbc, system.lm_centers, system.lm_vertices, system.static_pos)
+    svd_gpu, q_gpu = eng.tables()
+    assert np.array_equal(np.isnan(svd), np.isnan(svd_gpu))
+    assert np.array_equal(svd[~np.isnan(svd)], svd_gpu[~np.isnan(svd)])
+    # the squared cut-off is the exact boundary of  sqrt(q)/svd > cutoff
+    thr = orc.cutoff_round_to_zero_point(1.5, 30.0)
+    ok = ~np.isnan(svd)
+    q = q_gpu[ok]
+    assert np.all(np.sqrt(q) / svd[ok] <= thr)
+    assert np.all(np.sqrt(np.nextafter(q, np.inf)) / svd[ok] > thr)
+
+    want, nzero, cnt = _oracle_lv(system, frames)
+    eng.set_frames(frames)
+    eng.reset_status()
+    got32 = eng.fill_dense(dtype=torch.float32).cpu().numpy()
+    got64 = eng.fill_dense(dtype=torch.float64).cpu().numpy()
+    st = eng.status()
+    assert st.error_code == 0
+    assert st.n_list_overflow == 0
+    assert st.n_zero_rows == 2 * nzero          # two passes
+    assert st.nnz == 2 * cnt["nnz"]
+    _compare_lv(got32, want)
+    _compare_lv(got64, want)
+    # host-buffer drop-in entry
+    got_host, st2 = eng.fill_landmark_vectors_host(frames)
+    assert np.array_equal(got_host, got64)
+    assert st2.n_zero_rows == nzero
+    # selected frames
+    sel = [n_frames - 1, 0, n_frames // 2]
+    rows = eng.fill_frames(sel).cpu().numpy()
+    M = system.n_mobile
+    for i, f in enumerate(sel):
+        assert np.array_equal(rows[i * M:(i + 1) * M], got32[f * M:(f + 1) * M])
+
+
+def test_triclinic_cell_general_wrap_path():
+    import torch
+    from oracle import landmark_oracle as orc
+    from sitator_b200.engine import LandmarkEngine
+    t = U.triclinic_system()
+    eng = LandmarkEngine(t["cell"], t["static_idx"], t["mobile_idx"], t["n_atoms"], t["static"], t["centers"], t["verts"])
+    want, nzero, _ = orc.fill_landmark_vectors(t["cell"], t["static"], t["static_idx"], t["mobile_idx"], t["centers"],
+                                               t["verts"], t["frames"], check_for_zeros=False)
+    eng.set_frames(t["frames"])
+    got = eng.fill_dense(dtype=torch.float64).cpu().numpy()
+    assert np.count_nonzero(want) > 50
+    _compare_lv(got, want)
+
+
+def test_dynamic_lattice_mapping_with_swapped_statics():
+    import torch
+    system, cfg = syn.make_config("lgps_dynamic")
+    frames = system.trajectory(30, swap_statics_at=11)
+    want, nzero, cnt = _oracle_lv(system, frames, dynamic_lattice_mapping=True)
+    eng = U.engine_for(system, dynamic_lattice_mapping=True)
+    eng.set_frames(frames)
+    eng.reset_status()
+    got = eng.fill_dense(dtype=torch.float64).cpu().numpy()
+    st = eng.status()
+    assert st.error_code == 0
+    assert st.n_duplicate_nearest == cnt["n_duplicate_nearest"]
+    _compare_lv(got, want)
+    # without the dynamic map the swapped pair breaks the 1 A movement limit at frame 11 (helpers.pyx:76-80)
+    eng2 = U.engine_for(system, dynamic_lattice_mapping=False)
+    eng2.set_frames(frames)
+    eng2.reset_status()
+    eng2.fill_dense()
+    st2 = eng2.status()
+    assert st2.error_code == 1 and st2.frame == 11
+
+
+def test_errors_first_in_reference_order():
+    import torch
+    system, cfg = syn.make_config("toy_bcc")
+    frames = system.trajectory(60)
+    # push static atom 7 away in frames 20 and 9; mobile 3 far from everything? (zero vectors occur naturally)
+    frames[20, system.static_idx[7]] += 1.5
+    frames[9, system.static_idx[5]] += 1.3
+    frames[9, system.static_idx[2]] -= 1.3
+    eng = U.engine_for(system)
+    eng.set_frames(frames, frame0=1000)
+    eng.reset_status()
+    eng.fill_dense()
+    st = eng.status()
+    assert (st.error_code, st.frame, st.index) == (1, 1009, 2)
+    assert st.first_error(check_for_zeros=False) == (1, 1009, 2)
+
+
+def test_assign_matches_oracle_predict():
+    import torch
+    from oracle import landmark_oracle as orc
+    system, cfg = syn.make_config("toy_bcc")
+    frames = system.trajectory(300)
+    res = orc.run_landmark_analysis(system.cell, system.static_pos, system.static_idx, system.mobile_idx,
+                                    system.lm_centers, system.lm_vertices, frames, check_for_zero_landmarks=False)
+    centers = res["_centers"]                      # (C, L) rows with disjoint supports
+    C, L = centers.shape
+    cid = np.full(L, -1, dtype=np.int32)
+    w = np.zeros(L, dtype=np.float32)
+    for c in range(C):
+        nz = np.nonzero(centers[c])[0]
+        assert np.all(cid[nz] == -1)
+        cid[nz] = c
+        w[nz] = centers[c, nz]
+    eng = U.engine_for(system)
+    eng.set_frames(frames)
+    eng.set_centers(cid, w, C)
+    N = frames.shape[0] * system.n_mobile
+    labels = torch.empty(N, dtype=torch.int64, device="cuda")
+    confs = torch.empty(N, dtype=torch.float64, device="cuda")
+    counts = torch.zeros(C, dtype=torch.int64, device="cuda")
+    eng.pass_assign(0.7, labels=labels, confs=confs, counts=counts)
+    labels, confs, counts = labels.cpu().numpy(), confs.cpu().numpy(), counts.cpu().numpy()
+    want_l, want_c = res["cluster-labels"], res["cluster-confs"]
+    diff = labels != want_l
+    # a label may differ only where the decision is within TIE_TOL (reported, not hidden)
+    lv = res["landmark_vectors"]
+    dots = np.abs(lv @ centers.T)
+    srt = np.sort(dots, axis=1)
+    margin = srt[:, -1] - srt[:, -2]
+    near = (margin < U.TIE_TOL) | (np.abs(srt[:, -1] - 0.7) < U.TIE_TOL)
+    assert not np.any(diff & ~near), "%d labels differ outside the tie tolerance" % int(np.sum(diff & ~near))
+    same = ~diff
+    assert np.max(np.abs(confs[same] - want_c[same])) < U.CONF_ATOL
+    assert np.array_equal(counts, np.bincount(labels[labels >= 0], minlength=C))
