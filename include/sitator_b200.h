@@ -73,9 +73,9 @@ typedef struct sitb_status {
     int64_t zero_frame;
     uint64_t n_zero_rows;        /* self.n_all_zero_lvecs (helpers.pyx:124) */
     uint64_t n_duplicate_nearest;/* count of the warning at helpers.pyx:69-71 */
-    uint64_t n_list_overflow;    /* rows with more than 256 non-zero components (must be 0) */
+    uint64_t n_list_overflow;    /* rows with more than 128 non-zero components (must be 0) */
     uint64_t nnz;                /* non-zero landmark-vector components produced */
-    uint64_t n_float_ties;       /* cut-off tests that needed the double compare */
+    uint64_t n_screen_rejects;       /* landmarks that passed the float pre-screen but failed the exact double test */
 } sitb_status;
 
 const char* sitb_last_error(void);

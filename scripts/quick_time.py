@@ -12,11 +12,16 @@ frames = system.trajectory(F)
 eng = U.engine_for(system, dynamic_lattice_mapping=cfg["dynamic"])
 eng.set_frames(frames)
 L, M = system.n_landmarks, system.n_mobile
-cid = (np.arange(L) % 64).astype(np.int32); w = np.ones(L, dtype=np.float32)
-eng.set_centers(cid, w, 64)
+# realistic centres: a landmark belongs to the nearest true site if its centre is within 2 A of it
+d = system.lm_centers[:, None, :] - system.site_pos[None, :, :]
+d -= system.lengths * np.round(d / system.lengths)
+dist = np.sqrt((d ** 2).sum(-1))
+cid = np.where(dist.min(1) < 2.0, dist.argmin(1), -1).astype(np.int32); w = np.ones(L, dtype=np.float32)
+NC = len(system.site_pos)
+eng.set_centers(cid, w, NC)
 N = F * M
 labels = torch.empty(N, dtype=torch.int64, device="cuda"); confs = torch.empty(N, dtype=torch.float64, device="cuda")
-counts = torch.zeros(64, dtype=torch.int64, device="cuda")
+counts = torch.zeros(NC, dtype=torch.int64, device="cuda")
 def timeit(fn, reps=5):
     fn(); torch.cuda.synchronize()
     ts = []

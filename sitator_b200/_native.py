@@ -35,7 +35,7 @@ class Status(C.Structure):
         ("error_code", C.c_int32), ("index", C.c_int32), ("frame", C.c_int64),
         ("zero_error", C.c_int32), ("zero_index", C.c_int32), ("zero_frame", C.c_int64),
         ("n_zero_rows", C.c_uint64), ("n_duplicate_nearest", C.c_uint64),
-        ("n_list_overflow", C.c_uint64), ("nnz", C.c_uint64), ("n_float_ties", C.c_uint64),
+        ("n_list_overflow", C.c_uint64), ("nnz", C.c_uint64), ("n_screen_rejects", C.c_uint64),
     ]
 
 

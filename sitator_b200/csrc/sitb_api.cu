@@ -11,8 +11,9 @@
 
 namespace sitb {
 cudaError_t launch_tables(const Cell& cell, const double* centers, const double* ideal, const int* verts_in, int L,
-                          int V, int Lpad, int S, double cutoff, double steep_log2e, double* svd_out,
-                          uint16_t* verts, float* qf, double* q64, double* acoef, cudaStream_t stream);
+                          int V, int S, double cutoff, double* svd_out, double* q_out, cudaStream_t stream);
+void build_landmark_tables(const Cell& cell, int L, int V, int Lpad, int NB, int S, double steep_log2e,
+                           const int* verts_in, const double* svd, const double* q, HostTables& out);
 }
 
 using namespace sitb;
@@ -37,7 +38,7 @@ static int fail(int code, const char* fmt, ...) {
 struct sitb_ctx {
     int device = 0;
     int n_sms = 0, cc_major = 0, cc_minor = 0;
-    int A = 0, S = 0, M = 0, L = 0, V = 0, Lpad = 0;
+    int A = 0, S = 0, M = 0, L = 0, V = 0, Lpad = 0, NB = 1;
     Cell cell;
     double midpoint = 0, steepness = 0, cutoff = 0, static_thr = 0, bcoef = 0;
     int dynamic = 0, relaxed = 0;
@@ -49,10 +50,17 @@ struct sitb_ctx {
     double* d_centers = nullptr;
     int* d_verts_in = nullptr;
     double* d_svd = nullptr;
-    uint16_t* d_verts = nullptr;
-    float* d_qf = nullptr;
+    double* d_qorig = nullptr;
+    uint16_t* d_orig_of = nullptr;
+    std::vector<int> internal_of;     // caller's landmark index -> internal
+    std::vector<double> h_svd, h_qorig;
+    uint16_t* d_v0 = nullptr;
+    float* d_b0 = nullptr;
+    ushort4* d_va = nullptr;
+    float4* d_ba = nullptr;
     double* d_q64 = nullptr;
     double* d_acoef = nullptr;
+    uint8_t* d_nverts = nullptr;
     // centres
     int* d_cid = nullptr;
     float* d_cw = nullptr;
@@ -70,8 +78,8 @@ static void free_ctx(sitb_ctx* c) {
     if (!c) return;
     cudaSetDevice(c->device);
     cudaFree(c->d_static_idx); cudaFree(c->d_mobile_idx); cudaFree(c->d_ideal); cudaFree(c->d_centers);
-    cudaFree(c->d_verts_in); cudaFree(c->d_svd); cudaFree(c->d_verts); cudaFree(c->d_qf); cudaFree(c->d_q64);
-    cudaFree(c->d_acoef); cudaFree(c->d_cid); cudaFree(c->d_cw); cudaFree(c->d_frames_owned); cudaFree(c->d_status);
+    cudaFree(c->d_verts_in); cudaFree(c->d_svd); cudaFree(c->d_qorig); cudaFree(c->d_orig_of); cudaFree(c->d_v0); cudaFree(c->d_b0); cudaFree(c->d_va); cudaFree(c->d_ba);
+    cudaFree(c->d_q64); cudaFree(c->d_acoef); cudaFree(c->d_nverts); cudaFree(c->d_cid); cudaFree(c->d_cw); cudaFree(c->d_frames_owned); cudaFree(c->d_status);
     delete c;
 }
 
@@ -125,7 +133,8 @@ extern "C" int sitb_create(const sitb_network_desc* d, int device, sitb_ctx** ou
     if (e != cudaSuccess) { free_ctx(c); return fail(SITB_E_CUDA, "cudaGetDeviceProperties: %s", cudaGetErrorString(e)); }
     c->n_sms = prop.multiProcessorCount; c->cc_major = prop.major; c->cc_minor = prop.minor;
     c->A = d->n_atoms; c->S = d->n_static; c->M = d->n_mobile; c->L = d->n_landmarks; c->V = d->max_verts;
-    c->Lpad = (c->L + 31) & ~31;
+    c->Lpad = (c->L + 255) & ~255;   // K1 screens landmarks in unrolled groups of 8 x 32
+    c->NB = (c->V + 3) / 4;
     // cell
     for (int i = 0; i < 9; ++i) c->cell.c[i] = d->host_cellmat[i];
     if (d->host_cellmat_inv) {
@@ -159,7 +168,7 @@ extern "C" int sitb_create(const sitb_network_desc* d, int device, sitb_ctx** ou
     const double steep_log2e = c->steepness * log2e;
     c->bcoef = steep_log2e * c->midpoint;
 
-    const size_t LV = (size_t)c->L * c->V, LVp = (size_t)c->Lpad * c->V;
+    const size_t LV = (size_t)c->L * c->V;
 #define CKC(call)                                                                          \
     do {                                                                                   \
         cudaError_t e2_ = (call);                                                          \
@@ -174,17 +183,31 @@ extern "C" int sitb_create(const sitb_network_desc* d, int device, sitb_ctx** ou
     CKC(upload(&c->d_centers, d->host_centers, (size_t)c->L * 3));
     CKC(upload(&c->d_verts_in, d->host_verts, LV));
     CKC(cudaMalloc((void**)&c->d_svd, sizeof(double) * LV));
-    CKC(cudaMalloc((void**)&c->d_verts, sizeof(uint16_t) * LVp));
-    CKC(cudaMalloc((void**)&c->d_qf, sizeof(float) * LVp));
-    CKC(cudaMalloc((void**)&c->d_q64, sizeof(double) * LVp));
-    CKC(cudaMalloc((void**)&c->d_acoef, sizeof(double) * LVp));
+    CKC(cudaMalloc((void**)&c->d_qorig, sizeof(double) * LV));
     CKC(cudaMalloc((void**)&c->d_cid, sizeof(int) * (size_t)c->L));
     CKC(cudaMalloc((void**)&c->d_cw, sizeof(float) * (size_t)c->L));
     CKC(cudaMemset(c->d_cid, 0xFF, sizeof(int) * (size_t)c->L));
     CKC(cudaMemset(c->d_cw, 0, sizeof(float) * (size_t)c->L));
     CKC(cudaMalloc((void**)&c->d_status, sizeof(unsigned long long) * (2 + CNT_SLOTS)));
-    CKC(launch_tables(c->cell, c->d_centers, c->d_ideal, c->d_verts_in, c->L, c->V, c->Lpad, c->S, c->cutoff,
-                      steep_log2e, c->d_svd, c->d_verts, c->d_qf, c->d_q64, c->d_acoef, 0));
+    CKC(launch_tables(c->cell, c->d_centers, c->d_ideal, c->d_verts_in, c->L, c->V, c->S, c->cutoff, c->d_svd,
+                      c->d_qorig, 0));
+    c->h_svd.resize(LV); c->h_qorig.resize(LV);
+    CKC(cudaMemcpy(c->h_svd.data(), c->d_svd, sizeof(double) * LV, cudaMemcpyDeviceToHost));
+    CKC(cudaMemcpy(c->h_qorig.data(), c->d_qorig, sizeof(double) * LV, cudaMemcpyDeviceToHost));
+    {
+        HostTables ht;
+        build_landmark_tables(c->cell, c->L, c->V, c->Lpad, c->NB, c->S, steep_log2e, d->host_verts,
+                              c->h_svd.data(), c->h_qorig.data(), ht);
+        c->internal_of = ht.internal_of;
+        CKC(upload(&c->d_v0, ht.v0.data(), ht.v0.size()));
+        CKC(upload(&c->d_b0, ht.b0.data(), ht.b0.size()));
+        CKC(upload(&c->d_va, ht.va.data(), ht.va.size()));
+        CKC(upload(&c->d_ba, ht.ba.data(), ht.ba.size()));
+        CKC(upload(&c->d_q64, ht.q64.data(), ht.q64.size()));
+        CKC(upload(&c->d_acoef, ht.acoef.data(), ht.acoef.size()));
+        CKC(upload(&c->d_nverts, ht.nverts.data(), ht.nverts.size()));
+        CKC(upload(&c->d_orig_of, ht.orig_of.data(), ht.orig_of.size()));
+    }
     CKC(cudaDeviceSynchronize());
 #undef CKC
     *out = c;
@@ -213,13 +236,8 @@ extern "C" int sitb_get_tables(sitb_ctx* c, double* svd, double* q) {
     if (!c) return fail(SITB_E_INVALID, "null context");
     CK(cudaSetDevice(c->device));
     const size_t LV = (size_t)c->L * c->V;
-    if (svd) CK(cudaMemcpy(svd, c->d_svd, sizeof(double) * LV, cudaMemcpyDeviceToHost));
-    if (q) {
-        std::vector<double> tmp((size_t)c->Lpad * c->V);
-        CK(cudaMemcpy(tmp.data(), c->d_q64, sizeof(double) * tmp.size(), cudaMemcpyDeviceToHost));
-        for (int k = 0; k < c->L; ++k)
-            for (int h = 0; h < c->V; ++h) q[(size_t)k * c->V + h] = tmp[(size_t)h * c->Lpad + k];
-    }
+    if (svd) memcpy(svd, c->h_svd.data(), sizeof(double) * LV);
+    if (q) memcpy(q, c->h_qorig.data(), sizeof(double) * LV);
     return SITB_OK;
 }
 
@@ -277,7 +295,7 @@ extern "C" int sitb_get_status(sitb_ctx* c, sitb_status* out) {
     out->n_duplicate_nearest = h[2 + CNT_DUP_NEAREST];
     out->n_list_overflow = h[2 + CNT_LIST_OVERFLOW];
     out->nnz = h[2 + CNT_NNZ];
-    out->n_float_ties = h[2 + CNT_TIE_EXACT];
+    out->n_screen_rejects = h[2 + CNT_SCREEN_REJECT];
     return SITB_OK;
 }
 
@@ -295,9 +313,10 @@ static int base_params(sitb_ctx* c, int64_t begin, int64_t n, FillParams& p, con
     p.frame_list = nullptr;
     p.n_work = n;
     p.frame0 = c->frame0 + begin;
-    p.A = c->A; p.S = c->S; p.M = c->M; p.L = c->L; p.V = c->V; p.Lpad = c->Lpad;
+    p.A = c->A; p.S = c->S; p.M = c->M; p.L = c->L; p.V = c->V; p.Lpad = c->Lpad; p.NB = c->NB;
     p.static_idx = c->d_static_idx; p.mobile_idx = c->d_mobile_idx; p.ideal = c->d_ideal;
-    p.verts = c->d_verts; p.qf = c->d_qf; p.q64 = c->d_q64; p.acoef = c->d_acoef;
+    p.tab.v0 = c->d_v0; p.tab.b0 = c->d_b0; p.tab.va = c->d_va; p.tab.ba = c->d_ba;
+    p.tab.q64 = c->d_q64; p.tab.acoef = c->d_acoef; p.tab.nverts = c->d_nverts; p.tab.orig_of = c->d_orig_of;
     p.bcoef = c->bcoef; p.static_thr = c->static_thr; p.dynamic = c->dynamic; p.relaxed = c->relaxed;
     p.errkey = c->d_status; p.counters = c->d_status + 2;
     p.cid = c->d_cid; p.cw = c->d_cw; p.n_clusters = c->n_clusters;
@@ -345,8 +364,11 @@ extern "C" int sitb_set_centers(sitb_ctx* c, const int32_t* cid, const float* w,
     for (int k = 0; k < c->L; ++k)
         if (cid[k] < -1 || cid[k] >= n_clusters) return fail(SITB_E_INVALID, "sitb_set_centers: cluster id %d of landmark %d out of range", cid[k], k);
     CK(cudaSetDevice(c->device));
-    CK(cudaMemcpyAsync(c->d_cid, cid, sizeof(int) * (size_t)c->L, cudaMemcpyHostToDevice, c->stream));
-    CK(cudaMemcpyAsync(c->d_cw, w, sizeof(float) * (size_t)c->L, cudaMemcpyHostToDevice, c->stream));
+    std::vector<int> cid_i((size_t)c->L);
+    std::vector<float> w_i((size_t)c->L);
+    for (int k = 0; k < c->L; ++k) { cid_i[c->internal_of[k]] = cid[k]; w_i[c->internal_of[k]] = w[k]; }
+    CK(cudaMemcpyAsync(c->d_cid, cid_i.data(), sizeof(int) * (size_t)c->L, cudaMemcpyHostToDevice, c->stream));
+    CK(cudaMemcpyAsync(c->d_cw, w_i.data(), sizeof(float) * (size_t)c->L, cudaMemcpyHostToDevice, c->stream));
     CK(cudaStreamSynchronize(c->stream));
     c->n_clusters = n_clusters;
     return SITB_OK;

@@ -35,14 +35,11 @@ __device__ __forceinline__ double rowdot(const double* __restrict__ m, int d, do
                      __dmul_rn(m[3 * d + 2], p2));
 }
 
-// x - floor(x) for x known to lie in [-1, 2) (cheap selects), exact floor() otherwise
+// x - floor(x) for x in [-1, 2): floor is -1, 0 or 1, picked with two compares.  Callers use it
+// only for the fractional coordinate of (static + centroid - mobile) with both atoms already
+// wrapped into the cell (step 1 of K1), which lies in [-0.5, 1.5] up to rounding.
 __device__ __forceinline__ double frac_near(double f) {
-    double fl;
-    if (f >= -1.0 && f < 2.0) {
-        fl = (f >= 1.0) ? 1.0 : ((f < 0.0) ? -1.0 : 0.0);
-    } else {
-        fl = floor(f);
-    }
+    const double fl = (f >= 1.0) ? 1.0 : ((f < 0.0) ? -1.0 : 0.0);
     return __dsub_rn(f, fl);
 }
 
@@ -74,6 +71,18 @@ __device__ __forceinline__ void wrap_diag(const Cell& cell, double& x, double& y
     } else {
         f0 = __dsub_rn(f0, floor(f0)); f1 = __dsub_rn(f1, floor(f1)); f2 = __dsub_rn(f2, floor(f2));
     }
+    x = __dmul_rn(cell.c[0], f0);
+    y = __dmul_rn(cell.c[4], f1);
+    z = __dmul_rn(cell.c[8], f2);
+}
+
+// diagonal cell, also returning the wrapped fractional coordinates (in [0,1]) for the FP32 pre-screen
+__device__ __forceinline__ void wrap_diag_frac(const Cell& cell, double& x, double& y, double& z,
+                                               double& f0, double& f1, double& f2) {
+    f0 = __dmul_rn(cell.ci[0], x);
+    f1 = __dmul_rn(cell.ci[4], y);
+    f2 = __dmul_rn(cell.ci[8], z);
+    f0 = __dsub_rn(f0, floor(f0)); f1 = __dsub_rn(f1, floor(f1)); f2 = __dsub_rn(f2, floor(f2));
     x = __dmul_rn(cell.c[0], f0);
     y = __dmul_rn(cell.c[4], f1);
     z = __dmul_rn(cell.c[8], f2);

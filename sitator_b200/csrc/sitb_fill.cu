@@ -4,7 +4,7 @@
 //   LandmarkAnalysis.py:182-189   wrap a copy of the frame into the cell       (step 1 below)
 //   helpers.pyx:55-92             static-lattice check / dynamic lattice map   (step 2)
 //   helpers.pyx:95-114            per mobile atom: shift statics, wrap         (step 3a)
-//   helpers.pyx:134-212           fill_landmark_vec: logistic-cutoff product   (step 3b,3c)
+//   helpers.pyx:134-212           fill_landmark_vec: logistic-cutoff product   (steps 3b-3d)
 //   helpers.pyx:116-122           all-zero landmark vector check
 //   cluster/mcl.py:53             seen_ntimes                                  (MODE_STATS/STAGE)
 //   cluster/mcl.py:54             Gram (staged for the tcgen05 SYRK, or sparse outer products)
@@ -12,42 +12,62 @@
 //   cluster/mcl.py:81-83          best-matching landmark vector per cluster    (MODE_ASSIGN, best)
 //   cluster/mcl.py:118-122        representative landmark vector sums          (MODE_ASSIGN, rep)
 //
-// Work decomposition: one CTA per frame (grid-stride over frames), one warp per mobile atom.
-// Squared distances are computed in IEEE double exactly as the reference does (sitb_common.cuh);
-// the cut-off test "distance/site_vert_dist > 1.807" is applied as "d^2 > Q" with Q the exact
-// double boundary (sitb_tables.cu), pre-screened on float(d^2) vs float(Q) (rounding is monotone,
-// so only exact float ties need the double compare).  Only surviving landmarks (~1-2 %) evaluate
-// the logistic, in FP32 with an FP64-prepared argument.
+// Work decomposition: a CTA takes a small batch of frames (grid-stride); its warps claim the
+// batch's mobile atoms one at a time from a shared counter.  Per mobile atom the landmark walk is
+// split into phases so that no lane sits in a long serial dependency chain and the rare expensive
+// work is done on compacted lists:
+//   3a  squared distance to every static atom in FP32 (orthorhombic cells) -- a *screen* only
+//   3b  screen the first vertex of every landmark against a float bound that includes the FP32
+//       error margin (sitb_tables.cu): no landmark of the true support is ever dropped.  Passes
+//       are kept as one bit per lane and sub-iteration and compacted once per 1024 landmarks.
+//       Landmarks are numbered so that neighbours share their first vertex (few bank conflicts).
+//   3c  screen the remaining vertices of the ~13 % that passed (vector loads of the vertex block)
+//   3d  for the ~2 % left: recompute the squared distances in IEEE double exactly as the
+//       reference does (sitb_common.cuh), apply the exact cut-off  d^2 > Q  (bit-identical
+//       support), evaluate the logistic product in FP32 (log2 domain) from an FP64-prepared
+//       argument
+// For triclinic cells 3a is done in exact double (the reference's shift-and-wrap is not a
+// continuous function of position there, so a float screen can not be made conservative).
 #include "sitb_fill.cuh"
 #include <math_constants.h>
 
 namespace sitb {
 
 struct SmemLayout {
-    int Spad;
-    size_t off_ss, off_sm, off_wq64, off_tq, off_wqf, off_wev, off_wepr, off_hist, off_tv, off_wek,
-        off_wec, off_lmap, total;
+    int Spad, Mpad, qstride;
+    size_t off_ss, off_sm, off_ba, off_b0, off_fs, off_fm, off_wqf, off_wev, off_hist, off_lmap, off_seen,
+        off_cw, off_va, off_v0, off_cid, off_wcand, off_wek, off_task, total;
 };
 
-__host__ __device__ inline SmemLayout make_layout(int S, int M, int L, int V, int Lpad, int warps, int mode,
-                                                  int n_clusters) {
+__host__ __device__ inline SmemLayout make_layout(int S, int M, int L, int Lpad, int NB, int warps, int fb, int mode,
+                                                  int n_clusters, int dynamic) {
     SmemLayout l;
     l.Spad = (S + 3) & ~3;
+    l.Mpad = (M + 3) & ~3;
+    l.qstride = l.Spad + 4;     // per-warp screen distances + the dummy vertex slot [S]
     size_t o = 0;
-    l.off_ss = o;   o += sizeof(double) * 3 * (size_t)S;
-    l.off_sm = o;   o += sizeof(double) * 3 * (size_t)M;
-    l.off_wq64 = o; o += sizeof(double) * (size_t)warps * l.Spad;
-    l.off_tq = o;   o += sizeof(float) * (size_t)V * Lpad;
-    l.off_wqf = o;  o += sizeof(float) * (size_t)warps * l.Spad;
-    l.off_wev = o;  o += sizeof(float) * (size_t)warps * ENTRY_CAP;
-    l.off_wepr = o; o += sizeof(float) * (size_t)warps * ENTRY_CAP;
+    l.off_ss = o;    o += sizeof(double) * 3 * (size_t)S * fb;
+    l.off_sm = o;    o += sizeof(double) * 3 * (size_t)M * fb;
+    l.off_ba = o;    o += sizeof(float4) * (size_t)NB * Lpad;
+    l.off_b0 = o;    o += sizeof(float) * (size_t)Lpad;
+    l.off_fs = o;    o += sizeof(float) * 3 * (size_t)l.Spad * fb;
+    l.off_fm = o;    o += sizeof(float) * 3 * (size_t)l.Mpad * fb;
+    l.off_wqf = o;   o += sizeof(float) * (size_t)warps * l.qstride;
+    l.off_wev = o;   o += sizeof(float) * (size_t)warps * ENTRY_CAP;
     l.off_hist = o;
     if (mode == MODE_STATS || mode == MODE_STAGE) o += sizeof(unsigned) * (size_t)L;
     if (mode == MODE_ASSIGN) o += sizeof(unsigned) * (size_t)(n_clusters > 0 ? n_clusters : 1);
-    l.off_tv = o;   o += sizeof(uint16_t) * (size_t)V * Lpad;
-    l.off_wek = o;  o += sizeof(uint16_t) * (size_t)warps * ENTRY_CAP;
-    l.off_wec = o;  o += sizeof(int16_t) * (size_t)warps * ENTRY_CAP;
-    l.off_lmap = o; o += sizeof(unsigned) * (size_t)l.Spad * 2;   // lattice map + seen counts
+    l.off_lmap = o;  o += dynamic ? sizeof(unsigned) * (size_t)l.Spad * fb : 0;
+    l.off_seen = o;  o += dynamic ? sizeof(unsigned) * (size_t)l.Spad * fb : 0;
+    l.off_cw = o;    o += (mode == MODE_ASSIGN) ? sizeof(float) * (size_t)Lpad : 0;
+    o = (o + 7) & ~(size_t)7;
+    l.off_va = o;    o += sizeof(ushort4) * (size_t)NB * Lpad;
+    l.off_v0 = o;    o += sizeof(uint16_t) * (size_t)Lpad;
+    l.off_cid = o;   o += (mode == MODE_ASSIGN) ? sizeof(int16_t) * (size_t)Lpad : 0;
+    l.off_wcand = o; o += sizeof(uint16_t) * (size_t)warps * CAND_CAP;
+    l.off_wek = o;   o += sizeof(uint16_t) * (size_t)warps * ENTRY_CAP;
+    o = (o + 3) & ~(size_t)3;
+    l.off_task = o;  o += sizeof(int);
     l.total = (o + 15) & ~(size_t)15;
     return l;
 }
@@ -61,108 +81,172 @@ __device__ __forceinline__ void atomic_max_checked(unsigned long long* addr, uns
     if (key > *((volatile unsigned long long*)addr)) atomicMax(addr, key);
 }
 
-// logistic cut-off 1/(1+exp(steep*(d/svd-mid))) from the squared distance (helpers.pyx:197,205)
-__device__ __forceinline__ float cutoff_factor(double q, double acoef, double bcoef) {
-    // d = sqrt(q): float estimate + one Newton step with the residual taken in double
-    const float qf = __double2float_rn(q);
-    const float s0 = __fsqrt_rn(qf);
-    const double s0d = (double)s0;
-    const double res = fma(-s0d, s0d, q);
-    const double d = (s0 > 0.f) ? s0d + (double)(__double2float_rn(res) * __frcp_rn(s0 + s0)) : 0.0;
-    // exponent in base 2:  x2 = steep*log2e*(d/svd - mid)
-    double x2 = fma(d, acoef, -bcoef);
-    x2 = fmax(x2, -100.0);
-    const int n = __double2int_rn(x2);
-    const float fr = __double2float_rn(x2 - (double)n);
-    float e = exp2f(fr);
-    e = __int_as_float(__float_as_int(e) + (n << 23));   // e * 2^n, result stays normal (n >= -100)
-    return __frcp_rn(1.0f + e);
+__device__ __forceinline__ float ex2_approx(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ float lg2_approx(float x) {
+    float y;
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ float rsqrt_approx(float x) {
+    float y;
+    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
 }
 
-// ci^(1/n_verts)  (helpers.pyx:212)
-__device__ __forceinline__ float nth_root(float prod, int nv) {
-    switch (nv) {
-        case 1: return prod;
-        case 2: return __fsqrt_rn(prod);
-        case 3: return cbrtf(prod);
-        case 4: return __fsqrt_rn(__fsqrt_rn(prod));
-        default: return powf(prod, 1.0f / (float)nv);
+// log2(1 + exp(steep*(d/svd - mid))) = -log2 of the logistic cut-off (helpers.pyx:197,205),
+// d = sqrt(q).  The argument is prepared in double (one Newton step on a float rsqrt gives d to
+// ~1e-13; x2 = steep*log2e*(d/svd-mid) by one DFMA; integer/fraction split by the 1.5*2^52
+// trick), the transcendental part runs on the float SFU path.  Relative accuracy ~2e-7.
+__device__ __forceinline__ float cutoff_log2(double q, double acoef, double bcoef) {
+    const float qf = __double2float_rn(q);
+    const float r = rsqrt_approx(qf);
+    const float s0 = (qf > 0.f) ? qf * r : 0.f;
+    const float hr = (qf > 0.f) ? 0.5f * r : 0.f;
+    const double s0d = (double)s0;
+    const double res = fma(-s0d, s0d, q);
+    const double d = fma(res, (double)hr, s0d);
+    const double x2 = fma(d, acoef, -bcoef);
+    const double magic = 6755399441055744.0;             // 1.5 * 2^52
+    const double t = x2 + magic;
+    int n = __double2loint(t);                           // rint(x2)
+    const float fr = __double2float_rn(x2 - (t - magic));
+    n = max(-100, min(n, 120));
+    float e = ex2_approx(fr);
+    e = __int_as_float(__float_as_int(e) + (n << 23));   // e * 2^n, stays a normal float
+    return lg2_approx(1.0f + e);
+}
+
+__constant__ float c_inv_nv[MAX_VERTS + 1] = {0.f, 1.f, 0.5f, 1.f / 3.f, 0.25f, 0.2f, 1.f / 6.f, 1.f / 7.f, 0.125f};
+
+// u - round(u) for |u| < 2^22, two adds
+__device__ __forceinline__ float centre_frac(float u) {
+    const float magic = 12582912.0f;   // 1.5 * 2^23
+    return __fsub_rn(u, __fsub_rn(__fadd_rn(u, magic), magic));
+}
+
+__device__ __forceinline__ int warp_incl_scan(int v, int lane) {
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, v, o);
+        if (lane >= o) v += t;
     }
+    return v;
 }
 
 template <bool DIAG, int MODE>
-__global__ void __launch_bounds__(256) k_fill(const __grid_constant__ FillParams p) {
+__global__ void __launch_bounds__(DIAG ? 1024 : 512) k_fill(const __grid_constant__ FillParams p, const int FB) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
     const int nwarps = blockDim.x >> 5;
-    const int S = p.S, M = p.M, L = p.L, V = p.V, Lpad = p.Lpad;
-    const SmemLayout lay = make_layout(S, M, L, V, Lpad, nwarps, MODE, p.n_clusters);
-    double* ss = (double*)(smem_raw + lay.off_ss);
-    double* sm = (double*)(smem_raw + lay.off_sm);
-    double* q64w = (double*)(smem_raw + lay.off_wq64) + (size_t)warp * lay.Spad;
-    float* tq = (float*)(smem_raw + lay.off_tq);
-    float* qfw = (float*)(smem_raw + lay.off_wqf) + (size_t)warp * lay.Spad;
+    const int S = p.S, M = p.M, L = p.L, Lpad = p.Lpad, NB = p.NB;
+    const SmemLayout lay = make_layout(S, M, L, Lpad, NB, nwarps, FB, MODE, p.n_clusters, p.dynamic);
+    const int Spad = lay.Spad, Mpad = lay.Mpad;
+    double* ss = (double*)(smem_raw + lay.off_ss);          // [FB][S][3] wrapped statics (double)
+    double* sm = (double*)(smem_raw + lay.off_sm);          // [FB][M][3] wrapped mobiles (double)
+    float4* tba = (float4*)(smem_raw + lay.off_ba);         // [NB][Lpad] screen bounds, 4 vertices
+    float* tb0 = (float*)(smem_raw + lay.off_b0);           // [Lpad] screen bound of vertex 0
+    float* fs = (float*)(smem_raw + lay.off_fs);            // [FB][3][Spad] fractional statics (float, SoA)
+    float* fm = (float*)(smem_raw + lay.off_fm);            // [FB][3][Mpad]
+    float* qfw = (float*)(smem_raw + lay.off_wqf) + (size_t)warp * lay.qstride;
     float* ev = (float*)(smem_raw + lay.off_wev) + (size_t)warp * ENTRY_CAP;
-    float* epr = (float*)(smem_raw + lay.off_wepr) + (size_t)warp * ENTRY_CAP;
     unsigned* hist = (unsigned*)(smem_raw + lay.off_hist);
-    uint16_t* tv = (uint16_t*)(smem_raw + lay.off_tv);
+    unsigned* lmap_all = (unsigned*)(smem_raw + lay.off_lmap);
+    unsigned* seen_all = (unsigned*)(smem_raw + lay.off_seen);
+    float* tcw = (float*)(smem_raw + lay.off_cw);           // [Lpad] centre weight (MODE_ASSIGN)
+    ushort4* tva = (ushort4*)(smem_raw + lay.off_va);       // [NB][Lpad] vertex ids, 4 per block
+    uint16_t* tv0 = (uint16_t*)(smem_raw + lay.off_v0);     // [Lpad] vertex 0
+    int16_t* tcid = (int16_t*)(smem_raw + lay.off_cid);     // [Lpad] cluster of landmark (MODE_ASSIGN)
+    uint16_t* cand = (uint16_t*)(smem_raw + lay.off_wcand) + (size_t)warp * CAND_CAP;
     uint16_t* ek = (uint16_t*)(smem_raw + lay.off_wek) + (size_t)warp * ENTRY_CAP;
-    int16_t* ec = (int16_t*)(smem_raw + lay.off_wec) + (size_t)warp * ENTRY_CAP;
-    unsigned* lmap = (unsigned*)(smem_raw + lay.off_lmap);
-    unsigned* seen_cnt = lmap + lay.Spad;
+    int* task_counter = (int*)(smem_raw + lay.off_task);
 
     // ---- stage the landmark tables once per CTA ------------------------------------------
-    for (int i = threadIdx.x; i < V * Lpad; i += blockDim.x) {
-        tq[i] = p.qf[i];
-        tv[i] = p.verts[i];
+    for (int i = threadIdx.x; i < NB * Lpad; i += blockDim.x) {
+        tba[i] = p.tab.ba[i];
+        tva[i] = p.tab.va[i];
+    }
+    for (int i = threadIdx.x; i < Lpad; i += blockDim.x) {
+        tb0[i] = p.tab.b0[i];
+        tv0[i] = p.tab.v0[i];
+        if (MODE == MODE_ASSIGN) {
+            tcid[i] = (i < L) ? (int16_t)p.cid[i] : (int16_t)-1;
+            tcw[i] = (i < L) ? p.cw[i] : 0.f;
+        }
     }
     const bool use_hist = (MODE == MODE_STATS || MODE == MODE_STAGE) ||
                           (MODE == MODE_ASSIGN && p.counts != nullptr);
     const int hist_n = (MODE == MODE_ASSIGN) ? p.n_clusters : L;
     if (use_hist)
         for (int i = threadIdx.x; i < hist_n; i += blockDim.x) hist[i] = 0u;
+    if (lane == 0) qfw[S] = 0.f;                            // dummy vertex: passes every screen
     __syncthreads();
 
-    unsigned long long loc_zero = 0, loc_nnz = 0, loc_tie = 0, loc_over = 0, loc_dup = 0;
+    unsigned long long loc_zero = 0, loc_nnz = 0, loc_rej = 0, loc_over = 0, loc_dup = 0;
     const Cell& cell = p.cell;
+    const float Lx = (float)cell.c[0], Ly = (float)cell.c[4], Lz = (float)cell.c[8];
+    const int W = 4 * NB;
 
-    for (long long wi = blockIdx.x; wi < p.n_work; wi += gridDim.x) {
-        const long long f = p.frame_list ? p.frame_list[wi] : wi;
-        const long long gframe = p.frame0 + f;
-        const double* __restrict__ fr = p.frames + (size_t)f * (size_t)p.A * 3;
+    for (long long w0 = (long long)blockIdx.x * FB; w0 < p.n_work; w0 += (long long)gridDim.x * FB) {
+        const int nb = (int)((p.n_work - w0 < FB) ? (p.n_work - w0) : FB);
 
-        // ---- 1. wrap this frame's static and mobile atoms (LandmarkAnalysis.py:182-189) --
-        for (int t = threadIdx.x; t < S + M; t += blockDim.x) {
-            const int a = (t < S) ? p.static_idx[t] : p.mobile_idx[t - S];
+        // ---- 1. wrap the batch's static and mobile atoms (LandmarkAnalysis.py:182-189) ----
+        for (int t = threadIdx.x; t < nb * (S + M); t += blockDim.x) {
+            const int b = t / (S + M), r = t - b * (S + M);
+            const long long f = p.frame_list ? p.frame_list[w0 + b] : (w0 + b);
+            const double* __restrict__ fr = p.frames + (size_t)f * (size_t)p.A * 3;
+            const int a = (r < S) ? p.static_idx[r] : p.mobile_idx[r - S];
             double x = fr[3 * a + 0], y = fr[3 * a + 1], z = fr[3 * a + 2];
-            wrap_point<DIAG, false>(cell, x, y, z);
-            double* dst = (t < S) ? (ss + 3 * t) : (sm + 3 * (t - S));
+            if (DIAG) {
+                double f0, f1, f2;
+                wrap_diag_frac(cell, x, y, z, f0, f1, f2);
+                if (r < S) {
+                    float* d = fs + (size_t)b * 3 * Spad;
+                    d[r] = (float)f0; d[Spad + r] = (float)f1; d[2 * Spad + r] = (float)f2;
+                } else {
+                    float* d = fm + (size_t)b * 3 * Mpad;
+                    d[r - S] = (float)f0; d[Mpad + r - S] = (float)f1; d[2 * Mpad + r - S] = (float)f2;
+                }
+            } else {
+                wrap_point<false, false>(cell, x, y, z);
+            }
+            double* dst = (r < S) ? (ss + ((size_t)b * S + r) * 3) : (sm + ((size_t)b * M + (r - S)) * 3);
             dst[0] = x; dst[1] = y; dst[2] = z;
         }
         if (p.dynamic)
-            for (int t = threadIdx.x; t < S; t += blockDim.x) seen_cnt[t] = 0u;
+            for (int t = threadIdx.x; t < nb * Spad; t += blockDim.x) seen_all[t] = 0u;
+        if (threadIdx.x == 0) *task_counter = 0;
         __syncthreads();
 
         // ---- 2. static lattice (helpers.pyx:55-92) ---------------------------------------
         if (!p.dynamic) {
-            for (int s = threadIdx.x; s < S; s += blockDim.x) {
+            for (int t = threadIdx.x; t < nb * S; t += blockDim.x) {
+                const int b = t / S, s = t - b * S;
+                const long long gframe = p.frame0 + (p.frame_list ? p.frame_list[w0 + b] : (w0 + b));
+                const double* pt = ss + ((size_t)b * S + s) * 3;
                 const double ox = __dsub_rn(cell.cen[0], p.ideal[3 * s + 0]);
                 const double oy = __dsub_rn(cell.cen[1], p.ideal[3 * s + 1]);
                 const double oz = __dsub_rn(cell.cen[2], p.ideal[3 * s + 2]);
-                const double q = shifted_dist2<DIAG, false>(cell, ss[3 * s], ss[3 * s + 1], ss[3 * s + 2], ox, oy, oz);
+                const double q = shifted_dist2<DIAG, false>(cell, pt[0], pt[1], pt[2], ox, oy, oz);
                 if (__dsqrt_rn(q) > p.static_thr)
                     atomicMin(p.errkey, make_error_key(gframe, PHASE_STATIC_MOVED, (unsigned)s));
             }
         } else {
-            for (int li = warp; li < S; li += nwarps) {
+            for (int t = warp; t < nb * S; t += nwarps) {
+                const int b = t / S, li = t - b * S;
+                const long long gframe = p.frame0 + (p.frame_list ? p.frame_list[w0 + b] : (w0 + b));
+                const double* sb = ss + (size_t)b * S * 3;
                 const double ox = __dsub_rn(cell.cen[0], p.ideal[3 * li + 0]);
                 const double oy = __dsub_rn(cell.cen[1], p.ideal[3 * li + 1]);
                 const double oz = __dsub_rn(cell.cen[2], p.ideal[3 * li + 2]);
                 double bd = CUDART_INF;
                 int bj = 0x7FFFFFFF;
                 for (int j = lane; j < S; j += 32) {
-                    const double d = __dsqrt_rn(shifted_dist2<DIAG, false>(cell, ss[3 * j], ss[3 * j + 1], ss[3 * j + 2], ox, oy, oz));
+                    const double d = __dsqrt_rn(shifted_dist2<DIAG, false>(cell, sb[3 * j], sb[3 * j + 1], sb[3 * j + 2], ox, oy, oz));
                     if (d < bd) { bd = d; bj = j; }           // first minimum within the lane
                 }
 #pragma unroll
@@ -172,152 +256,231 @@ __global__ void __launch_bounds__(256) k_fill(const __grid_constant__ FillParams
                     if (od < bd || (od == bd && oj < bj)) { bd = od; bj = oj; }
                 }
                 if (lane == 0) {
-                    atomicAdd(&seen_cnt[bj], 1u);
-                    lmap[li] = (unsigned)bj;
+                    atomicAdd(&seen_all[(size_t)b * Spad + bj], 1u);
+                    lmap_all[(size_t)b * Spad + li] = (unsigned)bj;
                     if (bd > p.static_thr)
                         atomicMin(p.errkey, make_error_key(gframe, PHASE_STATIC_MOVED, (unsigned)li));
                 }
             }
             __syncthreads();
-            for (int t = threadIdx.x; t < S; t += blockDim.x) {
-                const unsigned c = seen_cnt[t];
-                if (c == 0u && !p.relaxed)
+            for (int t = threadIdx.x; t < nb * S; t += blockDim.x) {
+                const int b = t / S, s = t - b * S;
+                const unsigned c = seen_all[(size_t)b * Spad + s];
+                if (c == 0u && !p.relaxed) {
+                    const long long gframe = p.frame0 + (p.frame_list ? p.frame_list[w0 + b] : (w0 + b));
                     atomicMin(p.errkey, make_error_key(gframe, PHASE_STATIC_UNASSIGNED, 0u));
+                }
                 if (c > 1u) loc_dup += c - 1u;
             }
         }
         __syncthreads();
 
-        // ---- 3. one warp per mobile atom --------------------------------------------------
-        for (int j = warp; j < M; j += nwarps) {
-            const long long row_local = wi * M + j;                 // row in this launch's outputs
+        // ---- 3. one warp per mobile atom, claimed from a per-batch counter ------------------
+        for (;;) {
+            int jj = 0;
+            if (lane == 0) jj = atomicAdd(task_counter, 1);
+            jj = __shfl_sync(0xffffffffu, jj, 0);
+            if (jj >= nb * M) break;
+            int b = 0, j = jj;
+            while (j >= M) { j -= M; ++b; }
+            const long long fl = p.frame_list ? p.frame_list[w0 + b] : (w0 + b);
+            const long long gframe = p.frame0 + fl;
+            const long long row_local = (w0 + b) * M + j;            // row in this launch's outputs
             const unsigned long long row_global = (unsigned long long)(gframe * M + j);
-            // 3a. squared distances static -> mobile (helpers.pyx:99-103, :174-178)
-            const double ox = __dsub_rn(cell.cen[0], sm[3 * j + 0]);
-            const double oy = __dsub_rn(cell.cen[1], sm[3 * j + 1]);
-            const double oz = __dsub_rn(cell.cen[2], sm[3 * j + 2]);
-            for (int s = lane; s < S; s += 32) {
-                const int src = p.dynamic ? (int)lmap[s] : s;
-                const double q = shifted_dist2<DIAG, true>(cell, ss[3 * src], ss[3 * src + 1], ss[3 * src + 2], ox, oy, oz);
-                q64w[s] = q;
-                qfw[s] = __double2float_rn(q);
+            const double* sb = ss + (size_t)b * S * 3;
+            const unsigned* lmap = lmap_all + (size_t)b * Spad;
+            const double ox = __dsub_rn(cell.cen[0], sm[((size_t)b * M + j) * 3 + 0]);
+            const double oy = __dsub_rn(cell.cen[1], sm[((size_t)b * M + j) * 3 + 1]);
+            const double oz = __dsub_rn(cell.cen[2], sm[((size_t)b * M + j) * 3 + 2]);
+
+            // 3a. screen distances static -> mobile (helpers.pyx:99-103, :174-178)
+            if (DIAG) {
+                const float* fsb = fs + (size_t)b * 3 * Spad;
+                const float* fmb = fm + (size_t)b * 3 * Mpad;
+                const float mx = fmb[j], my = fmb[Mpad + j], mz = fmb[2 * Mpad + j];
+                for (int s = lane; s < S; s += 32) {
+                    const int src = p.dynamic ? (int)lmap[s] : s;
+                    const float cx = centre_frac(fsb[src] - mx) * Lx;
+                    const float cy = centre_frac(fsb[Spad + src] - my) * Ly;
+                    const float cz = centre_frac(fsb[2 * Spad + src] - mz) * Lz;
+                    qfw[s] = fmaf(cz, cz, fmaf(cy, cy, cx * cx));
+                }
+            } else {
+                for (int s = lane; s < S; s += 32) {
+                    const int src = p.dynamic ? (int)lmap[s] : s;
+                    qfw[s] = __double2float_rn(
+                        shifted_dist2<false, true>(cell, sb[3 * src], sb[3 * src + 1], sb[3 * src + 2], ox, oy, oz));
+                }
+            }
+            if (MODE == MODE_DENSE) {     // rows are written as zeros + scattered non-zeros
+                if (p.dense_f64) {
+                    double* o = (double*)p.dense_out + (size_t)row_local * L;
+                    for (int k = lane; k < L; k += 32) o[k] = 0.0;
+                } else {
+                    float* o = (float*)p.dense_out + (size_t)row_local * L;
+                    for (int k = lane; k < L; k += 32) o[k] = 0.f;
+                }
             }
             __syncwarp();
 
-            // 3b. landmark walk (helpers.pyx:186-212)
-            int nent = 0;
-            for (int k0 = 0; k0 < L; k0 += 32) {
-                const int k = k0 + lane;
-                bool alive = k < L;
-                int nv = 0;
-                if (alive) {
-                    for (int h = 0; h < V; ++h) {
-                        const unsigned v = tv[h * Lpad + k];
-                        if (v == VERT_END) break;
-                        ++nv;
-                        const float a = qfw[v];
-                        const float b = tq[h * Lpad + k];
-                        if (a > b) { alive = false; break; }
-                        if (a == b) {                          // float tie: decide in double
-                            ++loc_tie;
-                            if (q64w[v] > p.q64[h * Lpad + k]) { alive = false; break; }
+            int nsurv = 0, ncand = 0;
+            for (int kb = 0; kb < Lpad; kb += CAND_CAP) {
+                // 3b. first vertex of every landmark in the block: one pass bit per sub-iteration
+                // (Lpad is a multiple of 256: groups of 8 sub-iterations, fully unrolled)
+                const int ngroups = ((Lpad - kb) < CAND_CAP ? (Lpad - kb) : CAND_CAP) >> 8;
+                unsigned mask = 0u;
+                for (int g = 0; g < ngroups; ++g) {
+                    const uint16_t* v0p = tv0 + kb + 256 * g + lane;
+                    const float* b0p = tb0 + kb + 256 * g + lane;
+                    unsigned vtx[8];
+                    float bnd[8], qv[8];
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) { vtx[i] = v0p[32 * i]; bnd[i] = b0p[32 * i]; }
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) qv[i] = qfw[vtx[i]];
+                    unsigned m8 = 0u;
+#pragma unroll
+                    for (int i = 0; i < 8; ++i)
+                        if (!(qv[i] > bnd[i])) m8 |= 1u << i;
+                    mask |= m8 << (8 * g);
+                }
+                const int cnt = __popc(mask);
+                const int incl = warp_incl_scan(cnt, lane);
+                const int total = __shfl_sync(0xffffffffu, incl, 31);
+                int pos = ncand + incl - cnt;
+                while (mask) {
+                    const int u = __ffs(mask) - 1;
+                    mask &= mask - 1u;
+                    cand[pos++] = (uint16_t)(kb + 32 * u + lane);
+                }
+                ncand += total;
+                __syncwarp();
+                // run 3c when the next block could overflow the candidate list, or at the end
+                if (ncand + CAND_CAP <= CAND_CAP && kb + CAND_CAP < Lpad) continue;
+                // 3c. remaining vertices of the candidates -> survivors appended to ek[]
+                for (int i0 = 0; i0 < ncand; i0 += 32) {
+                    const int i = i0 + lane;
+                    bool ok = i < ncand;
+                    const int k = ok ? (int)cand[i] : 0;
+                    if (ok) {
+                        const ushort4 vv = tva[k];
+                        const float4 bb = tba[k];
+                        ok = !(qfw[vv.y] > bb.y) && !(qfw[vv.z] > bb.z) && !(qfw[vv.w] > bb.w);
+                        for (int blk = 1; blk < NB && ok; ++blk) {
+                            const ushort4 v2 = tva[(size_t)blk * Lpad + k];
+                            const float4 b2 = tba[(size_t)blk * Lpad + k];
+                            ok = !(qfw[v2.x] > b2.x) && !(qfw[v2.y] > b2.y) && !(qfw[v2.z] > b2.z) && !(qfw[v2.w] > b2.w);
                         }
                     }
-                    if (nv == 0) alive = false;
+                    const unsigned m = __ballot_sync(0xffffffffu, ok);
+                    if (ok) {
+                        const int q = nsurv + __popc(m & lanemask_lt());
+                        if (q < ENTRY_CAP) ek[q] = (uint16_t)k;
+                    }
+                    nsurv += __popc(m);
                 }
+                ncand = 0;
+                __syncwarp();
+            }
+            if (nsurv > ENTRY_CAP) { if (lane == 0) ++loc_over; nsurv = ENTRY_CAP; }
+
+            // 3d. exact test + value for the survivors (in-place: ek[i] -> ek[pos], ev[pos], pos <= i)
+            int nent = 0;
+            for (int i0 = 0; i0 < nsurv; i0 += 32) {
+                const int i = i0 + lane;
+                bool alive = i < nsurv;
+                const int k = alive ? (int)ek[i] : 0;
                 float val = 0.f;
                 if (alive) {
-                    float prod = 1.f;
-                    for (int h = 0; h < nv; ++h) {
-                        const unsigned v = tv[h * Lpad + k];
-                        prod *= cutoff_factor(q64w[v], p.acoef[h * Lpad + k], p.bcoef);
+                    float lsum = 0.f;
+                    int nv = 0;
+                    for (int blk = 0; blk < NB; ++blk) {
+                        const ushort4 vv = tva[(size_t)blk * Lpad + k];
+                        const double2* q2 = (const double2*)(p.tab.q64 + (size_t)k * W + 4 * blk);
+                        const double2* a2 = (const double2*)(p.tab.acoef + (size_t)k * W + 4 * blk);
+                        const double2 q01 = __ldg(q2), q23 = __ldg(q2 + 1), a01 = __ldg(a2), a23 = __ldg(a2 + 1);
+                        const unsigned vs[4] = {vv.x, vv.y, vv.z, vv.w};
+                        const double qs[4] = {q01.x, q01.y, q23.x, q23.y};
+                        const double as[4] = {a01.x, a01.y, a23.x, a23.y};
+#pragma unroll
+                        for (int h = 0; h < 4; ++h) {
+                            if (vs[h] != (unsigned)S) {
+                                const int src = p.dynamic ? (int)lmap[vs[h]] : (int)vs[h];
+                                const double q = shifted_dist2<DIAG, true>(cell, sb[3 * src], sb[3 * src + 1], sb[3 * src + 2], ox, oy, oz);
+                                if (q > qs[h]) alive = false;                 // helpers.pyx:199-203, exact
+                                lsum += cutoff_log2(q, as[h], p.bcoef);
+                                ++nv;
+                            }
+                        }
                     }
-                    val = nth_root(prod, nv);
-                }
-                if (MODE == MODE_DENSE) {
-                    if (k < L) {
-                        if (p.dense_f64) ((double*)p.dense_out)[(size_t)row_local * L + k] = (double)val;
-                        else ((float*)p.dense_out)[(size_t)row_local * L + k] = val;
-                    }
+                    if (alive) val = ex2_approx(-lsum * c_inv_nv[nv]);        // helpers.pyx:212
+                    else ++loc_rej;
                 }
                 const unsigned m = __ballot_sync(0xffffffffu, alive);
-                if (MODE != MODE_DENSE) {
-                    if (alive) {
-                        const int pos = nent + __popc(m & lanemask_lt());
-                        if (pos < ENTRY_CAP) { ek[pos] = (uint16_t)k; ev[pos] = val; }
-                    }
+                if (alive) {
+                    const int q = nent + __popc(m & lanemask_lt());
+                    ek[q] = (uint16_t)k;
+                    ev[q] = val;
                 }
                 nent += __popc(m);
             }
+            __syncwarp();
             if (lane == 0) {
                 loc_nnz += (unsigned long long)nent;
                 if (nent == 0) {
                     ++loc_zero;
-                    if (p.errkey)
-                        atomicMin(p.errkey + 1, make_error_key(gframe, PHASE_ZERO_LVEC, (unsigned)j));
+                    if (p.errkey) atomicMin(p.errkey + 1, make_error_key(gframe, PHASE_ZERO_LVEC, (unsigned)j));
                 }
-                if (nent > ENTRY_CAP) ++loc_over;
             }
-            if (nent > ENTRY_CAP) nent = ENTRY_CAP;
-            __syncwarp();
 
-            // 3c. sinks
-            if (MODE == MODE_STATS || MODE == MODE_STAGE) {
-                for (int e = lane; e < nent; e += 32) atomicAdd(&hist[ek[e]], 1u);
-            }
-            if (MODE == MODE_STATS) {
-                // upper triangle of the outer product; entries are sorted by landmark index
-                for (int a = 0; a < nent; ++a) {
-                    const unsigned ka = ek[a];
-                    const double va = (double)ev[a];
-                    for (int b = a + lane; b < nent; b += 32)
-                        atomicAdd(&p.gram[(size_t)ka * L + ek[b]], va * (double)ev[b]);
-                }
-            }
-            if (MODE == MODE_STAGE) {
-                for (int e = lane; e < nent; e += 32) {
-                    const float v = ev[e];
-                    const __half hi = __float2half_rn(v);
-                    const __half lo = __float2half_rn(v - __half2float(hi));
-                    const size_t o = (size_t)ek[e] * (size_t)p.stage_ld + (size_t)row_local;
-                    p.stage_hi[o] = hi;
-                    p.stage_lo[o] = lo;
-                }
-            }
+            // 3e. sinks
             if (MODE == MODE_ASSIGN) {
                 // centres have disjoint supports (cluster/mcl.py:80): dot = sum over the row's
-                // non-zeros of weight[landmark], grouped by cluster[landmark]
-                for (int e = lane; e < nent; e += 32) {
-                    const int k = ek[e];
-                    const int c = p.cid[k];
-                    ec[e] = (int16_t)c;
-                    epr[e] = (c >= 0) ? ev[e] * p.cw[k] : 0.f;
-                }
-                __syncwarp();
+                // non-zeros of weight[landmark], grouped by cluster[landmark].  A row touches few
+                // clusters: peel them off one at a time with warp votes.
                 float bestc = 0.f;      // untouched clusters have |dot| = 0; np.argmax -> index 0
                 int bestid = 0;
-                for (int base = 0; base < nent; base += 32) {
-                    const int e = base + lane;
-                    const int my = (e < nent) ? (int)ec[e] : -1;
-                    float tot = 0.f;
-                    bool first = true;
-                    if (my >= 0) {
-                        for (int e2 = 0; e2 < nent; ++e2) {
-                            if ((int)ec[e2] == my) {
-                                tot += epr[e2];
-                                if (e2 < e) first = false;
-                            }
-                        }
-                        const float conf = fabsf(tot);
-                        if (conf > bestc || (conf == bestc && my < bestid)) { bestc = conf; bestid = my; }
-                        if (p.best && first) atomic_max_checked(p.best + my, pack_key(conf, row_global));
-                    }
-                }
+                if (nent <= 32) {
+                    int myc = -1;
+                    float mypr = 0.f;
+                    if (lane < nent) { const int k = ek[lane]; myc = tcid[k]; mypr = ev[lane] * tcw[k]; }
+                    for (;;) {
+                        const int cur = __reduce_min_sync(0xffffffffu, myc >= 0 ? myc : 0x7FFFFFFF);
+                        if (cur == 0x7FFFFFFF) break;
+                        float part = (myc == cur) ? mypr : 0.f;
+                        if (myc == cur) myc = -1;
 #pragma unroll
-                for (int o = 16; o > 0; o >>= 1) {
-                    const float oc = __shfl_xor_sync(0xffffffffu, bestc, o);
-                    const int oi = __shfl_xor_sync(0xffffffffu, bestid, o);
-                    if (oc > bestc || (oc == bestc && oi < bestid)) { bestc = oc; bestid = oi; }
+                        for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+                        const float conf = fabsf(part);
+                        if (conf > bestc) { bestc = conf; bestid = cur; }     // ascending ids: ties keep the lower
+                        if (p.best && lane == 0) atomic_max_checked(p.best + cur, pack_key(conf, row_global));
+                    }
+                } else {
+                    int myc[ENTRY_CAP / 32];
+                    float mypr[ENTRY_CAP / 32];
+#pragma unroll
+                    for (int c = 0; c < ENTRY_CAP / 32; ++c) {
+                        const int e = 32 * c + lane;
+                        myc[c] = -1; mypr[c] = 0.f;
+                        if (e < nent) { const int k = ek[e]; myc[c] = tcid[k]; mypr[c] = ev[e] * tcw[k]; }
+                    }
+                    for (;;) {
+                        int mine = 0x7FFFFFFF;
+#pragma unroll
+                        for (int c = 0; c < ENTRY_CAP / 32; ++c)
+                            if (myc[c] >= 0 && myc[c] < mine) mine = myc[c];
+                        const int cur = __reduce_min_sync(0xffffffffu, mine);
+                        if (cur == 0x7FFFFFFF) break;
+                        float part = 0.f;
+#pragma unroll
+                        for (int c = 0; c < ENTRY_CAP / 32; ++c)
+                            if (myc[c] == cur) { part += mypr[c]; myc[c] = -1; }
+#pragma unroll
+                        for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+                        const float conf = fabsf(part);
+                        if (conf > bestc) { bestc = conf; bestid = cur; }
+                        if (p.best && lane == 0) atomic_max_checked(p.best + cur, pack_key(conf, row_global));
+                    }
                 }
                 long long label = bestid;
                 float conf = bestc;
@@ -333,7 +496,44 @@ __global__ void __launch_bounds__(256) k_fill(const __grid_constant__ FillParams
                 }
                 if (p.rep && label >= 0) {
                     for (int e = lane; e < nent; e += 32)
-                        atomicAdd(&p.rep[(size_t)label * L + ek[e]], (double)conf * (double)ev[e]);
+                        atomicAdd(&p.rep[(size_t)label * L + p.tab.orig_of[ek[e]]], (double)conf * (double)ev[e]);
+                }
+            } else {
+                // the other sinks address landmarks by the caller's numbering
+                if (MODE == MODE_STATS || MODE == MODE_STAGE)
+                    for (int e = lane; e < nent; e += 32) atomicAdd(&hist[ek[e]], 1u);
+                for (int e = lane; e < nent; e += 32) ek[e] = p.tab.orig_of[ek[e]];
+                __syncwarp();
+                if (MODE == MODE_DENSE) {
+                    if (p.dense_f64) {
+                        double* o = (double*)p.dense_out + (size_t)row_local * L;
+                        for (int e = lane; e < nent; e += 32) o[ek[e]] = (double)ev[e];
+                    } else {
+                        float* o = (float*)p.dense_out + (size_t)row_local * L;
+                        for (int e = lane; e < nent; e += 32) o[ek[e]] = ev[e];
+                    }
+                }
+                if (MODE == MODE_STATS) {
+                    // upper triangle of the outer product
+                    for (int a = 0; a < nent; ++a) {
+                        const unsigned ka = ek[a];
+                        const double va = (double)ev[a];
+                        for (int bq = a + lane; bq < nent; bq += 32) {
+                            const unsigned kq = ek[bq];
+                            const unsigned lo = ka < kq ? ka : kq, hi = ka < kq ? kq : ka;
+                            atomicAdd(&p.gram[(size_t)lo * L + hi], va * (double)ev[bq]);
+                        }
+                    }
+                }
+                if (MODE == MODE_STAGE) {
+                    for (int e = lane; e < nent; e += 32) {
+                        const float v = ev[e];
+                        const __half hi = __float2half_rn(v);
+                        const __half lo = __float2half_rn(v - __half2float(hi));
+                        const size_t o = (size_t)ek[e] * (size_t)p.stage_ld + (size_t)row_local;
+                        p.stage_hi[o] = hi;
+                        p.stage_lo[o] = lo;
+                    }
                 }
             }
             __syncwarp();
@@ -347,19 +547,19 @@ __global__ void __launch_bounds__(256) k_fill(const __grid_constant__ FillParams
         unsigned long long* dst = (MODE == MODE_ASSIGN) ? p.counts : p.seen;
         if (dst)
             for (int i = threadIdx.x; i < hist_n; i += blockDim.x)
-                if (hist[i]) atomicAdd(&dst[i], (unsigned long long)hist[i]);
+                if (hist[i]) atomicAdd(&dst[(MODE == MODE_ASSIGN) ? i : (int)p.tab.orig_of[i]], (unsigned long long)hist[i]);
     }
     if (p.counters) {
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) {
-            loc_tie += __shfl_xor_sync(0xffffffffu, loc_tie, o);
+            loc_rej += __shfl_xor_sync(0xffffffffu, loc_rej, o);
             loc_dup += __shfl_xor_sync(0xffffffffu, loc_dup, o);
         }
         if (lane == 0) {
             if (loc_zero) atomicAdd(&p.counters[CNT_ZERO_ROWS], loc_zero);
             if (loc_nnz) atomicAdd(&p.counters[CNT_NNZ], loc_nnz);
             if (loc_over) atomicAdd(&p.counters[CNT_LIST_OVERFLOW], loc_over);
-            if (loc_tie) atomicAdd(&p.counters[CNT_TIE_EXACT], loc_tie);
+            if (loc_rej) atomicAdd(&p.counters[CNT_SCREEN_REJECT], loc_rej);
             if (loc_dup) atomicAdd(&p.counters[CNT_DUP_NEAREST], loc_dup);
         }
     }
@@ -367,26 +567,47 @@ __global__ void __launch_bounds__(256) k_fill(const __grid_constant__ FillParams
 
 template <bool DIAG, int MODE>
 static cudaError_t launch_one(const FillParams& p, int n_sms, cudaStream_t stream) {
-    // as many warps per CTA as fit the shared-memory budget, grid = a multiple of the SM count
-    int warps = 8;
-    size_t bytes = 0;
-    const int ncl = p.n_clusters;
-    for (; warps >= 1; warps >>= 1) {
-        bytes = make_layout(p.S, p.M, p.L, p.V, p.Lpad, warps, MODE, ncl).total;
-        if (bytes <= 200 * 1024) break;
-    }
-    if (warps < 1) return cudaErrorInvalidConfiguration;
+    // warps per CTA and frames per batch: as many warps as fit the shared-memory budget with two
+    // CTAs per SM if possible; mobile atoms are claimed dynamically inside a batch, so the longest
+    // batch that fits is best (fewer CTA barriers, better balance)
     auto kern = k_fill<DIAG, MODE>;
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    // CTAs per SM x warps per CTA x frames per batch: maximise resident warps per SM within the
+    // 227 KB of shared memory (tables are per CTA, lists per warp, frame buffers per batch); mobile
+    // atoms are claimed dynamically inside a batch, so want >= 3 tasks per warp and batch
+    const int max_w = DIAG ? 32 : 16;
+    int best_w = 0, best_fb = 1;
+    size_t best_bytes = 0;
+    double best_score = -1.0;
+    for (int ctas = 2; ctas >= 1; --ctas) {
+        const size_t budget = (size_t)(227 * 1024) / ctas - 1024;
+        for (int w = max_w; w >= 1; w >>= 1) {
+            if (w * ctas > 64) continue;
+            int fb_fit = 0;
+            size_t bytes_fit = 0;
+            for (int fb = 1; fb <= 8; ++fb) {
+                const size_t bytes = make_layout(p.S, p.M, p.L, p.Lpad, p.NB, w, fb, MODE, p.n_clusters, p.dynamic).total;
+                if (bytes > budget) break;
+                fb_fit = fb; bytes_fit = bytes;
+            }
+            if (!fb_fit) continue;
+            const double fill = (double)(fb_fit * p.M) / (3.0 * w);
+            const double score = (double)(ctas * w) * (fill < 1.0 ? fill : 1.0) + 0.01 * ctas;
+            if (score > best_score) { best_score = score; best_w = w; best_fb = fb_fit; best_bytes = bytes_fit; }
+            break;   // smaller CTAs of the same count only lose warps
+        }
+    }
+    if (best_w == 0) return cudaErrorInvalidConfiguration;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)best_bytes);
     if (e != cudaSuccess) return e;
     int per_sm = 1;
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, warps * 32, bytes);
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, best_w * 32, best_bytes);
     if (e != cudaSuccess) return e;
     if (per_sm < 1) per_sm = 1;
+    const long long batches = (p.n_work + best_fb - 1) / best_fb;
     long long grid = (long long)n_sms * per_sm;
-    if (grid > p.n_work) grid = p.n_work;
+    if (grid > batches) grid = batches;
     if (grid < 1) return cudaSuccess;
-    kern<<<(unsigned)grid, warps * 32, bytes, stream>>>(p);
+    kern<<<(unsigned)grid, best_w * 32, best_bytes, stream>>>(p, best_fb);
     return cudaGetLastError();
 }
 

@@ -2,6 +2,7 @@
 // Parameter block shared by the kernel (sitb_fill.cu) and the C-ABI (sitb_api.cu).
 #pragma once
 #include <cuda_fp16.h>
+#include <vector>
 #include "sitb_common.cuh"
 
 namespace sitb {
@@ -13,12 +14,40 @@ enum FillMode : int {
     MODE_ASSIGN = 3,  // centre similarity, threshold, argmax (+ optional reductions)
 };
 
-static constexpr int ENTRY_CAP = 256;        // non-zero components kept per landmark vector
-static constexpr uint16_t VERT_END = 0xFFFF; // end of a landmark's vertex list (the reference's -1)
+static constexpr int ENTRY_CAP = 128;        // non-zero components kept per landmark vector
+static constexpr int CAND_CAP = 512;         // landmarks screened per block (= candidate list capacity)
+static constexpr int MAX_VERTS = 8;
 
 // counters[] slots
 enum : int { CNT_ZERO_ROWS = 0, CNT_DUP_NEAREST = 1, CNT_LIST_OVERFLOW = 2, CNT_NNZ = 3,
-             CNT_TIE_EXACT = 4, CNT_ROWS = 5, CNT_SLOTS = 8 };
+             CNT_SCREEN_REJECT = 4, CNT_ROWS = 5, CNT_SLOTS = 8 };
+
+// Landmark tables (built by sitb_tables.cu).  Vertex ids index the static lattice; a missing
+// vertex (the reference's -1 padding) is the dummy id S, whose screen distance is 0 and whose
+// bound is +inf, so it passes every screen test.  NB = ceil(V/4) blocks of 4 vertices.
+struct LandmarkTables {
+    const uint16_t* v0;     // [Lpad] first vertex (SoA copy for the first screen); pad rows: S
+    const float* b0;        // [Lpad] its screen bound; pad rows: -1 (never passes)
+    const ushort4* va;      // [NB][Lpad] vertices 4*blk .. 4*blk+3
+    const float4* ba;       // [NB][Lpad] screen bounds (float, including the FP32 error margin)
+    const double* q64;      // [Lpad][4*NB] exact squared cut-off: ratio > cutoff <=> d^2 > q64
+    const double* acoef;    // [Lpad][4*NB] steepness*log2(e)/site_vert_dist
+    const uint8_t* nverts;  // [Lpad]
+    const uint16_t* orig_of;// [Lpad] internal landmark number -> the caller's landmark index
+};
+
+// Host-side image of the tables (sitb_tables.cu: build_landmark_tables).  Landmarks are renumbered
+// internally (sorted by first vertex); every output is mapped back through orig_of.
+struct HostTables {
+    std::vector<uint16_t> v0;
+    std::vector<float> b0;
+    std::vector<ushort4> va;
+    std::vector<float4> ba;
+    std::vector<double> q64, acoef;
+    std::vector<uint8_t> nverts;
+    std::vector<uint16_t> orig_of;
+    std::vector<int> internal_of;   // [L] caller's index -> internal
+};
 
 struct FillParams {
     Cell cell;
@@ -26,14 +55,11 @@ struct FillParams {
     const long long* frame_list; // optional: process these frame indices only
     long long n_work;            // frames (or list entries) in this launch
     long long frame0;            // global index of frames[0]: row ids / error keys are global
-    int A, S, M, L, V, Lpad;
+    int A, S, M, L, V, Lpad, NB;
     const int* static_idx;       // [S] atom index of static lattice atom s
     const int* mobile_idx;       // [M]
     const double* ideal;         // [S][3] ideal static positions
-    const uint16_t* verts;       // [V][Lpad] vertex table, SoA, VERT_END terminated
-    const float* qf;             // [V][Lpad] float(Q): squared-distance cut-off, rounded
-    const double* q64;           // [V][Lpad] Q exact: ratio > cutoff  <=>  d^2 > Q
-    const double* acoef;         // [V][Lpad] steepness*log2(e)/site_vert_dist
+    LandmarkTables tab;
     double bcoef;                // steepness*log2(e)*midpoint
     double static_thr;           // static_movement_threshold
     int dynamic, relaxed;
@@ -44,13 +70,13 @@ struct FillParams {
     int dense_f64;
     // MODE_STATS / MODE_STAGE
     unsigned long long* seen;    // [L]
-    double* gram;                // [L][L] upper+lower filled
+    double* gram;                // [L][L] upper triangle (+=)
     __half* stage_hi;            // [Lpad][stage_ld]  (landmark-major: K-major operand for UMMA)
     __half* stage_lo;
     long long stage_ld;
     // MODE_ASSIGN
-    const int* cid;              // [L] cluster of landmark, -1 none
-    const float* cw;             // [L] centre weight of landmark
+    const int* cid;              // [L] cluster of landmark (internal numbering), -1 none
+    const float* cw;             // [L] centre weight of landmark (internal numbering)
     int n_clusters;
     float assign_thr;
     long long* labels;           // [n_work*M] int64, -1 unknown

@@ -8,31 +8,45 @@
 // The test is turned into a compare on the squared distance: with IEEE sqrt and divide both
 // monotone, there is a largest double T with T/svd <= cutoff and a largest double Q with
 // sqrt(Q) <= T; then  sqrt(q)/svd > cutoff  <=>  q > Q  for every double q, bit for bit.
+//
+// The device computes svd and Q per (landmark, vertex) in the reference's order; the host then
+// lays the kernel tables out (build_landmark_tables): landmarks are renumbered so that those
+// sharing a first vertex are adjacent (the first-vertex gather in K1 then hits one or two
+// shared-memory words per warp instead of 32 random ones), each landmark's tightest vertex is
+// tested first, and missing vertices become the always-passing dummy vertex S.
 #include "sitb_fill.cuh"
 #include <math_constants.h>
+#include <algorithm>
+#include <cmath>
+#include <limits>
+#include <numeric>
+#include <vector>
 
 namespace sitb {
 
+__device__ double exact_q_cutoff(double svd, double cutoff) {
+    double t = __dmul_rn(cutoff, svd);
+    for (int it = 0; it < 64 && __ddiv_rn(t, svd) > cutoff; ++it) t = nextafter(t, 0.0);
+    for (int it = 0; it < 64 && __ddiv_rn(nextafter(t, CUDART_INF), svd) <= cutoff; ++it) t = nextafter(t, CUDART_INF);
+    double Q = __dmul_rn(t, t);
+    for (int it = 0; it < 64 && __dsqrt_rn(Q) > t; ++it) Q = nextafter(Q, 0.0);
+    for (int it = 0; it < 64 && __dsqrt_rn(nextafter(Q, CUDART_INF)) <= t; ++it) Q = nextafter(Q, CUDART_INF);
+    return Q;
+}
+
+// svd_out[L][V] (NaN padded) and q_out[L][V] (+inf padded), both in the reference's layout
 __global__ void k_tables(Cell cell, const double* __restrict__ centers, const double* __restrict__ ideal,
-                         const int* __restrict__ verts_in, int L, int V, int Lpad, int S, double cutoff,
-                         double steep_log2e, double* __restrict__ svd_out, uint16_t* __restrict__ verts,
-                         float* __restrict__ qf, double* __restrict__ q64, double* __restrict__ acoef) {
+                         const int* __restrict__ verts_in, int L, int V, int S, double cutoff,
+                         double* __restrict__ svd_out, double* __restrict__ q_out) {
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= V * Lpad) return;
-    const int h = idx / Lpad, k = idx % Lpad;
-    int v = -1;
-    if (k < L) {
-        v = verts_in[k * V + h];
-        // the reference stops at the first -1 (helpers.pyx:192-193)
-        for (int hh = 0; hh < h; ++hh)
-            if (verts_in[k * V + hh] < 0) v = -1;
-    }
+    if (idx >= L * V) return;
+    const int k = idx / V, h = idx - k * V;
+    int v = verts_in[idx];
+    for (int hh = 0; hh < h; ++hh)
+        if (verts_in[k * V + hh] < 0) v = -1;       // the reference stops at the first -1 (helpers.pyx:192-193)
     if (v < 0 || v >= S) {
-        verts[idx] = VERT_END;
-        qf[idx] = CUDART_INF_F;
-        q64[idx] = CUDART_INF;
-        acoef[idx] = 0.0;
-        if (k < L) svd_out[k * V + h] = CUDART_NAN;
+        svd_out[idx] = CUDART_NAN;
+        q_out[idx] = CUDART_INF;
         return;
     }
     const double ox = __dsub_rn(cell.cen[0], centers[3 * k + 0]);
@@ -42,32 +56,93 @@ __global__ void k_tables(Cell cell, const double* __restrict__ centers, const do
         ? shifted_dist2<true, false>(cell, ideal[3 * v], ideal[3 * v + 1], ideal[3 * v + 2], ox, oy, oz)
         : shifted_dist2<false, false>(cell, ideal[3 * v], ideal[3 * v + 1], ideal[3 * v + 2], ox, oy, oz);
     const double svd = __dsqrt_rn(q);
-    svd_out[k * V + h] = svd;
-    verts[idx] = (uint16_t)v;
-    double Q;
-    if (!(svd > 0.0) || !(cutoff > 0.0)) {
-        Q = -1.0;                       // degenerate landmark: every ratio is inf/nan -> never counted
-        acoef[idx] = 0.0;
-    } else {
-        double t = __dmul_rn(cutoff, svd);
-        for (int it = 0; it < 64 && __ddiv_rn(t, svd) > cutoff; ++it) t = nextafter(t, 0.0);
-        for (int it = 0; it < 64 && __ddiv_rn(nextafter(t, CUDART_INF), svd) <= cutoff; ++it) t = nextafter(t, CUDART_INF);
-        Q = __dmul_rn(t, t);
-        for (int it = 0; it < 64 && __dsqrt_rn(Q) > t; ++it) Q = nextafter(Q, 0.0);
-        for (int it = 0; it < 64 && __dsqrt_rn(nextafter(Q, CUDART_INF)) <= t; ++it) Q = nextafter(Q, CUDART_INF);
-        acoef[idx] = steep_log2e / svd;
-    }
-    q64[idx] = Q;
-    qf[idx] = __double2float_rn(Q);
+    svd_out[idx] = svd;
+    // degenerate landmark (centre on a vertex): every ratio is inf/nan -> never counted
+    q_out[idx] = (svd > 0.0 && cutoff > 0.0) ? exact_q_cutoff(svd, cutoff) : -1.0;
 }
 
 cudaError_t launch_tables(const Cell& cell, const double* centers, const double* ideal, const int* verts_in, int L,
-                          int V, int Lpad, int S, double cutoff, double steep_log2e, double* svd_out,
-                          uint16_t* verts, float* qf, double* q64, double* acoef, cudaStream_t stream) {
-    const int n = V * Lpad;
-    k_tables<<<(n + 127) / 128, 128, 0, stream>>>(cell, centers, ideal, verts_in, L, V, Lpad, S, cutoff, steep_log2e,
-                                                 svd_out, verts, qf, q64, acoef);
+                          int V, int S, double cutoff, double* svd_out, double* q_out, cudaStream_t stream) {
+    const int n = L * V;
+    k_tables<<<(n + 127) / 128, 128, 0, stream>>>(cell, centers, ideal, verts_in, L, V, S, cutoff, svd_out, q_out);
     return cudaGetLastError();
+}
+
+// Float screen bound (sitb_fill.cu steps 3a-3c).  Orthorhombic cells: the screen distance is
+// computed in FP32 from float fractional coordinates as |(u - round(u)) * L|^2; each Cartesian
+// component is then off by at most ~1.8e-7 * L (two float conversions, one subtract, one
+// multiply); we allow 24 * 2^-24 * Lmax = 1.4e-6 * Lmax, i.e. 8x that, and bound the effect on
+// the squared distance at the cut-off.  Triclinic cells: the screen value is the exact double
+// rounded to float, and rounding is monotone, so float(Q) itself is the bound.
+static float screen_bound(const Cell& cell, double Q) {
+    if (!(Q > 0.0)) return -1.0f;
+    if (std::isinf(Q)) return std::numeric_limits<float>::infinity();
+    if (cell.diag) {
+        const double lmax = std::max(std::fabs(cell.c[0]), std::max(std::fabs(cell.c[4]), std::fabs(cell.c[8])));
+        const double dc = 24.0 * 5.9604644775390625e-08 * lmax;
+        const double marg = 2.0 * std::sqrt(3.0 * Q) * dc + 3.0 * dc * dc + 8.0 * 5.9604644775390625e-08 * Q;
+        return std::nextafter((float)(Q + marg), std::numeric_limits<float>::infinity());
+    }
+    return (float)Q;    // round to nearest
+}
+
+void build_landmark_tables(const Cell& cell, int L, int V, int Lpad, int NB, int S, double steep_log2e,
+                           const int* verts_in, const double* svd, const double* q, HostTables& out) {
+    const int W = 4 * NB;
+    // vertex order per landmark: tightest cut-off first, the rest in the reference's order
+    std::vector<int> nv(L), first(L);
+    for (int k = 0; k < L; ++k) {
+        int n = 0;
+        while (n < V && verts_in[(size_t)k * V + n] >= 0 && verts_in[(size_t)k * V + n] < S) ++n;
+        nv[k] = n;
+        int best = 0;
+        for (int h = 1; h < n; ++h)
+            if (q[(size_t)k * V + h] < q[(size_t)k * V + best]) best = h;
+        first[k] = best;
+    }
+    // renumber: by first-vertex atom, then by original index
+    std::vector<int> order(L);
+    std::iota(order.begin(), order.end(), 0);
+    std::stable_sort(order.begin(), order.end(), [&](int a, int b) {
+        return verts_in[(size_t)a * V + first[a]] < verts_in[(size_t)b * V + first[b]];
+    });
+    out.v0.assign(Lpad, (uint16_t)S);
+    out.b0.assign(Lpad, -1.0f);
+    out.va.assign((size_t)NB * Lpad, make_ushort4((uint16_t)S, (uint16_t)S, (uint16_t)S, (uint16_t)S));
+    const float inf = std::numeric_limits<float>::infinity();
+    out.ba.assign((size_t)NB * Lpad, make_float4(inf, inf, inf, inf));
+    out.q64.assign((size_t)Lpad * W, std::numeric_limits<double>::infinity());
+    out.acoef.assign((size_t)Lpad * W, 0.0);
+    out.nverts.assign(Lpad, 0);
+    out.orig_of.assign(Lpad, 0);
+    out.internal_of.assign(L, 0);
+    for (int ki = 0; ki < L; ++ki) {
+        const int k = order[ki];
+        out.orig_of[ki] = (uint16_t)k;
+        out.internal_of[k] = ki;
+        out.nverts[ki] = (uint8_t)nv[k];
+        uint16_t vs[MAX_VERTS];
+        float bs[MAX_VERTS];
+        for (int h = 0; h < W; ++h) { vs[h] = (uint16_t)S; bs[h] = inf; }
+        int slot = 0;
+        for (int pass = 0; pass < 2; ++pass) {
+            for (int h = 0; h < nv[k]; ++h) {
+                if ((pass == 0) != (h == first[k])) continue;
+                const double Q = q[(size_t)k * V + h], sv = svd[(size_t)k * V + h];
+                vs[slot] = (uint16_t)verts_in[(size_t)k * V + h];
+                bs[slot] = screen_bound(cell, Q);
+                out.q64[(size_t)ki * W + slot] = Q;
+                out.acoef[(size_t)ki * W + slot] = (sv > 0.0) ? steep_log2e / sv : 0.0;
+                ++slot;
+            }
+        }
+        out.v0[ki] = vs[0];
+        out.b0[ki] = (nv[k] > 0) ? bs[0] : -1.0f;
+        for (int blk = 0; blk < NB; ++blk) {
+            out.va[(size_t)blk * Lpad + ki] = make_ushort4(vs[4 * blk], vs[4 * blk + 1], vs[4 * blk + 2], vs[4 * blk + 3]);
+            out.ba[(size_t)blk * Lpad + ki] = make_float4(bs[4 * blk], bs[4 * blk + 1], bs[4 * blk + 2], bs[4 * blk + 3]);
+        }
+    }
 }
 
 }  // namespace sitb

@@ -32,7 +32,7 @@ class EngineStatus(object):
         self.n_duplicate_nearest = int(s.n_duplicate_nearest)
         self.n_list_overflow = int(s.n_list_overflow)
         self.nnz = int(s.nnz)
-        self.n_float_ties = int(s.n_float_ties)
+        self.n_screen_rejects = int(s.n_screen_rejects)
 
     def first_error(self, check_for_zeros):
         """(code, frame, index) of the first error in the reference's iteration order, or None."""
