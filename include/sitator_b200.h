@@ -109,20 +109,78 @@ int sitb_pass_stats(sitb_ctx* ctx, int64_t frame_begin, int64_t n, uint64_t* dev
 
 /* Cluster centres (cluster/mcl.py:70-96): centres have disjoint supports, so they are given as a
  * landmark -> cluster map (-1 none) and a landmark weight. */
-int sitb_set_centers(sitb_ctx* ctx, const int32_t* host_cluster_of_landmark, const float* host_weight,
+int sitb_set_centers(sitb_ctx* ctx, const int32_t* host_cluster_of_landmark, const double* host_weight,
                      int32_t n_clusters);
 
 /* DotProdClassifier.predict (DotProdClassifier.pyx:129-197, predict_normed=False) fused with the fill.
  * Any output pointer may be NULL.
  *   dev_labels[n*M] int64 (-1 unassigned), dev_confs[n*M] float64,
  *   dev_counts[C] += bincount(labels)                              (DotProdClassifier.pyx:92)
- *   dev_best[C]   = max over rows of key(|centre.x|, first row)    (cluster/mcl.py:81-83)
+ *   dev_best[3C]  = max over rows of (|centre.x|, first row)       (cluster/mcl.py:81-83)
  *   dev_rep[C][L] += conf * lvec, dev_rep_w[C] += conf             (cluster/mcl.py:118-122)
- *   dev_site_best[C] = max over rows of key(conf, first row)       (PBCCalculator.pyx:120-122 via LandmarkAnalysis.py:285)
- * key = (float bits << 32) | (0xFFFFFFFF - global row). */
-int sitb_pass_assign(sitb_ctx* ctx, int64_t frame_begin, int64_t n, float threshold, int64_t* dev_labels,
+ *   dev_site_best[3C] = max over rows of (conf, first row)         (PBCCalculator.pyx:120-122 via LandmarkAnalysis.py:285)
+ * A "best" table is 3*C uint64: [0,C) the value as float64 bits, [C,2C) the global row, [2C,3C) lock words;
+ * initialise it to zeros (value 0.0 at row 0 is what np.argmax gives when nothing matches). */
+int sitb_pass_assign(sitb_ctx* ctx, int64_t frame_begin, int64_t n, double threshold, int64_t* dev_labels,
                      double* dev_confs, uint64_t* dev_counts, uint64_t* dev_best, double* dev_rep,
                      double* dev_rep_w, uint64_t* dev_site_best);
+
+/* cluster/mcl.py:54-59: cov = gram/n_rows, correlation graph clipped at 0 with unit self loops for
+ * never-seen landmarks; dev_gram_upper is the [n][n] upper triangle written by sitb_pass_stats
+ * (or the SYRK), dev_cov and dev_graph are full [n][n] float64 outputs. */
+int sitb_landmark_graph(int device, const double* dev_gram_upper, int32_t n, double n_rows, double* dev_cov,
+                        double* dev_graph, void* cuda_stream);
+
+/* util/mcl.py:3-60 markov_clustering on the device in float64: dev_graph [n][n] (non-zero diagonal) ->
+ * dev_result [n][n] = the converged matrix m2 (attractor rows are read off it by the caller,
+ * util/mcl.py:52-60).  *converged = 0 when iterlimit was reached (the reference raises ValueError). */
+int sitb_markov_clustering(int device, const double* dev_graph, int32_t n, int32_t expansion, double inflation,
+                           double pruning_threshold, int32_t iterlimit, double* dev_result,
+                           int32_t* n_iterations, int32_t* converged, void* cuda_stream);
+
+/* ---- site centres: LandmarkAnalysis.py:276-287 via PBCCalculator.average (PBCCalculator.pyx:106-139) ----
+ * The average is centred on one point per site (the max-confidence row, or the first row when
+ * unweighted); the caller turns those points into offsets = cell centroid - point.
+ *   sitb_wrapped_mobile_rows: wrapped (LandmarkAnalysis.py:182-189) position of global rows -> [n][3]
+ *       (rows outside the resident shard give 0 0 0, so shards can be summed)
+ *   sitb_site_first_rows:     dev_first[s] = min(dev_first[s], first global row with label s)
+ *   sitb_site_accumulate:     dev_sums[s] += (w*x, w*y, w*z, w) of wrap(position + offset[s])
+ *   sitb_site_finish:         centre = wrap(sum/w - offset) */
+int sitb_wrapped_mobile_rows(sitb_ctx* ctx, const int64_t* dev_rows, int32_t n, double* dev_out);
+int sitb_site_first_rows(sitb_ctx* ctx, const int64_t* dev_labels, int32_t n_sites, uint64_t* dev_first);
+int sitb_site_accumulate(sitb_ctx* ctx, const int64_t* dev_labels, const double* dev_confs,
+                         const double* dev_offsets, int32_t n_sites, int32_t weighted, double* dev_sums);
+int sitb_site_finish(sitb_ctx* ctx, const double* dev_sums, const double* dev_offsets, int32_t n_sites,
+                     double* dev_centers);
+
+/* LandmarkAnalysis.py:288-296 (representative-landmark site centres): per site s the periodic average of the
+ * points with dev_weights[s][p] > 0, weighted by them, centred on the max-weight point -> dev_out [n_sites][3] */
+int sitb_weighted_point_average(sitb_ctx* ctx, const double* dev_points, const double* dev_weights,
+                                int32_t n_sites, int32_t n_points, double* dev_out);
+
+/* ---- integer passes over the assignment stream dev_traj [n_frames][n_mobile] int64 (-1 unknown) ----
+ * SiteTrajectory.check_multiple_occupancy (SiteTrajectory.py:205-232):
+ *   dev_out3 += {#(frame,site) holding >1 atom, #assigned atoms, #(frame,site) occupied};
+ *   dev_first_bad = min(frame << 32 | lowest site above max_mobile_per_site) (init all ones). */
+int sitb_check_multiple_occupancy(int device, const int64_t* dev_traj, int64_t n_frames, int32_t n_mobile,
+                                  int64_t frame0, int32_t max_mobile_per_site, uint64_t* dev_out3,
+                                  uint64_t* dev_first_bad, void* cuda_stream);
+/* SiteTrajectory._jumped_generator (SiteTrajectory.py:353-373): dev_from[f][a] = site left at frame f,
+ * -2 where the atom did not jump; *dev_total += number of jumps.  dev_carry_in [n_mobile] (may be NULL)
+ * is the last known site of each atom before this shard (unknown_as_jump: the previous frame's row). */
+int sitb_jump_scan(int device, const int64_t* dev_traj, int64_t n_frames, int32_t n_mobile,
+                   int32_t unknown_as_jump, int32_t first_frame_is_start, const int64_t* dev_carry_in,
+                   int32_t* dev_from, uint64_t* dev_total, void* cuda_stream);
+/* SiteTrajectory.jumps (SiteTrajectory.py:307-329): ordered list of (frame, atom, from, to) int64 rows */
+int sitb_jump_compact(int device, const int64_t* dev_traj, const int32_t* dev_from, int64_t n_frames,
+                      int32_t n_mobile, int64_t frame0, int64_t* dev_out, uint64_t capacity, void* cuda_stream);
+/* JumpAnalysis.run (dynamics/JumpAnalysis.py:27-135) accumulators, with NumPy's duplicate-index
+ * semantics: dev_n_ij [C][C] f64, dev_total_time [C], dev_lag_sum [C][C] f64, dev_lag_n [C][C], all +=.
+ * Carries (may be NULL): last known site and local frame index of the last jump before this shard. */
+int sitb_jump_analysis(int device, const int64_t* dev_traj, int64_t n_frames, int32_t n_mobile, int32_t n_sites,
+                       int32_t first_frame_is_start, const int64_t* dev_carry_label, const int64_t* dev_carry_jump,
+                       double* dev_n_ij, uint64_t* dev_total_time, double* dev_lag_sum, uint64_t* dev_lag_n,
+                       uint64_t* dev_n_problems, void* cuda_stream);
 
 /* Reference-facing, host buffers in and out: what sitator/landmark/helpers.pyx:12 computes.
  * frames [n_frames][n_atoms][3] float64 -> landmark vectors [n_frames*n_mobile][n_landmarks] float64. */

@@ -57,7 +57,19 @@ SIGNATURES = {
     "sitb_fill_dense_frames": (C.c_int, [_P, _P, C.c_int64, _P, C.c_int32]),
     "sitb_pass_stats": (C.c_int, [_P, C.c_int64, C.c_int64, _P, _P]),
     "sitb_set_centers": (C.c_int, [_P, _P, _P, C.c_int32]),
-    "sitb_pass_assign": (C.c_int, [_P, C.c_int64, C.c_int64, C.c_float] + [_P] * 7),
+    "sitb_pass_assign": (C.c_int, [_P, C.c_int64, C.c_int64, C.c_double] + [_P] * 7),
+    "sitb_landmark_graph": (C.c_int, [C.c_int, _P, C.c_int32, C.c_double, _P, _P, _P]),
+    "sitb_markov_clustering": (C.c_int, [C.c_int, _P, C.c_int32, C.c_int32, C.c_double, C.c_double, C.c_int32, _P,
+                                         C.POINTER(C.c_int32), C.POINTER(C.c_int32), _P]),
+    "sitb_wrapped_mobile_rows": (C.c_int, [_P, _P, C.c_int32, _P]),
+    "sitb_site_first_rows": (C.c_int, [_P, _P, C.c_int32, _P]),
+    "sitb_site_accumulate": (C.c_int, [_P, _P, _P, _P, C.c_int32, C.c_int32, _P]),
+    "sitb_site_finish": (C.c_int, [_P, _P, _P, C.c_int32, _P]),
+    "sitb_weighted_point_average": (C.c_int, [_P, _P, _P, C.c_int32, C.c_int32, _P]),
+    "sitb_check_multiple_occupancy": (C.c_int, [C.c_int, _P, C.c_int64, C.c_int32, C.c_int64, C.c_int32, _P, _P, _P]),
+    "sitb_jump_scan": (C.c_int, [C.c_int, _P, C.c_int64, C.c_int32, C.c_int32, C.c_int32, _P, _P, _P, _P]),
+    "sitb_jump_compact": (C.c_int, [C.c_int, _P, _P, C.c_int64, C.c_int32, C.c_int64, _P, C.c_uint64, _P]),
+    "sitb_jump_analysis": (C.c_int, [C.c_int, _P, C.c_int64, C.c_int32, C.c_int32, C.c_int32] + [_P] * 8),
     "sitb_fill_landmark_vectors_host": (C.c_int, [_P, _P, C.c_int64, _P, C.POINTER(Status)]),
 }
 

@@ -28,6 +28,16 @@ static int fail(int code, const char* fmt, ...) {
     return code;
 }
 
+namespace sitb {
+int set_error(int code, const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+}  // namespace sitb
+
 #define CK(call)                                                                                   \
     do {                                                                                           \
         cudaError_t e_ = (call);                                                                   \
@@ -63,7 +73,7 @@ struct sitb_ctx {
     uint8_t* d_nverts = nullptr;
     // centres
     int* d_cid = nullptr;
-    float* d_cw = nullptr;
+    double* d_cw = nullptr;
     int n_clusters = 0;
     // frames
     const double* d_frames = nullptr;
@@ -164,9 +174,8 @@ extern "C" int sitb_create(const sitb_network_desc* d, int device, sitb_ctx** ou
                                               : d->cutoff_midpoint + std::log((1.0 / 0.0001) - 1.0) / d->cutoff_steepness;
     c->static_thr = d->static_movement_threshold;
     c->dynamic = d->dynamic_lattice_mapping; c->relaxed = d->relaxed_lattice_checks;
-    const double log2e = 1.4426950408889634074;
-    const double steep_log2e = c->steepness * log2e;
-    c->bcoef = steep_log2e * c->midpoint;
+    const double steep_log2e = c->steepness;          // natural-exponent units (values are evaluated in double)
+    c->bcoef = c->steepness * c->midpoint;
 
     const size_t LV = (size_t)c->L * c->V;
 #define CKC(call)                                                                          \
@@ -185,9 +194,9 @@ extern "C" int sitb_create(const sitb_network_desc* d, int device, sitb_ctx** ou
     CKC(cudaMalloc((void**)&c->d_svd, sizeof(double) * LV));
     CKC(cudaMalloc((void**)&c->d_qorig, sizeof(double) * LV));
     CKC(cudaMalloc((void**)&c->d_cid, sizeof(int) * (size_t)c->L));
-    CKC(cudaMalloc((void**)&c->d_cw, sizeof(float) * (size_t)c->L));
+    CKC(cudaMalloc((void**)&c->d_cw, sizeof(double) * (size_t)c->L));
     CKC(cudaMemset(c->d_cid, 0xFF, sizeof(int) * (size_t)c->L));
-    CKC(cudaMemset(c->d_cw, 0, sizeof(float) * (size_t)c->L));
+    CKC(cudaMemset(c->d_cw, 0, sizeof(double) * (size_t)c->L));
     CKC(cudaMalloc((void**)&c->d_status, sizeof(unsigned long long) * (2 + CNT_SLOTS)));
     CKC(launch_tables(c->cell, c->d_centers, c->d_ideal, c->d_verts_in, c->L, c->V, c->S, c->cutoff, c->d_svd,
                       c->d_qorig, 0));
@@ -358,23 +367,23 @@ extern "C" int sitb_pass_stats(sitb_ctx* c, int64_t begin, int64_t n, uint64_t* 
     return SITB_OK;
 }
 
-extern "C" int sitb_set_centers(sitb_ctx* c, const int32_t* cid, const float* w, int32_t n_clusters) {
+extern "C" int sitb_set_centers(sitb_ctx* c, const int32_t* cid, const double* w, int32_t n_clusters) {
     if (!c || !cid || !w) return fail(SITB_E_INVALID, "sitb_set_centers: null argument");
     if (n_clusters < 0 || n_clusters > 32767) return fail(SITB_E_LIMIT, "sitb_set_centers: %d clusters (limit 32767)", n_clusters);
     for (int k = 0; k < c->L; ++k)
         if (cid[k] < -1 || cid[k] >= n_clusters) return fail(SITB_E_INVALID, "sitb_set_centers: cluster id %d of landmark %d out of range", cid[k], k);
     CK(cudaSetDevice(c->device));
     std::vector<int> cid_i((size_t)c->L);
-    std::vector<float> w_i((size_t)c->L);
+    std::vector<double> w_i((size_t)c->L);
     for (int k = 0; k < c->L; ++k) { cid_i[c->internal_of[k]] = cid[k]; w_i[c->internal_of[k]] = w[k]; }
     CK(cudaMemcpyAsync(c->d_cid, cid_i.data(), sizeof(int) * (size_t)c->L, cudaMemcpyHostToDevice, c->stream));
-    CK(cudaMemcpyAsync(c->d_cw, w_i.data(), sizeof(float) * (size_t)c->L, cudaMemcpyHostToDevice, c->stream));
+    CK(cudaMemcpyAsync(c->d_cw, w_i.data(), sizeof(double) * (size_t)c->L, cudaMemcpyHostToDevice, c->stream));
     CK(cudaStreamSynchronize(c->stream));
     c->n_clusters = n_clusters;
     return SITB_OK;
 }
 
-extern "C" int sitb_pass_assign(sitb_ctx* c, int64_t begin, int64_t n, float thr, int64_t* labels, double* confs,
+extern "C" int sitb_pass_assign(sitb_ctx* c, int64_t begin, int64_t n, double thr, int64_t* labels, double* confs,
                                 uint64_t* counts, uint64_t* best, double* rep, double* rep_w, uint64_t* site_best) {
     FillParams p;
     int rc = base_params(c, begin, n, p, "sitb_pass_assign");
@@ -422,5 +431,71 @@ extern "C" int sitb_fill_landmark_vectors_host(sitb_ctx* c, const double* host_f
     cudaFree(d_in); cudaFree(d_out);
     if (rc) return rc;
     if (status) return sitb_get_status(c, status);
+    return SITB_OK;
+}
+
+// ---- site centres (LandmarkAnalysis.py:276-287, PBCCalculator.pyx:106-139) -----------------------
+namespace sitb {
+cudaError_t launch_wrapped_rows(const Cell& cell, const double* frames, int A, int M, const int* mobile_idx,
+                                long long frame0, long long n_frames, const long long* rows, int n, double* out,
+                                cudaStream_t st);
+cudaError_t launch_site_accumulate(const Cell& cell, const double* frames, int A, int M, const int* mobile_idx,
+                                   long long n_frames, const long long* labels, const double* confs,
+                                   const double* offset, int C, int weighted, double* sums, int n_sms, cudaStream_t st);
+cudaError_t launch_site_finish(const Cell& cell, const double* sums, const double* offset, int C, double* centers,
+                               cudaStream_t st);
+cudaError_t launch_first_row(const long long* labels, long long n, long long row0, int C, unsigned long long* first,
+                             int n_sms, cudaStream_t st);
+}
+
+extern "C" int sitb_wrapped_mobile_rows(sitb_ctx* c, const int64_t* dev_rows, int32_t n, double* dev_out) {
+    if (!c || !dev_rows || !dev_out || n < 0) return fail(SITB_E_INVALID, "sitb_wrapped_mobile_rows: bad argument");
+    if (!c->d_frames) return fail(SITB_E_STATE, "sitb_wrapped_mobile_rows: no frames resident");
+    CK(cudaSetDevice(c->device));
+    CK(launch_wrapped_rows(c->cell, c->d_frames, c->A, c->M, c->d_mobile_idx, c->frame0, c->n_frames,
+                           (const long long*)dev_rows, n, dev_out, c->stream));
+    return SITB_OK;
+}
+
+extern "C" int sitb_site_first_rows(sitb_ctx* c, const int64_t* dev_labels, int32_t n_sites, uint64_t* dev_first) {
+    if (!c || !dev_labels || !dev_first || n_sites <= 0) return fail(SITB_E_INVALID, "sitb_site_first_rows: bad argument");
+    CK(cudaSetDevice(c->device));
+    CK(launch_first_row((const long long*)dev_labels, c->n_frames * c->M, c->frame0 * c->M, n_sites,
+                        (unsigned long long*)dev_first, c->n_sms, c->stream));
+    return SITB_OK;
+}
+
+extern "C" int sitb_site_accumulate(sitb_ctx* c, const int64_t* dev_labels, const double* dev_confs,
+                                    const double* dev_offsets, int32_t n_sites, int32_t weighted, double* dev_sums) {
+    if (!c || !dev_labels || !dev_offsets || !dev_sums || n_sites <= 0 || (weighted && !dev_confs))
+        return fail(SITB_E_INVALID, "sitb_site_accumulate: bad argument");
+    if (!c->d_frames) return fail(SITB_E_STATE, "sitb_site_accumulate: no frames resident");
+    CK(cudaSetDevice(c->device));
+    CK(launch_site_accumulate(c->cell, c->d_frames, c->A, c->M, c->d_mobile_idx, c->n_frames,
+                              (const long long*)dev_labels, dev_confs, dev_offsets, n_sites, weighted, dev_sums,
+                              c->n_sms, c->stream));
+    return SITB_OK;
+}
+
+extern "C" int sitb_site_finish(sitb_ctx* c, const double* dev_sums, const double* dev_offsets, int32_t n_sites,
+                                double* dev_centers) {
+    if (!c || !dev_sums || !dev_offsets || !dev_centers || n_sites <= 0)
+        return fail(SITB_E_INVALID, "sitb_site_finish: bad argument");
+    CK(cudaSetDevice(c->device));
+    CK(launch_site_finish(c->cell, dev_sums, dev_offsets, n_sites, dev_centers, c->stream));
+    return SITB_OK;
+}
+
+namespace sitb {
+cudaError_t launch_weighted_point_average(const Cell& cell, const double* pts, const double* w, int C, int P,
+                                          double* out, cudaStream_t st);
+}
+
+extern "C" int sitb_weighted_point_average(sitb_ctx* c, const double* dev_points, const double* dev_weights,
+                                           int32_t n_sites, int32_t n_points, double* dev_out) {
+    if (!c || !dev_points || !dev_weights || !dev_out || n_sites <= 0 || n_points <= 0)
+        return fail(SITB_E_INVALID, "sitb_weighted_point_average: bad argument");
+    CK(cudaSetDevice(c->device));
+    CK(launch_weighted_point_average(c->cell, dev_points, dev_weights, n_sites, n_points, dev_out, c->stream));
     return SITB_OK;
 }

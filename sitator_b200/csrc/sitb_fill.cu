@@ -47,19 +47,19 @@ __host__ __device__ inline SmemLayout make_layout(int S, int M, int L, int Lpad,
     l.qstride = l.Spad + 4;     // per-warp screen distances + the dummy vertex slot [S]
     size_t o = 0;
     l.off_ss = o;    o += sizeof(double) * 3 * (size_t)S * fb;
+    l.off_wev = o;   o += sizeof(double) * (size_t)warps * ENTRY_CAP;
+    l.off_cw = o;    o += (mode == MODE_ASSIGN) ? sizeof(double) * (size_t)Lpad : 0;
     l.off_sm = o;    o += sizeof(double) * 3 * (size_t)M * fb;
     l.off_ba = o;    o += sizeof(float4) * (size_t)NB * Lpad;
     l.off_b0 = o;    o += sizeof(float) * (size_t)Lpad;
     l.off_fs = o;    o += sizeof(float) * 3 * (size_t)l.Spad * fb;
     l.off_fm = o;    o += sizeof(float) * 3 * (size_t)l.Mpad * fb;
     l.off_wqf = o;   o += sizeof(float) * (size_t)warps * l.qstride;
-    l.off_wev = o;   o += sizeof(float) * (size_t)warps * ENTRY_CAP;
     l.off_hist = o;
     if (mode == MODE_STATS || mode == MODE_STAGE) o += sizeof(unsigned) * (size_t)L;
     if (mode == MODE_ASSIGN) o += sizeof(unsigned) * (size_t)(n_clusters > 0 ? n_clusters : 1);
     l.off_lmap = o;  o += dynamic ? sizeof(unsigned) * (size_t)l.Spad * fb : 0;
     l.off_seen = o;  o += dynamic ? sizeof(unsigned) * (size_t)l.Spad * fb : 0;
-    l.off_cw = o;    o += (mode == MODE_ASSIGN) ? sizeof(float) * (size_t)Lpad : 0;
     o = (o + 7) & ~(size_t)7;
     l.off_va = o;    o += sizeof(ushort4) * (size_t)NB * Lpad;
     l.off_v0 = o;    o += sizeof(uint16_t) * (size_t)Lpad;
@@ -72,55 +72,34 @@ __host__ __device__ inline SmemLayout make_layout(int S, int M, int L, int Lpad,
     return l;
 }
 
-__device__ __forceinline__ unsigned long long pack_key(float v, unsigned long long row) {
-    return ((unsigned long long)__float_as_uint(v) << 32) | (unsigned long long)(0xFFFFFFFFu - (unsigned)row);
+// (prod of (1 + exp(steep*(d/svd - mid))))^(-1/n): the landmark component (helpers.pyx:205-212) from
+// the product P of the logistic denominators.  Everything in double: values agree with the
+// reference's libm evaluation to ~1e-15, which is what its own argmax-over-rows decisions
+// (cluster/mcl.py:83) need -- near saturation neighbouring rows differ by ~1e-8 only.
+__device__ __forceinline__ double inv_root(double P, int nv) {
+    switch (nv) {
+        case 1: return 1.0 / P;
+        case 2: return 1.0 / sqrt(P);
+        case 3: return 1.0 / cbrt(P);
+        case 4: return 1.0 / sqrt(sqrt(P));
+        default: return pow(P, -1.0 / (double)nv);
+    }
 }
 
-__device__ __forceinline__ void atomic_max_checked(unsigned long long* addr, unsigned long long key) {
-    // monotone non-decreasing cell: a stale read can only under-estimate, so the check is safe
-    if (key > *((volatile unsigned long long*)addr)) atomicMax(addr, key);
+// lock-protected lexicographic max of (value, first row): slot layout [C] value bits | [C] row | [C] lock
+__device__ __forceinline__ void best_update(unsigned long long* tab, int C, int c, double v, unsigned long long row) {
+    const unsigned long long vb = (unsigned long long)__double_as_longlong(v);     // v >= 0: bits are monotone
+    volatile unsigned long long* val = tab + c;
+    volatile unsigned long long* rw = tab + C + c;
+    if (vb < *val) return;                                  // values only grow: a stale read can only let us in
+    unsigned* lock = (unsigned*)(tab + 2 * (size_t)C + c);
+    while (atomicCAS(lock, 0u, 1u) != 0u) {}
+    __threadfence();
+    const unsigned long long cv = *val, cr = *rw;
+    if (vb > cv || (vb == cv && row < cr)) { *val = vb; *rw = row; }
+    __threadfence();
+    atomicExch(lock, 0u);
 }
-
-__device__ __forceinline__ float ex2_approx(float x) {
-    float y;
-    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
-    return y;
-}
-__device__ __forceinline__ float lg2_approx(float x) {
-    float y;
-    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
-    return y;
-}
-__device__ __forceinline__ float rsqrt_approx(float x) {
-    float y;
-    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
-    return y;
-}
-
-// log2(1 + exp(steep*(d/svd - mid))) = -log2 of the logistic cut-off (helpers.pyx:197,205),
-// d = sqrt(q).  The argument is prepared in double (one Newton step on a float rsqrt gives d to
-// ~1e-13; x2 = steep*log2e*(d/svd-mid) by one DFMA; integer/fraction split by the 1.5*2^52
-// trick), the transcendental part runs on the float SFU path.  Relative accuracy ~2e-7.
-__device__ __forceinline__ float cutoff_log2(double q, double acoef, double bcoef) {
-    const float qf = __double2float_rn(q);
-    const float r = rsqrt_approx(qf);
-    const float s0 = (qf > 0.f) ? qf * r : 0.f;
-    const float hr = (qf > 0.f) ? 0.5f * r : 0.f;
-    const double s0d = (double)s0;
-    const double res = fma(-s0d, s0d, q);
-    const double d = fma(res, (double)hr, s0d);
-    const double x2 = fma(d, acoef, -bcoef);
-    const double magic = 6755399441055744.0;             // 1.5 * 2^52
-    const double t = x2 + magic;
-    int n = __double2loint(t);                           // rint(x2)
-    const float fr = __double2float_rn(x2 - (t - magic));
-    n = max(-100, min(n, 120));
-    float e = ex2_approx(fr);
-    e = __int_as_float(__float_as_int(e) + (n << 23));   // e * 2^n, stays a normal float
-    return lg2_approx(1.0f + e);
-}
-
-__constant__ float c_inv_nv[MAX_VERTS + 1] = {0.f, 1.f, 0.5f, 1.f / 3.f, 0.25f, 0.2f, 1.f / 6.f, 1.f / 7.f, 0.125f};
 
 // u - round(u) for |u| < 2^22, two adds
 __device__ __forceinline__ float centre_frac(float u) {
@@ -153,11 +132,11 @@ __global__ void __launch_bounds__(DIAG ? 1024 : 512) k_fill(const __grid_constan
     float* fs = (float*)(smem_raw + lay.off_fs);            // [FB][3][Spad] fractional statics (float, SoA)
     float* fm = (float*)(smem_raw + lay.off_fm);            // [FB][3][Mpad]
     float* qfw = (float*)(smem_raw + lay.off_wqf) + (size_t)warp * lay.qstride;
-    float* ev = (float*)(smem_raw + lay.off_wev) + (size_t)warp * ENTRY_CAP;
+    double* ev = (double*)(smem_raw + lay.off_wev) + (size_t)warp * ENTRY_CAP;
     unsigned* hist = (unsigned*)(smem_raw + lay.off_hist);
     unsigned* lmap_all = (unsigned*)(smem_raw + lay.off_lmap);
     unsigned* seen_all = (unsigned*)(smem_raw + lay.off_seen);
-    float* tcw = (float*)(smem_raw + lay.off_cw);           // [Lpad] centre weight (MODE_ASSIGN)
+    double* tcw = (double*)(smem_raw + lay.off_cw);         // [Lpad] centre weight (MODE_ASSIGN)
     ushort4* tva = (ushort4*)(smem_raw + lay.off_va);       // [NB][Lpad] vertex ids, 4 per block
     uint16_t* tv0 = (uint16_t*)(smem_raw + lay.off_v0);     // [Lpad] vertex 0
     int16_t* tcid = (int16_t*)(smem_raw + lay.off_cid);     // [Lpad] cluster of landmark (MODE_ASSIGN)
@@ -175,7 +154,7 @@ __global__ void __launch_bounds__(DIAG ? 1024 : 512) k_fill(const __grid_constan
         tv0[i] = p.tab.v0[i];
         if (MODE == MODE_ASSIGN) {
             tcid[i] = (i < L) ? (int16_t)p.cid[i] : (int16_t)-1;
-            tcw[i] = (i < L) ? p.cw[i] : 0.f;
+            tcw[i] = (i < L) ? p.cw[i] : 0.0;
         }
     }
     const bool use_hist = (MODE == MODE_STATS || MODE == MODE_STAGE) ||
@@ -390,9 +369,9 @@ __global__ void __launch_bounds__(DIAG ? 1024 : 512) k_fill(const __grid_constan
                 const int i = i0 + lane;
                 bool alive = i < nsurv;
                 const int k = alive ? (int)ek[i] : 0;
-                float val = 0.f;
+                double val = 0.0;
                 if (alive) {
-                    float lsum = 0.f;
+                    double P = 1.0;
                     int nv = 0;
                     for (int blk = 0; blk < NB; ++blk) {
                         const ushort4 vv = tva[(size_t)blk * Lpad + k];
@@ -408,12 +387,13 @@ __global__ void __launch_bounds__(DIAG ? 1024 : 512) k_fill(const __grid_constan
                                 const int src = p.dynamic ? (int)lmap[vs[h]] : (int)vs[h];
                                 const double q = shifted_dist2<DIAG, true>(cell, sb[3 * src], sb[3 * src + 1], sb[3 * src + 2], ox, oy, oz);
                                 if (q > qs[h]) alive = false;                 // helpers.pyx:199-203, exact
-                                lsum += cutoff_log2(q, as[h], p.bcoef);
+                                // 1 + exp(steep*(d/svd - mid))                 helpers.pyx:197,205
+                                P *= 1.0 + exp(fma(__dsqrt_rn(q), as[h], -p.bcoef));
                                 ++nv;
                             }
                         }
                     }
-                    if (alive) val = ex2_approx(-lsum * c_inv_nv[nv]);        // helpers.pyx:212
+                    if (alive) val = inv_root(P, nv);                         // helpers.pyx:212
                     else ++loc_rej;
                 }
                 const unsigned m = __ballot_sync(0xffffffffu, alive);
@@ -438,30 +418,30 @@ __global__ void __launch_bounds__(DIAG ? 1024 : 512) k_fill(const __grid_constan
                 // centres have disjoint supports (cluster/mcl.py:80): dot = sum over the row's
                 // non-zeros of weight[landmark], grouped by cluster[landmark].  A row touches few
                 // clusters: peel them off one at a time with warp votes.
-                float bestc = 0.f;      // untouched clusters have |dot| = 0; np.argmax -> index 0
+                double bestc = 0.0;     // untouched clusters have |dot| = 0; np.argmax -> index 0
                 int bestid = 0;
                 if (nent <= 32) {
                     int myc = -1;
-                    float mypr = 0.f;
+                    double mypr = 0.0;
                     if (lane < nent) { const int k = ek[lane]; myc = tcid[k]; mypr = ev[lane] * tcw[k]; }
                     for (;;) {
                         const int cur = __reduce_min_sync(0xffffffffu, myc >= 0 ? myc : 0x7FFFFFFF);
                         if (cur == 0x7FFFFFFF) break;
-                        float part = (myc == cur) ? mypr : 0.f;
+                        double part = (myc == cur) ? mypr : 0.0;
                         if (myc == cur) myc = -1;
 #pragma unroll
                         for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
-                        const float conf = fabsf(part);
+                        const double conf = fabs(part);
                         if (conf > bestc) { bestc = conf; bestid = cur; }     // ascending ids: ties keep the lower
-                        if (p.best && lane == 0) atomic_max_checked(p.best + cur, pack_key(conf, row_global));
+                        if (p.best && lane == 0) best_update(p.best, p.n_clusters, cur, conf, row_global);
                     }
                 } else {
                     int myc[ENTRY_CAP / 32];
-                    float mypr[ENTRY_CAP / 32];
+                    double mypr[ENTRY_CAP / 32];
 #pragma unroll
                     for (int c = 0; c < ENTRY_CAP / 32; ++c) {
                         const int e = 32 * c + lane;
-                        myc[c] = -1; mypr[c] = 0.f;
+                        myc[c] = -1; mypr[c] = 0.0;
                         if (e < nent) { const int k = ek[e]; myc[c] = tcid[k]; mypr[c] = ev[e] * tcw[k]; }
                     }
                     for (;;) {
@@ -471,32 +451,32 @@ __global__ void __launch_bounds__(DIAG ? 1024 : 512) k_fill(const __grid_constan
                             if (myc[c] >= 0 && myc[c] < mine) mine = myc[c];
                         const int cur = __reduce_min_sync(0xffffffffu, mine);
                         if (cur == 0x7FFFFFFF) break;
-                        float part = 0.f;
+                        double part = 0.0;
 #pragma unroll
                         for (int c = 0; c < ENTRY_CAP / 32; ++c)
                             if (myc[c] == cur) { part += mypr[c]; myc[c] = -1; }
 #pragma unroll
                         for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
-                        const float conf = fabsf(part);
+                        const double conf = fabs(part);
                         if (conf > bestc) { bestc = conf; bestid = cur; }
-                        if (p.best && lane == 0) atomic_max_checked(p.best + cur, pack_key(conf, row_global));
+                        if (p.best && lane == 0) best_update(p.best, p.n_clusters, cur, conf, row_global);
                     }
                 }
                 long long label = bestid;
-                float conf = bestc;
-                if (nent == 0 || !(conf >= p.assign_thr)) { label = -1; conf = 0.f; }   // DotProdClassifier.pyx:168-172,184-186
+                double conf = bestc;
+                if (nent == 0 || !(conf >= p.assign_thr)) { label = -1; conf = 0.0; }   // DotProdClassifier.pyx:168-172,184-186
                 if (lane == 0) {
                     if (p.labels) p.labels[row_local] = label;
-                    if (p.confs) p.confs[row_local] = (double)conf;
+                    if (p.confs) p.confs[row_local] = conf;
                     if (label >= 0) {
                         if (p.counts) atomicAdd(&hist[label], 1u);
-                        if (p.rep_w) atomicAdd(&p.rep_w[label], (double)conf);
-                        if (p.site_best) atomic_max_checked(p.site_best + label, pack_key(conf, row_global));
+                        if (p.rep_w) atomicAdd(&p.rep_w[label], conf);
+                        if (p.site_best) best_update(p.site_best, p.n_clusters, (int)label, conf, row_global);
                     }
                 }
                 if (p.rep && label >= 0) {
                     for (int e = lane; e < nent; e += 32)
-                        atomicAdd(&p.rep[(size_t)label * L + p.tab.orig_of[ek[e]]], (double)conf * (double)ev[e]);
+                        atomicAdd(&p.rep[(size_t)label * L + p.tab.orig_of[ek[e]]], conf * ev[e]);
                 }
             } else {
                 // the other sinks address landmarks by the caller's numbering
@@ -507,29 +487,29 @@ __global__ void __launch_bounds__(DIAG ? 1024 : 512) k_fill(const __grid_constan
                 if (MODE == MODE_DENSE) {
                     if (p.dense_f64) {
                         double* o = (double*)p.dense_out + (size_t)row_local * L;
-                        for (int e = lane; e < nent; e += 32) o[ek[e]] = (double)ev[e];
+                        for (int e = lane; e < nent; e += 32) o[ek[e]] = ev[e];
                     } else {
                         float* o = (float*)p.dense_out + (size_t)row_local * L;
-                        for (int e = lane; e < nent; e += 32) o[ek[e]] = ev[e];
+                        for (int e = lane; e < nent; e += 32) o[ek[e]] = (float)ev[e];
                     }
                 }
                 if (MODE == MODE_STATS) {
                     // upper triangle of the outer product
                     for (int a = 0; a < nent; ++a) {
                         const unsigned ka = ek[a];
-                        const double va = (double)ev[a];
+                        const double va = ev[a];
                         for (int bq = a + lane; bq < nent; bq += 32) {
                             const unsigned kq = ek[bq];
                             const unsigned lo = ka < kq ? ka : kq, hi = ka < kq ? kq : ka;
-                            atomicAdd(&p.gram[(size_t)lo * L + hi], va * (double)ev[bq]);
+                            atomicAdd(&p.gram[(size_t)lo * L + hi], va * ev[bq]);
                         }
                     }
                 }
                 if (MODE == MODE_STAGE) {
                     for (int e = lane; e < nent; e += 32) {
-                        const float v = ev[e];
-                        const __half hi = __float2half_rn(v);
-                        const __half lo = __float2half_rn(v - __half2float(hi));
+                        const double v = ev[e];
+                        const __half hi = __double2half(v);
+                        const __half lo = __double2half(v - (double)__half2float(hi));
                         const size_t o = (size_t)ek[e] * (size_t)p.stage_ld + (size_t)row_local;
                         p.stage_hi[o] = hi;
                         p.stage_lo[o] = lo;

@@ -31,7 +31,7 @@ struct LandmarkTables {
     const ushort4* va;      // [NB][Lpad] vertices 4*blk .. 4*blk+3
     const float4* ba;       // [NB][Lpad] screen bounds (float, including the FP32 error margin)
     const double* q64;      // [Lpad][4*NB] exact squared cut-off: ratio > cutoff <=> d^2 > q64
-    const double* acoef;    // [Lpad][4*NB] steepness*log2(e)/site_vert_dist
+    const double* acoef;    // [Lpad][4*NB] steepness/site_vert_dist
     const uint8_t* nverts;  // [Lpad]
     const uint16_t* orig_of;// [Lpad] internal landmark number -> the caller's landmark index
 };
@@ -60,7 +60,7 @@ struct FillParams {
     const int* mobile_idx;       // [M]
     const double* ideal;         // [S][3] ideal static positions
     LandmarkTables tab;
-    double bcoef;                // steepness*log2(e)*midpoint
+    double bcoef;                // steepness*midpoint
     double static_thr;           // static_movement_threshold
     int dynamic, relaxed;
     unsigned long long* errkey;  // [2] atomicMin of make_error_key: [0] lattice errors, [1] zero landmark vectors
@@ -76,16 +76,16 @@ struct FillParams {
     long long stage_ld;
     // MODE_ASSIGN
     const int* cid;              // [L] cluster of landmark (internal numbering), -1 none
-    const float* cw;             // [L] centre weight of landmark (internal numbering)
+    const double* cw;            // [L] centre weight of landmark (internal numbering)
     int n_clusters;
-    float assign_thr;
+    double assign_thr;
     long long* labels;           // [n_work*M] int64, -1 unknown
     double* confs;               // [n_work*M]
     unsigned long long* counts;  // [C] optional bincount of labels
-    unsigned long long* best;    // [C] optional max over rows of (|dot| bits << 32 | ~row)
+    unsigned long long* best;    // [3C] optional max over rows of (|dot|, first row): value bits | row | lock
     double* rep;                 // [C][L] optional sum conf*lvec
     double* rep_w;               // [C]
-    unsigned long long* site_best; // [C] optional max over rows of (conf bits << 32 | ~row)
+    unsigned long long* site_best; // [3C] optional max over rows of (conf, first row), same layout
 };
 
 cudaError_t launch_fill(const FillParams& p, int mode, int n_sms, cudaStream_t stream);

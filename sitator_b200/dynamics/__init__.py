@@ -1,0 +1,1 @@
+from .JumpAnalysis import JumpAnalysis

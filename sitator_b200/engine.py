@@ -215,7 +215,7 @@ class LandmarkEngine(object):
 
     def set_centers(self, cluster_of_landmark, weight, n_clusters):
         cid = np.ascontiguousarray(cluster_of_landmark, dtype=np.int32)
-        w = np.ascontiguousarray(weight, dtype=np.float32)
+        w = np.ascontiguousarray(weight, dtype=np.float64)
         assert cid.shape == (self.L,) and w.shape == (self.L,)
         _native.check(self._lib.sitb_set_centers(self._ctx, cid.ctypes.data, w.ctypes.data, int(n_clusters)))
         self.n_clusters = int(n_clusters)
@@ -226,6 +226,53 @@ class LandmarkEngine(object):
         _native.check(self._lib.sitb_pass_assign(
             self._ctx, begin, n, float(threshold), self._ptr(labels), self._ptr(confs), self._ptr(counts),
             self._ptr(best), self._ptr(rep), self._ptr(rep_w), self._ptr(site_best)))
+
+    # ---- site centres (LandmarkAnalysis.py:276-299) -------------------------------------------------
+    def wrapped_mobile_rows(self, global_rows):
+        """(n, 3) wrapped positions of the given global (frame * M + mobile) rows; zeros where not resident."""
+        torch = _torch()
+        rows = torch.as_tensor(np.asarray(global_rows, dtype=np.int64), device=self.device)
+        out = self._empty((len(rows), 3), torch.float64)
+        _native.check(self._lib.sitb_wrapped_mobile_rows(self._ctx, self._ptr(rows), len(rows), self._ptr(out)))
+        return out
+
+    def site_centers(self, labels, confs, n_sites, weighted, site_best=None, comm=None):
+        """PBCCalculator.average (PBCCalculator.pyx:106-139) of the wrapped mobile positions assigned to
+        each site: (n_sites, 3) float64 numpy."""
+        torch = _torch()
+        if weighted:
+            # centring point = the max-confidence row, first maximum (np.argmax, PBCCalculator.pyx:120-122)
+            assert site_best is not None
+            _, anchor_rows = read_best_table(site_best, comm)
+        else:
+            first = torch.full((n_sites,), -1, dtype=torch.int64, device=self.device)     # all ones
+            _native.check(self._lib.sitb_site_first_rows(self._ctx, self._ptr(labels), n_sites, self._ptr(first)))
+            if comm is not None:
+                comm.allreduce_min_u64_(first)
+            anchor_rows = first.cpu().numpy().view(np.uint64).astype(np.int64)
+        anchors = self.wrapped_mobile_rows(anchor_rows)
+        if comm is not None:
+            comm.allreduce_sum_(anchors)
+        centroid = torch.as_tensor(self.cell_centroid, device=self.device)
+        offsets = (centroid[None, :] - anchors).contiguous()
+        sums = self._zeros((n_sites, 4), torch.float64)
+        _native.check(self._lib.sitb_site_accumulate(self._ctx, self._ptr(labels), self._ptr(confs),
+                                                     self._ptr(offsets), n_sites, int(bool(weighted)), self._ptr(sums)))
+        if comm is not None:
+            comm.allreduce_sum_(sums)
+        out = self._empty((n_sites, 3), torch.float64)
+        _native.check(self._lib.sitb_site_finish(self._ctx, self._ptr(sums), self._ptr(offsets), n_sites, self._ptr(out)))
+        return out.cpu().numpy()
+
+    def weighted_point_averages(self, points, weights):
+        """Per row of ``weights`` (n_sites, n_points): periodic weighted average of ``points`` with weight > 0."""
+        torch = _torch()
+        pts = torch.as_tensor(np.ascontiguousarray(points, dtype=np.float64), device=self.device)
+        w = torch.as_tensor(np.ascontiguousarray(weights, dtype=np.float64), device=self.device)
+        out = self._empty((w.shape[0], 3), torch.float64)
+        _native.check(self._lib.sitb_weighted_point_average(self._ctx, self._ptr(pts), self._ptr(w), w.shape[0],
+                                                            w.shape[1], self._ptr(out)))
+        return out.cpu().numpy()
 
     def fill_landmark_vectors_host(self, frames):
         """Host in, host out: the drop-in for ``helpers._fill_landmark_vectors`` (helpers.pyx:12)."""
@@ -239,14 +286,21 @@ class LandmarkEngine(object):
         return out, EngineStatus(s)
 
 
-def unpack_key(keys):
-    """Split the (value bits << 32 | ~row) keys written by the assign pass: (float32 values, int64 rows)."""
-    keys = np.asarray(keys, dtype=np.uint64)
-    vals = (keys >> np.uint64(32)).astype(np.uint32).view(np.float32)
-    rows = (np.uint64(0xFFFFFFFF) - (keys & np.uint64(0xFFFFFFFF))).astype(np.int64)
+def new_best_table(n, device):
+    """Zeroed (3n,) int64 table for the assign pass's lexicographic max of (value, first row)."""
+    return _torch().zeros((3 * n,), dtype=_torch().int64, device=device)
+
+
+def read_best_table(tab, comm=None):
+    """(float64 values, int64 rows) of a best table; with ``comm`` the lexicographic max over ranks."""
+    n = tab.shape[0] // 3
+    h = tab[:2 * n].cpu().numpy()
+    vals = h[:n].view(np.float64).copy()
+    rows = h[n:].copy()
+    if comm is not None:
+        allv = comm.allgather_numpy(vals)
+        allr = comm.allgather_numpy(rows)
+        order = np.lexsort((allr, -allv), axis=0)[0]          # max value, then lowest row
+        vals = np.take_along_axis(allv, order[None, :], 0)[0]
+        rows = np.take_along_axis(allr, order[None, :], 0)[0]
     return vals, rows
-
-
-def initial_key():
-    """Key of (value 0.0, row 0): what np.argmax gives when every |dot| is zero."""
-    return np.uint64(0xFFFFFFFF)

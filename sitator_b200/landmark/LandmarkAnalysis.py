@@ -1,0 +1,289 @@
+"""``LandmarkAnalysis``: the drop-in, B200-native replacement of sitator's landmark analysis.
+
+Same constructor, ``run(sn, frames) -> SiteTrajectory``, properties, attributes, constants and
+exceptions as the reference's ``sitator/landmark/LandmarkAnalysis.py:29-318``.  ``run`` drives
+device passes (``sitator_b200.engine``, ``csrc/``) instead of the Cython fill + NumPy clustering:
+
+  reference step                                   here
+  ------------------------------------------------ ------------------------------------------------
+  wrap a copy of frames (:181-189)                 fused into K1 (frames are only read)
+  site-vertex distances (:191-202)                 context creation (sitb_tables.cu)
+  helpers._fill_landmark_vectors (:220)            K1, once per clustering pass, never stored dense
+  cluster plugin (:234-242)                        ``landmark.cluster.<name>.do_landmark_clustering``
+  site centres (:276-299)                          K6 (``sitb_site_*``)
+  check_multiple_occupancy (:311)                  K5 (``sitb_check_multiple_occupancy``)
+
+Frame-sharded runs: when ``torch.distributed`` is initialised (one process per GPU) ``frames`` is
+this rank's contiguous block of the trajectory, rank order = frame order; the returned
+``SiteTrajectory`` covers the same block with globally consistent sites.
+"""
+import importlib
+import logging
+import math
+
+import numpy as np
+
+from ..SiteNetwork import SiteNetwork
+from ..SiteTrajectory import SiteTrajectory
+from ..errors import MultipleOccupancyError, InsufficientSitesError  # noqa: F401
+from .errors import StaticLatticeError, ZeroLandmarkError
+
+logger = logging.getLogger(__name__)
+
+from functools import wraps
+
+
+def analysis_result(func):
+    @property
+    @wraps(func)
+    def wrapper(self, *args, **kwargs):
+        if not self._has_run:
+            raise ValueError("This LandmarkAnalysis hasn't been run yet.")
+        return func(self, *args, **kwargs)
+    return wrapper
+
+
+class LandmarkAnalysis(object):
+    """Site analysis of mobile atoms in a static lattice with landmark analysis.
+
+    Parameters are those of the reference (``LandmarkAnalysis.py:95-108``); ``cutoff_center`` is
+    accepted as an alias of ``cutoff_midpoint`` (the reference's docstring uses the former name).
+    ``force_no_memmap`` is accepted and ignored: landmark vectors are never stored.
+    """
+
+    SITE_CENTERS_REAL_UNWEIGHTED = 'real-unweighted'
+    SITE_CENTERS_REAL_WEIGHTED = 'real-weighted'
+    SITE_CENTERS_REPRESENTATIVE_LANDMARK = 'representative-landmark'
+
+    CLUSTERING_CLUSTER_SIZE = 'cluster-size'
+    CLUSTERING_LABELS = 'cluster-labels'
+    CLUSTERING_CONFIDENCES = 'cluster-confs'
+    CLUSTERING_LANDMARK_GROUPINGS = 'cluster-landmark-groupings'
+    CLUSTERING_REPRESENTATIVE_LANDMARKS = 'cluster-representative-lvecs'
+
+    def __init__(self,
+                 clustering_algorithm='dotprod',
+                 clustering_params={},
+                 cutoff_midpoint=1.5,
+                 cutoff_steepness=30,
+                 minimum_site_occupancy=0.01,
+                 site_centers_method=SITE_CENTERS_REAL_WEIGHTED,
+                 check_for_zero_landmarks=True,
+                 static_movement_threshold=1.0,
+                 dynamic_lattice_mapping=False,
+                 relaxed_lattice_checks=False,
+                 max_mobile_per_site=1,
+                 force_no_memmap=False,
+                 verbose=True,
+                 cutoff_center=None,
+                 device=None):
+        self._cutoff_midpoint = cutoff_midpoint if cutoff_center is None else cutoff_center
+        self._cutoff_steepness = cutoff_steepness
+        self._minimum_site_occupancy = minimum_site_occupancy
+
+        self._cluster_algo = clustering_algorithm
+        self._clustering_params = clustering_params
+
+        self.verbose = verbose
+        self.check_for_zero_landmarks = check_for_zero_landmarks
+        self.site_centers_method = site_centers_method
+        self.dynamic_lattice_mapping = dynamic_lattice_mapping
+        self.relaxed_lattice_checks = relaxed_lattice_checks
+
+        self._landmark_vectors = None
+        self._landmark_dimension = None
+
+        self.static_movement_threshold = static_movement_threshold
+        self.max_mobile_per_site = max_mobile_per_site
+
+        self.force_no_memmap = force_no_memmap
+        self._device = device
+        self._engine = None
+        self._has_run = False
+        self.stats = {}
+
+    @property
+    def cutoff(self):
+        return (self._cutoff_midpoint, self._cutoff_steepness)
+
+    @analysis_result
+    def landmark_vectors(self):
+        """Landmark vectors from the last ``run()``: materialised on demand as a read-only
+        (n_frames * n_mobile, landmark_dimension) float64 array."""
+        if self._landmark_vectors is None:
+            import torch
+            eng = self._engine
+            out = np.empty((eng.n_frames * eng.M, eng.L), dtype=np.float64)
+            step = max(1, (256 << 20) // (eng.M * eng.L * 8))
+            for f0 in range(0, eng.n_frames, step):
+                n = min(step, eng.n_frames - f0)
+                out[f0 * eng.M:(f0 + n) * eng.M] = eng.fill_dense(f0, n, dtype=torch.float64).cpu().numpy()
+            self._landmark_vectors = out
+        view = self._landmark_vectors[:]
+        view.flags.writeable = False
+        return view
+
+    @analysis_result
+    def landmark_dimension(self):
+        """Number of components in a single landmark vector."""
+        return self._landmark_dimension
+
+    # ---------------------------------------------------------------------------------------------
+    def _raise_first_error(self, status, comm, engine):
+        first = status.first_error(self.check_for_zero_landmarks)
+        key = (1 << 62) if first is None else ((first[1] << 8) | first[0])     # (frame, code) ordering
+        if comm is not None:
+            gkey = comm.allreduce_min_int(key)
+            if gkey == (1 << 62):
+                return
+            if gkey != key:      # another rank holds the first error; raise the same type with its frame
+                code, frame = gkey & 0xFF, gkey >> 8
+                first = (code, frame, -1)
+        if first is None:
+            return
+        code, frame, index = first
+        if code == 1:
+            raise StaticLatticeError(
+                "No static atom position within %f A threshold of static lattice position %i"
+                % (self.static_movement_threshold, index),
+                lattice_atoms=[index], frame=frame, try_recentering=True)
+        if code == 2:
+            not_assigned = engine.unassigned_lattice_atoms(frame) if hasattr(engine, "unassigned_lattice_atoms") else None
+            raise StaticLatticeError(
+                "At frame %i, static positions of atoms %s not assigned to lattice positions" % (frame, not_assigned),
+                lattice_atoms=not_assigned, frame=frame, try_recentering=True)
+        if code == 3:
+            raise ZeroLandmarkError(mobile_index=index, frame=frame)
+
+    def run(self, sn, frames):
+        """Run the landmark analysis.
+
+        Args:
+            sn (SiteNetwork): the landmark basis; each site is a landmark defined by its vertex
+                static atoms (``sn.vertices``).
+            frames (ndarray n_frames x n_atoms x 3, float64): a trajectory, may be unwrapped.  It is
+                only read (the reference wraps a copy).
+        """
+        import torch
+        from ..engine import LandmarkEngine
+        from .source import LandmarkVectorSource
+        from . import parallel
+
+        if not (isinstance(sn, SiteNetwork) or all(hasattr(sn, a) for a in ("static_mask", "mobile_mask", "centers", "vertices"))):
+            raise TypeError("sn must be a SiteNetwork")
+        if self._has_run:
+            raise ValueError("Cannot rerun LandmarkAnalysis!")
+        if frames.shape[1:] != (sn.n_total, 3):
+            raise ValueError("Wrong shape %s for frames." % (frames.shape,))
+        if sn.vertices is None:
+            raise ValueError("Input SiteNetwork must have vertices")
+        if self.site_centers_method not in (self.SITE_CENTERS_REAL_WEIGHTED, self.SITE_CENTERS_REAL_UNWEIGHTED,
+                                            self.SITE_CENTERS_REPRESENTATIVE_LANDMARK):
+            raise ValueError("Invalid site centers method '%s'" % self.site_centers_method)
+        if self._cluster_algo == 'dotprod':
+            raise NotImplementedError(
+                "clustering_algorithm='dotprod' (the online clustering of DotProdClassifier.fit_centers) is not built "
+                "yet (SURVEY.md section 8f-1); use clustering_algorithm='mcl'. There is no CPU fallback.")
+
+        n_frames = len(frames)
+        logger.info("--- Running Landmark Analysis ---")
+        comm = parallel.default_comm()
+        frame0 = 0 if comm is None else comm.exclusive_scan_int(n_frames)
+
+        # -- Steps 0/1: context (cell, tables, site-vertex distances); frames resident on the device
+        self._landmark_dimension = sn.n_sites
+        t_start = torch.cuda.Event(enable_timing=True); t_end = torch.cuda.Event(enable_timing=True)
+        engine = LandmarkEngine.from_site_network(
+            sn, cutoff_midpoint=self._cutoff_midpoint, cutoff_steepness=self._cutoff_steepness,
+            static_movement_threshold=self.static_movement_threshold,
+            dynamic_lattice_mapping=self.dynamic_lattice_mapping,
+            relaxed_lattice_checks=self.relaxed_lattice_checks, device=self._device)
+        self._engine = engine
+        t_start.record()
+        engine.set_frames(frames, frame0=frame0)
+        engine.reset_status()
+
+        # -- Steps 2/3: landmark vectors + clustering
+        logger.info("  - computing landmark vectors / clustering -")
+        source = LandmarkVectorSource(engine, comm)
+        clustermod = importlib.import_module("sitator_b200.landmark.cluster." + self._cluster_algo)
+        if hasattr(clustermod, "landmark_graph"):
+            clustermod.landmark_graph(source)          # pass A runs the lattice / zero-vector checks
+        status = engine.status()
+        self._raise_first_error(status, comm, engine)
+        if status.n_list_overflow:
+            raise RuntimeError("%d landmark vectors have more than 128 non-zero components; "
+                               "the device lists would truncate them" % status.n_list_overflow)
+        self.n_all_zero_lvecs = status.n_zero_rows if comm is None else comm.allreduce_sum_scalar(status.n_zero_rows)
+        if status.n_duplicate_nearest:
+            logger.warning("%i times a static atom was the closest to more than one static lattice position"
+                           % status.n_duplicate_nearest)
+        if not self.check_for_zero_landmarks and self.n_all_zero_lvecs > 0:
+            logger.warning("     Had %i all-zero landmark vectors; no error because `check_for_zero_landmarks = False`."
+                           % self.n_all_zero_lvecs)
+
+        logger.info("  - clustering landmark vectors -")
+        clustering = clustermod.do_landmark_clustering(
+            source, clustering_params=self._clustering_params,
+            min_samples=self._minimum_site_occupancy / float(sn.n_mobile), verbose=self.verbose)
+
+        cluster_counts = clustering[LandmarkAnalysis.CLUSTERING_CLUSTER_SIZE]
+        lmk_lbls = clustering[LandmarkAnalysis.CLUSTERING_LABELS]
+        lmk_confs = clustering[LandmarkAnalysis.CLUSTERING_CONFIDENCES]
+        landmark_clusters = clustering.get(LandmarkAnalysis.CLUSTERING_LANDMARK_GROUPINGS)
+        if landmark_clusters is not None:
+            assert len(cluster_counts) == len(landmark_clusters)
+        rep_lvecs = clustering.get(LandmarkAnalysis.CLUSTERING_REPRESENTATIVE_LANDMARKS)
+        if rep_lvecs is not None:
+            rep_lvecs = np.asarray(rep_lvecs)
+            assert rep_lvecs.shape == (len(cluster_counts), engine.L)
+
+        n_unassigned = int(np.sum(lmk_lbls < 0))
+        n_rows = len(lmk_lbls)
+        if comm is not None:
+            n_unassigned = comm.allreduce_sum_scalar(n_unassigned)
+            n_rows = comm.allreduce_sum_scalar(n_rows)
+        logger.info("    Failed to assign %i%% of mobile particle positions to sites." % (100.0 * n_unassigned / float(n_rows)))
+
+        lmk_lbls = lmk_lbls.reshape(n_frames, sn.n_mobile)
+        lmk_confs = lmk_confs.reshape(n_frames, sn.n_mobile)
+        n_sites = len(cluster_counts)
+        if n_sites < (sn.n_mobile / self.max_mobile_per_site):
+            raise InsufficientSitesError(verb="Landmark analysis", n_sites=n_sites, n_mobile=sn.n_mobile)
+        logger.info("    Identified %i sites with assignment counts %s" % (n_sites, cluster_counts))
+
+        # -- output network: site centres (LandmarkAnalysis.py:276-299)
+        out_sn = sn.copy()
+        dev_labels = clustering.get('_dev_labels')
+        dev_confs = clustering.get('_dev_confs')
+        if dev_labels is None:
+            dev_labels = torch.as_tensor(np.ascontiguousarray(lmk_lbls.reshape(-1)), device=engine.device)
+            dev_confs = torch.as_tensor(np.ascontiguousarray(lmk_confs.reshape(-1)), device=engine.device)
+        if self.site_centers_method in (self.SITE_CENTERS_REAL_WEIGHTED, self.SITE_CENTERS_REAL_UNWEIGHTED):
+            weighted = self.site_centers_method == self.SITE_CENTERS_REAL_WEIGHTED
+            site_centers = engine.site_centers(dev_labels, dev_confs, n_sites, weighted,
+                                               clustering.get('_dev_site_best') if weighted else None, comm)
+        else:
+            if rep_lvecs is None:
+                raise ValueError("Chosen clustering method (with current parameters) didn't return representative "
+                                 "landmark vectors; can't use SITE_CENTERS_REPRESENTATIVE_LANDMARK.")
+            site_centers = engine.weighted_point_averages(np.asarray(sn.centers), rep_lvecs)
+        out_sn.centers = site_centers
+        if landmark_clusters is not None:
+            out_sn.vertices = [set.union(*[set(sn.vertices[l]) for l in lclust]) for lclust in landmark_clusters]
+
+        out_st = SiteTrajectory(out_sn, lmk_lbls, lmk_confs)
+        out_st.frame0 = frame0
+        out_st._comm = comm
+
+        # Check that multiple particles are never assigned to one site at the same time
+        self.n_multiple_assignments, self.avg_mobile_per_site = out_st.check_multiple_occupancy(
+            max_mobile_per_site=self.max_mobile_per_site, _dev_traj=dev_labels.view(n_frames, sn.n_mobile))
+
+        out_st.set_real_traj(frames)
+        t_end.record()
+        torch.cuda.synchronize(engine.device)
+        self.stats = {"run_ms": t_start.elapsed_time(t_end), "n_screen_rejects": status.n_screen_rejects,
+                      "nnz": status.nnz, "mcl_iterations": clustering.get('_mcl_iterations')}
+        self._has_run = True
+        return out_st

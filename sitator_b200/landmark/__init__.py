@@ -1,0 +1,2 @@
+from .errors import StaticLatticeError, ZeroLandmarkError, LandmarkAnalysisError
+from .LandmarkAnalysis import LandmarkAnalysis

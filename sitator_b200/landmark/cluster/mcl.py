@@ -1,0 +1,194 @@
+"""Cluster landmarks into sites with Markov clustering, then assign every landmark vector.
+
+GPU restatement of the reference plugin ``sitator/landmark/cluster/mcl.py:43-131`` behind the same
+plugin contract (``do_landmark_clustering(landmark_vectors, clustering_params, min_samples, verbose)``
+returning the same dict keys, ``LandmarkAnalysis.py:89-93,234-256``).  ``landmark_vectors`` is a
+:class:`~sitator_b200.landmark.source.LandmarkVectorSource`: the (N, L) matrix is never stored.
+
+Valid clustering params (as in the reference):
+ - ``"assignment_threshold"`` (float in [0, 1]): similarity below which a landmark vector is unassigned.
+ - ``"good_site_normed_threshold"``: minimum cosine similarity between a site's unit vector and its
+   best matching landmark vector.
+ - ``"good_site_projected_threshold"``: minimum inner product of the same pair.
+ - everything else goes to :func:`sitator_b200.util.mcl.markov_clustering_device`.
+
+Device passes (each a launch of the fused kernel K1 over the resident frames):
+  A  seen counts + Gram                      -> cov, correlation graph, MCL, per-cluster eigenvectors
+  B  best matching landmark vector per cluster (max |centre . x|, first row)       (mcl.py:81-89)
+  C  predict + bincount                      -> min_samples filter                  (DotProdClassifier.pyx:86-108)
+  D  predict with the kept centres + representative landmark vectors + per-site max-confidence row
+"""
+import ctypes as C
+import logging
+
+import numpy as np
+
+from ... import _native
+from ...engine import new_best_table, read_best_table
+from ...util.mcl import markov_clustering_device, clusters_from_matrix
+
+logger = logging.getLogger(__name__)
+
+DEFAULT_PARAMS = {
+    'inflation': 4,
+    'assignment_threshold': 0.7,
+}
+
+CLUSTERING_CLUSTER_SIZE = 'cluster-size'
+CLUSTERING_LABELS = 'cluster-labels'
+CLUSTERING_CONFIDENCES = 'cluster-confs'
+CLUSTERING_LANDMARK_GROUPINGS = 'cluster-landmark-groupings'
+CLUSTERING_REPRESENTATIVE_LANDMARKS = 'cluster-representative-lvecs'
+
+
+def principal_vector(block):
+    """Eigenvector of the largest eigenvalue of a (small, PSD) covariance block -- what
+    ``eigsh(block, k=1)`` returns in the reference (mcl.py:74-79); its sign is arbitrary there and
+    every consumer takes ``abs`` (mcl.py:82,85; DotProdClassifier.pyx:179)."""
+    if block.shape[0] == 1:
+        return np.array([1.0])
+    w, v = np.linalg.eigh(block)
+    return v[:, -1]
+
+
+def landmark_graph(source):
+    """Pass A + mcl.py:53-59.  Returns (seen (L,) int64 numpy, cov (L,L) numpy, graph torch tensor)."""
+    import torch
+    eng = source.engine
+    lib = _native.load()
+    if source.gram_upper is None:
+        seen, gram = eng.pass_stats()
+        if source.comm is not None:
+            source.comm.allreduce_sum_(seen)
+            source.comm.allreduce_sum_(gram)
+        source.seen, source.gram_upper = seen, gram
+    L = eng.L
+    cov = torch.empty((L, L), dtype=torch.float64, device=eng.device)
+    graph = torch.empty((L, L), dtype=torch.float64, device=eng.device)
+    stream = torch.cuda.current_stream(eng.device).cuda_stream
+    _native.check(lib.sitb_landmark_graph(eng.device.index, C.c_void_p(source.gram_upper.data_ptr()), L,
+                                          float(source.n_total), C.c_void_p(cov.data_ptr()),
+                                          C.c_void_p(graph.data_ptr()), C.c_void_p(stream)))
+    return source.seen.cpu().numpy(), cov.cpu().numpy(), graph
+
+
+def _centre_tables(clusters, vectors, L):
+    cid = np.full(L, -1, dtype=np.int32)
+    w = np.zeros(L, dtype=np.float64)
+    for i, (cl, vec) in enumerate(zip(clusters, vectors)):
+        cl = np.asarray(cl, dtype=np.int64)
+        if np.any(cid[cl] != -1):
+            raise ValueError("landmark clusters overlap; the sparse centre representation needs disjoint clusters")
+        cid[cl] = i
+        w[cl] = vec
+    return cid, w
+
+
+def do_landmark_clustering(landmark_vectors, clustering_params, min_samples, verbose):
+    import torch
+    source = landmark_vectors
+    eng = source.engine
+    comm = source.comm
+    L = eng.L
+    params = DEFAULT_PARAMS.copy()
+    params.update(clustering_params)
+
+    seen_ntimes, cov, graph = landmark_graph(source)
+
+    predict_threshold = params.pop('assignment_threshold')
+    good_site_normed_threshold = params.pop('good_site_normed_threshold', predict_threshold)
+    good_site_project_thresh = params.pop('good_site_projected_threshold', predict_threshold)
+    weighted_reps = params.pop('weighted_representative_landmarks', True)
+
+    # -- cluster landmarks (mcl.py:66-68)
+    m2, n_iter = markov_clustering_device(graph, **params)
+    clusters = clusters_from_matrix(m2.cpu().numpy())
+    logger.debug("Markov clustering converged in %i iterations: %i clusters" % (n_iter, len(clusters)))
+    clusters = [list(c) for c in clusters if seen_ntimes[c[0]] > 0]
+    n_clusters = len(clusters)
+    if n_clusters == 0:
+        raise ValueError("Markov clustering found no landmark cluster that was ever seen")
+
+    # -- centres: principal eigenvector of each cluster's covariance block (mcl.py:73-80)
+    vectors = [principal_vector(cov[np.ix_(cl, cl)]) for cl in clusters]
+    cid, w = _centre_tables(clusters, vectors, L)
+
+    # -- pass B: best matching landmark vector per cluster (mcl.py:81-89)
+    eng.set_centers(cid, w, n_clusters)
+    best = new_best_table(n_clusters, eng.device)
+    eng.pass_assign(float('nan'), best=best)
+    _, best_rows = read_best_table(best, comm)
+    best_lvecs = source.rows(best_rows)                                   # (n_clusters, L) float64
+    good = np.zeros(n_clusters, dtype=bool)
+    scale = np.ones(n_clusters)
+    for i, cl in enumerate(clusters):
+        centre = np.zeros(L)
+        centre[cl] = vectors[i]
+        best_match_dot = abs(float(np.dot(best_lvecs[i], centre)))
+        norm = np.linalg.norm(best_lvecs[i])
+        with np.errstate(divide='ignore', invalid='ignore'):
+            best_match_dot_norm = best_match_dot / norm
+        good[i] = (best_match_dot_norm >= good_site_normed_threshold) and (best_match_dot >= good_site_project_thresh)
+        scale[i] = best_match_dot
+    logger.debug("Kept %i/%i landmark clusters as good sites" % (int(np.sum(good)), len(good)))
+
+    # -- keep the good sites (mcl.py:94-96)
+    clusters = [c for i, c in enumerate(clusters) if good[i]]
+    vectors = [vectors[i] / scale[i] for i in range(n_clusters) if good[i]]
+    n_clusters = len(clusters)
+    if n_clusters == 0:
+        raise ValueError("`min_samples` too large; all 0 clusters under threshold.")
+
+    # -- pass C: predict + bincount, then the min_samples filter (DotProdClassifier.pyx:86-115)
+    cid, w = _centre_tables(clusters, vectors, L)
+    eng.set_centers(cid, w, n_clusters)
+    counts = torch.zeros((n_clusters,), dtype=torch.int64, device=eng.device)
+    eng.pass_assign(predict_threshold, counts=counts)
+    if comm is not None:
+        comm.allreduce_sum_(counts)
+    cluster_counts = counts.cpu().numpy()
+    total_n_assigned = int(cluster_counts.sum())
+    if isinstance(min_samples, (int, np.integer)):
+        ms = int(min_samples)
+    else:
+        ms = int(np.floor(min_samples * total_n_assigned))
+    ms = max(ms, 1)
+    count_mask = cluster_counts >= ms
+    if not np.any(count_mask):
+        raise ValueError("`min_samples` too large; all %i clusters under threshold." % len(count_mask))
+    logger.info("DotProdClassifier: %i/%i assignment counts below threshold %s (%s); %i clusters remain." %
+                (int(np.sum(~count_mask)), len(count_mask), min_samples, ms, int(np.sum(count_mask))))
+    clusters = [c for i, c in enumerate(clusters) if count_mask[i]]
+    vectors = [v for i, v in enumerate(vectors) if count_mask[i]]
+    kept_counts = cluster_counts[count_mask]
+    n_sites = len(clusters)
+
+    # -- pass D: final predict + representative landmark vectors (mcl.py:114-122) + per-site best row
+    cid, w = _centre_tables(clusters, vectors, L)
+    eng.set_centers(cid, w, n_sites)
+    N = source.n_local
+    labels = torch.empty((N,), dtype=torch.int64, device=eng.device)
+    confs = torch.empty((N,), dtype=torch.float64, device=eng.device)
+    rep = torch.zeros((n_sites, L), dtype=torch.float64, device=eng.device)
+    rep_w = torch.zeros((n_sites,), dtype=torch.float64, device=eng.device)
+    site_best = new_best_table(n_sites, eng.device)
+    eng.pass_assign(predict_threshold, labels=labels, confs=confs, rep=rep, rep_w=rep_w, site_best=site_best)
+    if comm is not None:
+        comm.allreduce_sum_(rep)
+        comm.allreduce_sum_(rep_w)
+    if weighted_reps:
+        reps = (rep / rep_w[:, None]).cpu().numpy()
+    else:
+        raise NotImplementedError("weighted_representative_landmarks=False (the reference cannot reach it either: "
+                                  "the key is forwarded to markov_clustering, mcl.py:66,115)")
+
+    return {
+        CLUSTERING_CLUSTER_SIZE: kept_counts,
+        CLUSTERING_LABELS: labels.cpu().numpy(),
+        CLUSTERING_CONFIDENCES: confs.cpu().numpy(),
+        CLUSTERING_LANDMARK_GROUPINGS: clusters,
+        CLUSTERING_REPRESENTATIVE_LANDMARKS: reps,
+        # device-side copies for the rest of LandmarkAnalysis.run (not part of the reference contract)
+        '_dev_labels': labels, '_dev_confs': confs, '_dev_site_best': site_best,
+        '_centers': (cid, w), '_mcl_iterations': n_iter,
+    }

@@ -1,0 +1,45 @@
+"""The clustering plugins' view of the landmark vectors.
+
+The reference hands its clustering plugins a dense (N, L) float64 matrix, memory-mapped from a
+temp file (``LandmarkAnalysis.py:209-218``, 67 GB at BASELINE config 2).  Here the landmark
+vectors are never stored dense: a plugin receives a :class:`LandmarkVectorSource`, which can
+stream reductions over them (each one a pass of the fused kernel over the resident frames) and
+materialise selected rows.  In a frame-sharded run every rank holds one source over its shard and
+the reductions are all-reduced.
+"""
+import numpy as np
+
+
+class LandmarkVectorSource(object):
+    def __init__(self, engine, comm=None):
+        self.engine = engine
+        self.comm = comm                      # landmark.parallel.Comm or None
+        self.n_local = engine.n_frames * engine.M
+        self.n_total = self.n_local if comm is None else int(comm.allreduce_sum_scalar(self.n_local))
+        self.row0 = engine.frame0 * engine.M  # global index of the first local row
+        self.seen = None
+        self.gram_upper = None
+
+    @property
+    def shape(self):
+        return (self.n_total, self.engine.L)
+
+    def __len__(self):
+        return self.n_total
+
+    def rows(self, global_rows):
+        """float64 landmark vectors of the given global rows (each must be resident on some rank)."""
+        import torch
+        eng = self.engine
+        global_rows = np.asarray(global_rows, dtype=np.int64)
+        out = np.zeros((len(global_rows), eng.L), dtype=np.float64)
+        local = (global_rows >= self.row0) & (global_rows < self.row0 + self.n_local)
+        if np.any(local):
+            lr = global_rows[local] - self.row0
+            frames = np.unique(lr // eng.M)
+            dense = eng.fill_frames(frames, dtype=torch.float64).cpu().numpy()
+            pos = np.searchsorted(frames, lr // eng.M)
+            out[local] = dense[pos * eng.M + lr % eng.M]
+        if self.comm is not None:
+            out = self.comm.allreduce_sum_numpy(out)
+        return out

@@ -1,0 +1,69 @@
+#!/usr/bin/env python
+"""Generate the golden fixtures in tests/golden/ by running the UNMODIFIED reference (compiled into
+oracle/_ref from /root/reference by oracle/build_ref.py) on seeded synthetic inputs.
+
+Run in the build container (needs /root/reference):  python tests/golden/make_golden.py
+The inputs are regenerated from (config name, n_frames) by sitator_b200.synthetic, so only the
+reference's outputs are stored.
+"""
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+
+from oracle import build_ref, ref_loader          # noqa: E402
+from sitator_b200 import synthetic as syn          # noqa: E402
+
+CASES = [
+    # (fixture name, config, n_frames, trajectory kwargs)
+    ("toy_bcc_300", "toy_bcc", 300, {}),
+    ("llzo_60", "llzo", 60, {}),
+    ("lgps_dynamic_40", "lgps_dynamic", 40, {"swap_statics_at": 13}),
+]
+
+
+def run_case(ref, name, config, n_frames, traj_kw):
+    system, cfg = syn.make_config(config)
+    frames = system.trajectory(n_frames, **traj_kw)
+    sn = syn.site_network_for(system, ref.SiteNetwork, ref.Atoms)
+    la = ref.LandmarkAnalysis(clustering_algorithm='mcl', verbose=False, force_no_memmap=True,
+                              dynamic_lattice_mapping=cfg["dynamic"],
+                              check_for_zero_landmarks=cfg.get("check_for_zero_landmarks", True),
+                              max_mobile_per_site=cfg.get("max_mobile_per_site", 1))
+    st = la.run(sn, frames)
+    lv = np.asarray(la.landmark_vectors)
+    nz = np.nonzero(lv)
+    jumps = np.asarray(list(st.jumps()), dtype=np.int64).reshape(-1, 4)
+    jumps_u = np.asarray(list(st.jumps(unknown_as_jump=True)), dtype=np.int64).reshape(-1, 4)
+    ref.JumpAnalysis().run(st)
+    out_sn = st.site_network
+    zero_rows = ~lv.any(axis=1)
+    confs = st.confidences.copy()
+    confs.reshape(-1)[zero_rows] = 0.0          # uninitialised in the reference (DotProdClassifier.pyx:168-172)
+    vert_len = np.array([len(v) for v in out_sn.vertices])
+    np.savez_compressed(
+        os.path.join(HERE, name + ".npz"),
+        config=config, n_frames=n_frames, traj_kw=repr(traj_kw),
+        lv_rows=nz[0].astype(np.int32), lv_cols=nz[1].astype(np.int16), lv_vals=lv[nz], lv_shape=np.array(lv.shape),
+        n_all_zero_lvecs=la.n_all_zero_lvecs,
+        labels=st.traj, confs=confs, site_centers=np.asarray(out_sn.centers),
+        site_vertices=np.concatenate([sorted(v) for v in out_sn.vertices]), site_vertices_len=vert_len,
+        n_multiple_assignments=la.n_multiple_assignments, avg_mobile_per_site=la.avg_mobile_per_site,
+        jumps=jumps, jumps_unknown_as_jump=jumps_u,
+        n_ij=out_sn.n_ij, p_ij=out_sn.p_ij, jump_lag=out_sn.jump_lag, residence_times=out_sn.residence_times,
+        occupancy_freqs=out_sn.occupancy_freqs, total_corrected_residences=out_sn.total_corrected_residences,
+    )
+    print("%s: %d frames, %d sites, %d jumps, %d non-zero lvec components, %d unassigned"
+          % (name, n_frames, out_sn.n_sites, len(jumps), len(nz[0]), int(np.sum(st.traj < 0))))
+
+
+if __name__ == "__main__":
+    if not build_ref.build(verbose=False):
+        sys.exit("needs /root/reference to build oracle/_ref")
+    ref = ref_loader.load()
+    for case in CASES:
+        run_case(ref, *case)

@@ -1,0 +1,110 @@
+"""CPU: the NumPy oracle against the golden outputs of the compiled reference (tests/golden/*.npz),
+plus known-answer tests derived from the reference code."""
+import math
+
+import numpy as np
+import pytest
+
+from oracle import landmark_oracle as orc
+from tests import _util as U
+
+
+@pytest.mark.parametrize("name", U.GOLDEN_CASES)
+def test_oracle_reproduces_reference_golden(name):
+    g, system, cfg, frames = U.load_golden(name)
+    kw = U.analysis_kwargs(cfg)
+    res = orc.run_landmark_analysis(system.cell, system.static_pos, system.static_idx, system.mobile_idx,
+                                    system.lm_centers, system.lm_vertices, frames,
+                                    dynamic_lattice_mapping=kw["dynamic_lattice_mapping"],
+                                    check_for_zero_landmarks=kw["check_for_zero_landmarks"],
+                                    max_mobile_per_site=kw["max_mobile_per_site"])
+    lv = res["landmark_vectors"]
+    assert np.array_equal(lv != 0, g["landmark_vectors"] != 0)
+    assert np.max(np.abs(lv - g["landmark_vectors"])) < 1e-14
+    assert res["n_all_zero_lvecs"] == int(g["n_all_zero_lvecs"])
+    assert np.array_equal(res["labels"], g["labels"])              # same site order: same set() logic
+    assert np.max(np.abs(res["confs"] - g["confs"])) < 1e-12
+    assert np.max(np.abs(res["site_centers"] - g["site_centers"])) < 1e-11
+    assert res["site_vertices"] == g["site_vertex_sets"]
+    assert res["n_multiple_assignments"] == int(g["n_multiple_assignments"])
+    assert abs(res["avg_mobile_per_site"] - float(g["avg_mobile_per_site"])) < 1e-12
+    assert np.array_equal(orc.jumps(res["labels"]), g["jumps"])
+    assert np.array_equal(orc.jumps(res["labels"], unknown_as_jump=True), g["jumps_unknown_as_jump"])
+    ja = orc.jump_analysis(res["labels"], len(res["cluster-size"]))
+    for key in ("n_ij", "jump_lag", "residence_times", "occupancy_freqs", "total_corrected_residences"):
+        assert np.array_equal(ja[key], g[key]), key
+    assert np.array_equal(np.nan_to_num(ja["p_ij"], nan=-1.0), np.nan_to_num(g["p_ij"], nan=-1.0))
+
+
+def test_oracle_against_live_reference_if_built():
+    from oracle import ref_loader
+    if not ref_loader.available():
+        pytest.skip("oracle/_ref not built in this environment")
+    ref = ref_loader.load()
+    from sitator_b200 import synthetic as syn
+    system, cfg = syn.make_config("toy_bcc")
+    frames = system.trajectory(80, seed=11)
+    pb = ref.PBCCalculator(system.cell)
+    op = orc.PBC(system.cell)
+    rng = np.random.default_rng(0)
+    pts = rng.normal(0, 20, (50, 3))
+    a = pts.copy(); pb.wrap_points(a)
+    b = op.wrap_points(pts.copy())
+    assert np.array_equal(a, b)
+    assert np.array_equal(pb.distances(pts[0], pts[1:]), op.distances(pts[0], pts[1:]))
+    w = rng.random(49)
+    near = system.static_pos[:10] + rng.normal(0, 0.1, (10, 3))
+    assert np.array_equal(pb.average(near, weights=w[:10]), op.average(near, weights=w[:10]))
+
+
+def test_known_answers_from_the_reference_formulas():
+    # helpers.pyx:127-131 with midpoint 1.5, steepness 30, threshold 1e-4
+    assert orc.cutoff_round_to_zero_point(1.5, 30.0) == pytest.approx(1.8070080122325283, abs=1e-15)
+    # a mobile atom exactly on a landmark centre of an ideal lattice: every ratio is 1
+    cell = np.eye(3) * 10.0
+    static = np.array([[4.0, 5.0, 5.0], [6.0, 5.0, 5.0], [5.0, 4.0, 5.0], [5.0, 6.0, 5.0]])
+    centre = np.array([[5.0, 5.0, 5.0]])
+    frames = np.concatenate([static, centre])[None]
+    lv, nz, _ = orc.fill_landmark_vectors(cell, static, np.arange(4), np.array([4]), centre, [[0, 1, 2, 3]], frames)
+    assert lv[0, 0] == pytest.approx(1.0 / (1.0 + math.exp(30 * (1 - 1.5))), rel=1e-15)
+    # just inside / outside the short-circuit (helpers.pyx:199-203): the component jumps from ~0.1 to 0
+    thr = orc.cutoff_round_to_zero_point(1.5, 30.0)
+    for scale, expect_zero in ((thr * (1 - 1e-9), False), (thr * (1 + 1e-9), True)):
+        fr = frames.copy()
+        fr[0, 4] = [5.0 + (scale - 1.0), 5.0, 5.0]      # distance to atom 0 becomes `scale`
+        lv, _, _ = orc.fill_landmark_vectors(cell, static, np.arange(4), np.array([4]), centre, [[0, 1, 2, 3]], fr,
+                                             check_for_zeros=False)
+        assert (lv[0, 0] == 0.0) == expect_zero
+        if not expect_zero:
+            assert 0.05 < lv[0, 0] < 0.2
+    # wrap of a point on a cell face and in a triclinic cell (PBCCalculator.pyx:341-366)
+    p = orc.PBC(cell).wrap_points(np.array([[10.0, -0.0, 25.0]]))
+    assert np.allclose(p, [[0.0, 0.0, 5.0]])
+    tri = np.array([[9.0, 0.5, 0.0], [1.0, 8.0, 0.2], [0.0, 1.5, 10.0]])
+    q = orc.PBC(tri).wrap_points(np.array([[30.0, -7.0, 12.0]]))
+    f = q @ np.linalg.inv(tri)
+    assert np.all(f >= -1e-12) and np.all(f < 1 + 1e-12)
+
+
+def test_markov_clustering_returns_blocks():
+    g = np.zeros((7, 7))
+    g[:3, :3] = 1.0
+    g[3:5, 3:5] = 1.0
+    g[5:, 5:] = 1.0
+    g += 1e-7
+    np.fill_diagonal(g, 1.0)
+    cl = sorted(tuple(int(x) for x in c) for c in orc.markov_clustering(g, inflation=4))
+    assert cl == [(0, 1, 2), (3, 4), (5, 6)]
+
+
+def test_jump_scan_hand_written_table():
+    t = np.array([[-1, 2, 3],
+                  [4, 2, -1],
+                  [4, 5, -1],
+                  [-1, 5, 3],
+                  [6, -1, 7]])
+    j = orc.jumps(t)
+    # a first appearance after an unknown start is a jump from -1 (SiteTrajectory.py:361-373)
+    assert j.tolist() == [[1, 0, -1, 4], [2, 1, 2, 5], [4, 0, 4, 6], [4, 2, 3, 7]]
+    ju = orc.jumps(t, unknown_as_jump=True)
+    assert [1, 2, 3, -1] in ju.tolist() and [3, 0, 4, -1] in ju.tolist()
