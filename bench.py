@@ -1,0 +1,394 @@
+#!/usr/bin/env python
+"""Benchmark of the landmark-analysis hot path (BASELINE.json: frame*atoms/s, landmark + assign).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    torchrun --nnodes=1 --nproc-per-node N ... bench.py --gpus N --steps K --warmup W
+
+Workload: BASELINE.json configs[1] -- synthetic cubic LLZO cell (136 static + 56 mobile = 192 atoms,
+1500 landmarks), 10^5 frames per GPU, static lattice (sitator_b200.synthetic 'llzo').
+
+One *step* = one pass of the fused landmark-fill + site-assign kernel (K1, MODE_ASSIGN) over the
+rank's 10^5 resident frames with the cluster centres of a previous full analysis.  ``value`` =
+frames * atoms * n_gpus / (max over ranks of the CUDA-event time per step).  The resident frames
+(461 MB) are larger than L2 (126 MB), so every step streams them from HBM.
+
+``e2e`` = the same metric for the whole ``LandmarkAnalysis(clustering_algorithm='mcl').run(sn, frames)``
+through the public API with the frames in pinned HOST memory: host->device copy, all device passes
+(Gram, Markov clustering, best-match, two assign passes, site centres, occupancy check) and the
+device->host read of labels and confidences are inside the timed region.
+
+``--impl reference`` times the unmodified reference (compiled into oracle/_ref) on the host cores on
+bounded samples of the same workload and prints the same line.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+WORKLOAD = "llzo"
+METRIC = "frame*atoms/s (landmark fill + site assign)"
+UNIT = "frame*atoms/s"
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--frames", type=int, default=None, help="frames per GPU (default: the config's 100000)")
+    ap.add_argument("--e2e-steps", type=int, default=2)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-frames", type=int, default=400)
+    return ap.parse_args()
+
+
+def dist_env():
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    return rank, local, world
+
+
+# ----------------------------------------------------------------------------------------------
+# clocks
+# ----------------------------------------------------------------------------------------------
+class ClockSampler(object):
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu = gpu_index
+        self.proc = None
+        self.path = None
+
+    def start(self):
+        try:
+            fd, self.path = tempfile.mkstemp(suffix=".csv")
+            os.close(fd)
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        if self.proc is None:
+            return out
+        try:
+            self.proc.terminate()
+            self.proc.wait(timeout=5)
+        except Exception:
+            pass
+        try:
+            rows = [r.strip().split(",") for r in open(self.path) if r.strip()]
+            sm = [float(r[1]) for r in rows if len(r) >= 9]
+            mx = [float(r[2]) for r in rows if len(r) >= 9]
+            if sm:
+                out["sm_mhz"] = float(np.median(sm))
+                out["sm_max_mhz"] = float(max(mx))
+                out["samples"] = len(sm)
+            names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+            seen = set()
+            for r in rows:
+                if len(r) >= 9:
+                    for n, v in zip(names, r[5:9]):
+                        if v.strip().lower().startswith("active"):
+                            seen.add(n)
+            out["reasons"] = sorted(seen)
+        except Exception:
+            pass
+        finally:
+            try:
+                os.unlink(self.path)
+            except Exception:
+                pass
+        return out
+
+
+# ----------------------------------------------------------------------------------------------
+# reference arm / cpu baseline
+# ----------------------------------------------------------------------------------------------
+def reference_run_once(ref, system, cfg, frames):
+    from sitator_b200 import synthetic as syn
+    sn = syn.site_network_for(system, ref.SiteNetwork, ref.Atoms)
+    la = ref.LandmarkAnalysis(clustering_algorithm='mcl', verbose=False, force_no_memmap=True,
+                              max_mobile_per_site=cfg.get("max_mobile_per_site", 1))
+    t = time.perf_counter()
+    la.run(sn, frames)
+    return time.perf_counter() - t
+
+
+def load_reference():
+    """The compiled reference if oracle/_ref is present (kind 'reference'), else None."""
+    try:
+        from oracle import ref_loader
+        if ref_loader.available():
+            import logging
+            logging.disable(logging.WARNING)
+            try:
+                import sklearn.covariance  # noqa: F401  (cluster/mcl.py:22 imports it; do not bill the import)
+            except Exception:
+                pass
+            return ref_loader.load()
+    except Exception as e:  # pragma: no cover
+        sys.stderr.write("reference unavailable: %r\n" % (e,))
+    return None
+
+
+def port_run_once(system, cfg, frames):
+    from oracle import landmark_oracle as orc
+    t = time.perf_counter()
+    orc.run_landmark_analysis(system.cell, system.static_pos, system.static_idx, system.mobile_idx,
+                              system.lm_centers, system.lm_vertices, frames,
+                              max_mobile_per_site=cfg.get("max_mobile_per_site", 1))
+    return time.perf_counter() - t
+
+
+def blas_threads():
+    try:
+        from threadpoolctl import threadpool_info
+        return max([p.get("num_threads", 1) for p in threadpool_info()] or [1])
+    except Exception:
+        return None
+
+
+def cpu_baseline(system, cfg, frames, n_frames):
+    ref = load_reference()
+    sample = np.ascontiguousarray(frames[:n_frames])
+    if ref is not None:
+        dt = reference_run_once(ref, system, cfg, sample)
+        kind = "reference"
+    else:
+        dt = port_run_once(system, cfg, sample)
+        kind = "port"
+    return {
+        "value": n_frames * system.n_total / dt, "unit": UNIT, "cores": 1, "kind": kind,
+        "blas_threads": blas_threads(), "host_cpus": os.cpu_count(), "seconds": dt,
+        "sample": "whole LandmarkAnalysis.run (mcl) on the first %d frames of the same trajectory; fill and assign "
+                  "are single-threaded in the reference, only np.dot/matrix_power use BLAS threads" % n_frames,
+    }
+
+
+def run_reference_arm(args):
+    rank, local, world = dist_env()
+    if rank != 0:
+        return
+    from sitator_b200 import synthetic as syn
+    system, cfg = syn.make_config(WORKLOAD)
+    n_steps = args.steps + args.warmup
+    # bounded sample per step: the reference runs ~20 frames/s on this shape; keep the arm within ~150 s
+    per_step = max(40, min(600, int(150.0 / max(n_steps, 1) * 18.0)))
+    frames = system.trajectory(per_step)
+    ref = load_reference()
+    kind = "reference" if ref is not None else "port"
+    times = []
+    for i in range(n_steps):
+        dt = reference_run_once(ref, system, cfg, frames) if ref is not None else port_run_once(system, cfg, frames)
+        if i >= args.warmup:
+            times.append(dt)
+    t = float(np.mean(times))
+    value = per_step * system.n_total / t
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": t * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": workload_name(system, per_step), "frames_per_step": per_step},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": 1, "kind": kind, "blas_threads": blas_threads(),
+                         "host_cpus": os.cpu_count(),
+                         "sample": "whole LandmarkAnalysis.run (mcl) on %d frames per step" % per_step},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
+
+
+def workload_name(system, n_frames):
+    return ("synthetic LLZO-shaped cell (BASELINE configs[1]): %d static + %d mobile = %d atoms, %d landmarks, "
+            "%d frames per GPU, static lattice" % (system.n_static, system.n_mobile, system.n_total,
+                                                   system.n_landmarks, n_frames))
+
+
+# ----------------------------------------------------------------------------------------------
+# our arm
+# ----------------------------------------------------------------------------------------------
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.isfile(p):
+        try:
+            return json.load(open(p)), "measured"
+        except Exception:
+            pass
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0}, "fallback"
+
+
+def work_counters(system, cfg, frames):
+    """E (vertex-ratio evaluations under the reference's short-circuit), X (logistic evaluations) and nnz
+    per landmark vector, counted once with the oracle by
+    scripts/make_work_counters.py and committed as profiles/work_counters.json."""
+    w = json.load(open(os.path.join(ROOT, "profiles", "work_counters.json")))[WORKLOAD]
+    assert (w["S"], w["M"], w["L"]) == (system.n_static, system.n_mobile, system.n_landmarks)
+    return w["E_per_lvec"], w["X_per_lvec"], w["nnz_per_lvec"]
+
+
+def run_ours(args):
+    import ctypes as C
+    import torch
+    import torch.distributed as dist
+    rank, local, world = dist_env()
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (there is no CPU fallback)")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    from sitator_b200 import synthetic as syn, _native
+    from sitator_b200.landmark import LandmarkAnalysis
+    from sitator_b200.landmark.cluster import mcl as cluster_mcl
+    from sitator_b200.landmark.source import LandmarkVectorSource
+    from sitator_b200.landmark import parallel
+
+    system, cfg = syn.make_config(WORKLOAD)
+    F = args.frames or cfg["n_frames"]
+    A, M, L = system.n_total, system.n_mobile, system.n_landmarks
+    # every rank: its own block of the trajectory, in pinned host memory
+    pinned = torch.empty((F, A, 3), dtype=torch.float64, pin_memory=True)
+    frames = pinned.numpy()
+    chunk = 20000
+    for f0 in range(0, F, chunk):
+        n = min(chunk, F - f0)
+        frames[f0:f0 + n] = system.trajectory(n, seed=1000 * rank + f0 // chunk + system.seed)
+    kw = dict(max_mobile_per_site=cfg.get("max_mobile_per_site", 1),
+              check_for_zero_landmarks=cfg.get("check_for_zero_landmarks", True))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(ms):
+        if world > 1:
+            t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            return float(t.item())
+        return ms
+
+    # ---- e2e: whole run() from pinned host frames (also yields the centres for the kernel steps) -------
+    e2e_ms = []
+    la = None
+    for i in range(1 + max(1, args.e2e_steps)):
+        la = LandmarkAnalysis(clustering_algorithm='mcl', verbose=False, **kw)
+        sn = syn.site_network_for(system)
+        barrier()
+        a = torch.cuda.Event(enable_timing=True); b = torch.cuda.Event(enable_timing=True)
+        a.record()
+        st = la.run(sn, frames)
+        b.record()
+        barrier()
+        if i > 0:
+            e2e_ms.append(max_over_ranks(a.elapsed_time(b)))
+    n_sites = st.site_network.n_sites
+    e2e_t = float(np.mean(e2e_ms)) * 1e-3
+    e2e = {"value": F * A * world / e2e_t, "unit": UNIT, "h2d_bytes_per_step": int(frames.nbytes),
+           "d2h_bytes_per_step": int(F * M * 16), "ms": e2e_t * 1e3, "steps": len(e2e_ms), "n_sites": int(n_sites),
+           "what": "LandmarkAnalysis(clustering_algorithm='mcl').run(sn, frames) with frames in pinned host memory"}
+
+    # ---- value: the fused fill + assign pass over the resident frames --------------------------------
+    eng = la._engine                       # frames of the last run are still resident
+    labels = torch.empty(F * M, dtype=torch.int64, device="cuda")
+    confs = torch.empty(F * M, dtype=torch.float64, device="cuda")
+    counts = torch.zeros(eng.n_clusters, dtype=torch.int64, device="cuda")
+
+    def step():
+        eng.pass_assign(0.7, labels=labels, confs=confs, counts=counts)
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    barrier()
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    t_all0 = torch.cuda.Event(enable_timing=True); t_all1 = torch.cuda.Event(enable_timing=True)
+    t_all0.record()
+    for a, b in evs:
+        a.record(); step(); b.record()
+    t_all1.record()
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    total_ms = max_over_ranks(t_all0.elapsed_time(t_all1))
+    kernel_ms = float(np.mean([a.elapsed_time(b) for a, b in evs]))
+    ms_per_step = total_ms / args.steps
+    value = F * A * world / (ms_per_step * 1e-3)
+    # labels of the timed pass must equal the run's own (same centres, same frames)
+    same = bool(np.array_equal(labels.view(F, M).cpu().numpy(), st.traj))
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant kernel (K1) -------------------------------------------------------
+    lib = _native.load()
+    fp32, fp64, sfu = C.c_double(), C.c_double(), C.c_double()
+    _native.check(lib.sitb_microbench(local, C.byref(fp32), C.byref(fp64), C.byref(sfu)))
+    E, X, nnz = work_counters(system, cfg, frames)
+    S = system.n_static
+    ops_per_lvec = 47.0 * S + 2.0 * E + 4.0 * X + 2.0 * nnz
+    lvec_per_launch = F * M
+    achieved = ops_per_lvec * lvec_per_launch / (kernel_ms * 1e-3)
+    peaks, peaks_src = measured_peaks()
+    bytes_per_launch = F * (24.0 * A + 16.0 * M)
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "k1_traffic.json")
+    if os.path.isfile(tp):
+        try:
+            tj = json.load(open(tp))
+            traffic = tj.get("dram_bytes_per_frame", 0.0) * F
+        except Exception:
+            traffic = None
+    roofline = {
+        "kernel": "k_fill<DIAG, MODE_ASSIGN> (fused wrap + lattice check + landmark fill + assign)",
+        "bound": "fp32", "achieved": achieved / 1e12, "peak": fp32.value / 1e12, "unit": "TFLOP/s",
+        "frac": achieved / fp32.value, "traffic": traffic,
+        "note": "FLOP = the FP32-pipe lane operations of SURVEY.md 8d (47*S + 2*E + 4*X + 2*nnz per landmark vector, "
+                "FMA = 1), peak = FFMA issue rate measured on this GPU by sitb_microbench; K1 is issue-bound, not HBM-bound",
+        "ops_per_landmark_vector": ops_per_lvec, "E": E, "X": X, "nnz": nnz,
+        "kernel_ms": kernel_ms, "measured_fp64_tflops": fp64.value / 1e12, "measured_sfu_tops": sfu.value / 1e12,
+        "hbm": {"bound": "hbm", "achieved": bytes_per_launch / (kernel_ms * 1e-3) / 1e9, "peak": peaks["hbm_gbs"],
+                "unit": "GB/s", "frac": bytes_per_launch / (kernel_ms * 1e-3) / 1e9 / peaks["hbm_gbs"],
+                "peak_source": peaks_src, "algorithmic_bytes_per_frame": 24.0 * A + 16.0 * M},
+    }
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic",
+        "config": {"workload": workload_name(system, F), "frames_per_gpu": F, "n_sites": int(n_sites),
+                   "l2": "resident frames (%d MB) larger than L2 (126 MB); every step streams them from HBM" % (frames.nbytes >> 20),
+                   "step": "one K1 pass (fill + assign) over all resident frames, centres from a previous run"},
+        "e2e": e2e, "gpu_launches": args.steps, "clocks": clocks, "roofline": roofline,
+        "labels_match_run": same,
+    }
+    if not args.no_cpu_baseline:
+        line["cpu_baseline"] = cpu_baseline(system, cfg, frames, min(args.cpu_frames, F))
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    a = parse_args()
+    if a.impl == "reference":
+        run_reference_arm(a)
+    else:
+        run_ours(a)

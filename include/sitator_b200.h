@@ -182,6 +182,10 @@ int sitb_jump_analysis(int device, const int64_t* dev_traj, int64_t n_frames, in
                        double* dev_n_ij, uint64_t* dev_total_time, double* dev_lag_sum, uint64_t* dev_lag_n,
                        uint64_t* dev_n_problems, void* cuda_stream);
 
+/* Pipe micro-benchmarks for bench.py's roofline denominators: device-wide FP32 FMA, FP64 FMA and
+ * SFU (ex2) operations per second (one instruction lane = one operation). No reference counterpart. */
+int sitb_microbench(int device, double* fp32_ops, double* fp64_ops, double* sfu_ops);
+
 /* Reference-facing, host buffers in and out: what sitator/landmark/helpers.pyx:12 computes.
  * frames [n_frames][n_atoms][3] float64 -> landmark vectors [n_frames*n_mobile][n_landmarks] float64. */
 int sitb_fill_landmark_vectors_host(sitb_ctx* ctx, const double* host_frames, int64_t n_frames,
