@@ -107,6 +107,20 @@ int sitb_fill_dense_frames(sitb_ctx* ctx, const int64_t* dev_frame_list, int64_t
  * triangle) by sparse outer products in FP64 -- the exact cross-check of the tensor-core SYRK. */
 int sitb_pass_stats(sitb_ctx* ctx, int64_t frame_begin, int64_t n, uint64_t* dev_seen, double* dev_gram_upper);
 
+/* sitb_pass_stats that also keeps every landmark vector in compressed form (they are ~1.5 % dense):
+ * dev_row_ptr[n*M] = offset << 8 | count (all ones: pool exhausted, grow and rerun), entries
+ * (landmark index uint16, value float64) at dev_pool_k/v[offset ...], *dev_cursor = entries used. */
+int sitb_pass_stats_cached(sitb_ctx* ctx, int64_t frame_begin, int64_t n, uint64_t* dev_seen, double* dev_gram_upper,
+                           uint64_t* dev_row_ptr, uint16_t* dev_pool_k, double* dev_pool_v, uint64_t* dev_cursor,
+                           uint64_t capacity);
+/* sitb_pass_assign over rows cached by sitb_pass_stats_cached (same outputs, same semantics); row0 = global
+ * index of the first row.  The later passes of the clustering plugin (cluster/mcl.py:81-83, :98-122) stream the
+ * compressed rows instead of recomputing them. */
+int sitb_assign_sparse(sitb_ctx* ctx, const uint64_t* dev_row_ptr, const uint16_t* dev_pool_k, const double* dev_pool_v,
+                       int64_t n_rows, int64_t row0, double threshold, int64_t* dev_labels, double* dev_confs,
+                       uint64_t* dev_counts, uint64_t* dev_best, double* dev_rep, double* dev_rep_w,
+                       uint64_t* dev_site_best);
+
 /* Cluster centres (cluster/mcl.py:70-96): centres have disjoint supports, so they are given as a
  * landmark -> cluster map (-1 none) and a landmark weight. */
 int sitb_set_centers(sitb_ctx* ctx, const int32_t* host_cluster_of_landmark, const double* host_weight,

@@ -19,6 +19,7 @@ eng = U.engine_for(system, dynamic_lattice_mapping=cfg["dynamic"])
 eng.set_frames(frames)
 src = LandmarkVectorSource(eng)
 seen, cov, graph = gm.landmark_graph(src)
+cov = cov.cpu().numpy()
 print("seen equal", np.array_equal(seen, seen_o), "cov max abs diff", np.abs(cov - cov_o).max(), "rel", (np.abs(cov - cov_o) / (np.abs(cov_o) + 1e-300)).max())
 gg = graph.cpu().numpy()
 print("graph max abs diff", np.abs(gg - graph_o).max())

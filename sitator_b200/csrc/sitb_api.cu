@@ -74,6 +74,8 @@ struct sitb_ctx {
     // centres
     int* d_cid = nullptr;
     double* d_cw = nullptr;
+    int* d_cid_orig = nullptr;        // the same tables in the caller's landmark numbering (sparse-row passes)
+    double* d_cw_orig = nullptr;
     int n_clusters = 0;
     // frames
     const double* d_frames = nullptr;
@@ -89,7 +91,7 @@ static void free_ctx(sitb_ctx* c) {
     cudaSetDevice(c->device);
     cudaFree(c->d_static_idx); cudaFree(c->d_mobile_idx); cudaFree(c->d_ideal); cudaFree(c->d_centers);
     cudaFree(c->d_verts_in); cudaFree(c->d_svd); cudaFree(c->d_qorig); cudaFree(c->d_orig_of); cudaFree(c->d_v0); cudaFree(c->d_b0); cudaFree(c->d_va); cudaFree(c->d_ba);
-    cudaFree(c->d_q64); cudaFree(c->d_acoef); cudaFree(c->d_nverts); cudaFree(c->d_cid); cudaFree(c->d_cw); cudaFree(c->d_frames_owned); cudaFree(c->d_status);
+    cudaFree(c->d_q64); cudaFree(c->d_acoef); cudaFree(c->d_nverts); cudaFree(c->d_cid); cudaFree(c->d_cw); cudaFree(c->d_cid_orig); cudaFree(c->d_cw_orig); cudaFree(c->d_frames_owned); cudaFree(c->d_status);
     delete c;
 }
 
@@ -378,6 +380,12 @@ extern "C" int sitb_set_centers(sitb_ctx* c, const int32_t* cid, const double* w
     for (int k = 0; k < c->L; ++k) { cid_i[c->internal_of[k]] = cid[k]; w_i[c->internal_of[k]] = w[k]; }
     CK(cudaMemcpyAsync(c->d_cid, cid_i.data(), sizeof(int) * (size_t)c->L, cudaMemcpyHostToDevice, c->stream));
     CK(cudaMemcpyAsync(c->d_cw, w_i.data(), sizeof(double) * (size_t)c->L, cudaMemcpyHostToDevice, c->stream));
+    if (!c->d_cid_orig) {
+        CK(cudaMalloc((void**)&c->d_cid_orig, sizeof(int) * (size_t)c->L));
+        CK(cudaMalloc((void**)&c->d_cw_orig, sizeof(double) * (size_t)c->L));
+    }
+    CK(cudaMemcpyAsync(c->d_cid_orig, cid, sizeof(int) * (size_t)c->L, cudaMemcpyHostToDevice, c->stream));
+    CK(cudaMemcpyAsync(c->d_cw_orig, w, sizeof(double) * (size_t)c->L, cudaMemcpyHostToDevice, c->stream));
     CK(cudaStreamSynchronize(c->stream));
     c->n_clusters = n_clusters;
     return SITB_OK;
@@ -431,6 +439,46 @@ extern "C" int sitb_fill_landmark_vectors_host(sitb_ctx* c, const double* host_f
     cudaFree(d_in); cudaFree(d_out);
     if (rc) return rc;
     if (status) return sitb_get_status(c, status);
+    return SITB_OK;
+}
+
+// ---- cached sparse landmark vectors ---------------------------------------------------------------
+namespace sitb {
+cudaError_t launch_assign_sparse(const unsigned long long* row_ptr, const uint16_t* pk, const double* pv,
+                                 long long n_rows, long long row0, int L, const int* cid, const double* cw,
+                                 int n_clusters, double thr, long long* labels, double* confs,
+                                 unsigned long long* counts, unsigned long long* best, double* rep, double* rep_w,
+                                 unsigned long long* site_best, int n_sms, cudaStream_t st);
+}
+
+extern "C" int sitb_pass_stats_cached(sitb_ctx* c, int64_t begin, int64_t n, uint64_t* dev_seen, double* dev_gram,
+                                      uint64_t* dev_row_ptr, uint16_t* dev_pool_k, double* dev_pool_v,
+                                      uint64_t* dev_cursor, uint64_t capacity) {
+    FillParams p;
+    int rc = base_params(c, begin, n, p, "sitb_pass_stats_cached");
+    if (rc) return rc;
+    if (!dev_seen || !dev_gram || !dev_row_ptr || !dev_pool_k || !dev_pool_v || !dev_cursor)
+        return fail(SITB_E_INVALID, "sitb_pass_stats_cached: null output");
+    CK(cudaSetDevice(c->device));
+    p.seen = (unsigned long long*)dev_seen; p.gram = dev_gram;
+    p.sparse_ptr = (unsigned long long*)dev_row_ptr; p.sparse_k = dev_pool_k; p.sparse_v = dev_pool_v;
+    p.sparse_cursor = (unsigned long long*)dev_cursor; p.sparse_capacity = capacity;
+    CK(launch_fill(p, MODE_STATS, c->n_sms, c->stream));
+    return SITB_OK;
+}
+
+extern "C" int sitb_assign_sparse(sitb_ctx* c, const uint64_t* dev_row_ptr, const uint16_t* dev_pool_k,
+                                  const double* dev_pool_v, int64_t n_rows, int64_t row0, double thr,
+                                  int64_t* labels, double* confs, uint64_t* counts, uint64_t* best, double* rep,
+                                  double* rep_w, uint64_t* site_best) {
+    if (!c || !dev_row_ptr || !dev_pool_k || !dev_pool_v || n_rows < 0)
+        return fail(SITB_E_INVALID, "sitb_assign_sparse: bad argument");
+    if (!c->d_cid_orig) return fail(SITB_E_STATE, "sitb_assign_sparse: no centres set (sitb_set_centers)");
+    CK(cudaSetDevice(c->device));
+    CK(launch_assign_sparse((const unsigned long long*)dev_row_ptr, dev_pool_k, dev_pool_v, n_rows, row0, c->L,
+                            c->d_cid_orig, c->d_cw_orig, c->n_clusters, thr, (long long*)labels, confs,
+                            (unsigned long long*)counts, (unsigned long long*)best, rep, rep_w,
+                            (unsigned long long*)site_best, c->n_sms, c->stream));
     return SITB_OK;
 }
 

@@ -28,7 +28,7 @@
 //       argument
 // For triclinic cells 3a is done in exact double (the reference's shift-and-wrap is not a
 // continuous function of position there, so a float screen can not be made conservative).
-#include "sitb_fill.cuh"
+#include "sitb_assign.cuh"
 #include <math_constants.h>
 
 namespace sitb {
@@ -84,21 +84,6 @@ __device__ __forceinline__ double inv_root(double P, int nv) {
         case 4: return 1.0 / sqrt(sqrt(P));
         default: return pow(P, -1.0 / (double)nv);
     }
-}
-
-// lock-protected lexicographic max of (value, first row): slot layout [C] value bits | [C] row | [C] lock
-__device__ __forceinline__ void best_update(unsigned long long* tab, int C, int c, double v, unsigned long long row) {
-    const unsigned long long vb = (unsigned long long)__double_as_longlong(v);     // v >= 0: bits are monotone
-    volatile unsigned long long* val = tab + c;
-    volatile unsigned long long* rw = tab + C + c;
-    if (vb < *val) return;                                  // values only grow: a stale read can only let us in
-    unsigned* lock = (unsigned*)(tab + 2 * (size_t)C + c);
-    while (atomicCAS(lock, 0u, 1u) != 0u) {}
-    __threadfence();
-    const unsigned long long cv = *val, cr = *rw;
-    if (vb > cv || (vb == cv && row < cr)) { *val = vb; *rw = row; }
-    __threadfence();
-    atomicExch(lock, 0u);
 }
 
 // u - round(u) for |u| < 2^22, two adds
@@ -418,23 +403,13 @@ __global__ void __launch_bounds__(DIAG ? 1024 : 512) k_fill(const __grid_constan
                 // centres have disjoint supports (cluster/mcl.py:80): dot = sum over the row's
                 // non-zeros of weight[landmark], grouped by cluster[landmark].  A row touches few
                 // clusters: peel them off one at a time with warp votes.
-                double bestc = 0.0;     // untouched clusters have |dot| = 0; np.argmax -> index 0
-                int bestid = 0;
+                double bestc;           // untouched clusters have |dot| = 0; np.argmax -> index 0
+                int bestid;
                 if (nent <= 32) {
-                    int myc = -1;
-                    double mypr = 0.0;
-                    if (lane < nent) { const int k = ek[lane]; myc = tcid[k]; mypr = ev[lane] * tcw[k]; }
-                    for (;;) {
-                        const int cur = __reduce_min_sync(0xffffffffu, myc >= 0 ? myc : 0x7FFFFFFF);
-                        if (cur == 0x7FFFFFFF) break;
-                        double part = (myc == cur) ? mypr : 0.0;
-                        if (myc == cur) myc = -1;
-#pragma unroll
-                        for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
-                        const double conf = fabs(part);
-                        if (conf > bestc) { bestc = conf; bestid = cur; }     // ascending ids: ties keep the lower
-                        if (p.best && lane == 0) best_update(p.best, p.n_clusters, cur, conf, row_global);
-                    }
+                    int myc[1] = {-1};
+                    double mypr[1] = {0.0};
+                    if (lane < nent) { const int k = ek[lane]; myc[0] = tcid[k]; mypr[0] = ev[lane] * tcw[k]; }
+                    peel_clusters<1>(myc, mypr, lane, p.best, p.n_clusters, row_global, bestc, bestid);
                 } else {
                     int myc[ENTRY_CAP / 32];
                     double mypr[ENTRY_CAP / 32];
@@ -444,23 +419,7 @@ __global__ void __launch_bounds__(DIAG ? 1024 : 512) k_fill(const __grid_constan
                         myc[c] = -1; mypr[c] = 0.0;
                         if (e < nent) { const int k = ek[e]; myc[c] = tcid[k]; mypr[c] = ev[e] * tcw[k]; }
                     }
-                    for (;;) {
-                        int mine = 0x7FFFFFFF;
-#pragma unroll
-                        for (int c = 0; c < ENTRY_CAP / 32; ++c)
-                            if (myc[c] >= 0 && myc[c] < mine) mine = myc[c];
-                        const int cur = __reduce_min_sync(0xffffffffu, mine);
-                        if (cur == 0x7FFFFFFF) break;
-                        double part = 0.0;
-#pragma unroll
-                        for (int c = 0; c < ENTRY_CAP / 32; ++c)
-                            if (myc[c] == cur) { part += mypr[c]; myc[c] = -1; }
-#pragma unroll
-                        for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
-                        const double conf = fabs(part);
-                        if (conf > bestc) { bestc = conf; bestid = cur; }
-                        if (p.best && lane == 0) best_update(p.best, p.n_clusters, cur, conf, row_global);
-                    }
+                    peel_clusters<ENTRY_CAP / 32>(myc, mypr, lane, p.best, p.n_clusters, row_global, bestc, bestid);
                 }
                 long long label = bestid;
                 double conf = bestc;
@@ -484,6 +443,18 @@ __global__ void __launch_bounds__(DIAG ? 1024 : 512) k_fill(const __grid_constan
                     for (int e = lane; e < nent; e += 32) atomicAdd(&hist[ek[e]], 1u);
                 for (int e = lane; e < nent; e += 32) ek[e] = p.tab.orig_of[ek[e]];
                 __syncwarp();
+                if ((MODE == MODE_STATS || MODE == MODE_STAGE) && p.sparse_ptr) {
+                    // keep the row in compressed form: later passes read ~250 B instead of recomputing it
+                    unsigned long long off = 0;
+                    if (lane == 0) off = atomicAdd(p.sparse_cursor, (unsigned long long)nent);
+                    off = __shfl_sync(0xffffffffu, off, 0);
+                    if (off + (unsigned long long)nent <= p.sparse_capacity) {
+                        for (int e = lane; e < nent; e += 32) { p.sparse_k[off + e] = ek[e]; p.sparse_v[off + e] = ev[e]; }
+                        if (lane == 0) p.sparse_ptr[row_local] = (off << 8) | (unsigned long long)nent;
+                    } else if (lane == 0) {
+                        p.sparse_ptr[row_local] = ~0ull;          // pool exhausted: the host grows it and reruns
+                    }
+                }
                 if (MODE == MODE_DENSE) {
                     if (p.dense_f64) {
                         double* o = (double*)p.dense_out + (size_t)row_local * L;

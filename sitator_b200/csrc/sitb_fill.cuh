@@ -74,6 +74,13 @@ struct FillParams {
     __half* stage_hi;            // [Lpad][stage_ld]  (landmark-major: K-major operand for UMMA)
     __half* stage_lo;
     long long stage_ld;
+    // compressed rows (MODE_STATS / MODE_STAGE, optional): row r -> sparse_ptr[r] = offset << 8 | count,
+    // entries (caller's landmark index, value) at sparse_k/v[offset ...]; ~0 marks "pool exhausted"
+    unsigned long long* sparse_ptr;
+    uint16_t* sparse_k;
+    double* sparse_v;
+    unsigned long long* sparse_cursor;
+    unsigned long long sparse_capacity;
     // MODE_ASSIGN
     const int* cid;              // [L] cluster of landmark (internal numbering), -1 none
     const double* cw;            // [L] centre weight of landmark (internal numbering)

@@ -213,6 +213,38 @@ class LandmarkEngine(object):
         _native.check(self._lib.sitb_pass_stats(self._ctx, begin, n, self._ptr(seen), self._ptr(gram)))
         return seen, gram
 
+    def pass_stats_cached(self, seen=None, gram=None, entries_per_row=40):
+        """Pass A that also caches every landmark vector compressed (SparseRows); grows the pool on overflow."""
+        torch = _torch()
+        n_rows = self.n_frames * self.M
+        if seen is None:
+            seen = self._zeros((self.L,), torch.int64)
+        if gram is None:
+            gram = self._zeros((self.L, self.L), torch.float64)
+        while True:
+            cap = int(n_rows * entries_per_row) + 1024
+            rows = SparseRows(self._empty((n_rows,), torch.int64), self._empty((cap,), torch.int16),
+                              self._empty((cap,), torch.float64), self._zeros((1,), torch.int64), cap, n_rows,
+                              self.frame0 * self.M)
+            seen_try, gram_try = seen.clone(), gram.clone()
+            _native.check(self._lib.sitb_pass_stats_cached(
+                self._ctx, 0, self.n_frames, self._ptr(seen_try), self._ptr(gram_try), self._ptr(rows.ptr),
+                self._ptr(rows.k), self._ptr(rows.v), self._ptr(rows.cursor), cap))
+            used = int(rows.cursor.item())
+            if used <= cap:
+                seen.copy_(seen_try); gram.copy_(gram_try)
+                rows.used = used
+                return seen, gram, rows
+            entries_per_row = used / float(n_rows) * 1.05 + 1     # exact requirement is known now
+            self.reset_status()
+
+    def assign_sparse(self, rows, threshold, labels=None, confs=None, counts=None, best=None, rep=None, rep_w=None,
+                      site_best=None):
+        _native.check(self._lib.sitb_assign_sparse(
+            self._ctx, self._ptr(rows.ptr), self._ptr(rows.k), self._ptr(rows.v), rows.n_rows, rows.row0,
+            float(threshold), self._ptr(labels), self._ptr(confs), self._ptr(counts), self._ptr(best), self._ptr(rep),
+            self._ptr(rep_w), self._ptr(site_best)))
+
     def set_centers(self, cluster_of_landmark, weight, n_clusters):
         cid = np.ascontiguousarray(cluster_of_landmark, dtype=np.int32)
         w = np.ascontiguousarray(weight, dtype=np.float64)
@@ -284,6 +316,15 @@ class LandmarkEngine(object):
         _native.check(self._lib.sitb_fill_landmark_vectors_host(
             self._ctx, frames.ctypes.data, frames.shape[0], out.ctypes.data, C.byref(s)))
         return out, EngineStatus(s)
+
+
+class SparseRows(object):
+    """Compressed landmark vectors of the resident frames (device tensors)."""
+
+    def __init__(self, ptr, k, v, cursor, capacity, n_rows, row0):
+        self.ptr, self.k, self.v, self.cursor = ptr, k, v, cursor
+        self.capacity, self.n_rows, self.row0 = capacity, n_rows, row0
+        self.used = 0
 
 
 def new_best_table(n, device):

@@ -12,7 +12,8 @@ Valid clustering params (as in the reference):
  - ``"good_site_projected_threshold"``: minimum inner product of the same pair.
  - everything else goes to :func:`sitator_b200.util.mcl.markov_clustering_device`.
 
-Device passes (each a launch of the fused kernel K1 over the resident frames):
+Device passes (A is a launch of the fused kernel K1 over the resident frames and also caches every
+landmark vector in compressed form; B-D then stream those ~230-byte rows, or rerun K1 if they were not cached):
   A  seen counts + Gram                      -> cov, correlation graph, MCL, per-cluster eigenvectors
   B  best matching landmark vector per cluster (max |centre . x|, first row)       (mcl.py:81-89)
   C  predict + bincount                      -> min_samples filter                  (DotProdClassifier.pyx:86-108)
@@ -57,7 +58,12 @@ def landmark_graph(source):
     eng = source.engine
     lib = _native.load()
     if source.gram_upper is None:
-        seen, gram = eng.pass_stats()
+        # keep the rows compressed for the later passes when they fit comfortably (~400 B per row)
+        free_bytes, _ = torch.cuda.mem_get_info(eng.device)
+        if source.cache_rows and source.n_local * 420 < 0.5 * free_bytes:
+            seen, gram, source.sparse = eng.pass_stats_cached()
+        else:
+            seen, gram = eng.pass_stats()
         if source.comm is not None:
             source.comm.allreduce_sum_(seen)
             source.comm.allreduce_sum_(gram)
@@ -69,7 +75,54 @@ def landmark_graph(source):
     _native.check(lib.sitb_landmark_graph(eng.device.index, C.c_void_p(source.gram_upper.data_ptr()), L,
                                           float(source.n_total), C.c_void_p(cov.data_ptr()),
                                           C.c_void_p(graph.data_ptr()), C.c_void_p(stream)))
-    return source.seen.cpu().numpy(), cov.cpu().numpy(), graph
+    return source.seen.cpu().numpy(), cov, graph
+
+
+def _clusters_on_device(m2):
+    """util/mcl.py:52-60 with only the attractor rows leaving the device."""
+    import torch
+    attractors = torch.nonzero(torch.diagonal(m2) != 0).reshape(-1)
+    rows = (m2.index_select(0, attractors) != 0).cpu().numpy()
+    clusters = set()
+    for r in rows:
+        clusters.add(tuple(r.nonzero()[0]))
+    return list(clusters)
+
+
+def _covariance_blocks(cov, clusters):
+    """cov[cl][:, cl] for every cluster (mcl.py:78), gathered on the device in one indexing call."""
+    import torch
+    ri, ci, sizes = [], [], []
+    for cl in clusters:
+        cl = np.asarray(cl, dtype=np.int64)
+        ri.append(np.repeat(cl, len(cl)))
+        ci.append(np.tile(cl, len(cl)))
+        sizes.append(len(cl))
+    ri = torch.as_tensor(np.concatenate(ri), device=cov.device)
+    ci = torch.as_tensor(np.concatenate(ci), device=cov.device)
+    flat = cov[ri, ci].cpu().numpy()
+    out, o = [], 0
+    for n in sizes:
+        out.append(flat[o:o + n * n].reshape(n, n))
+        o += n * n
+    return out
+
+
+def _to_host(t):
+    """Device -> host through a pinned staging buffer (a pageable .cpu() runs at a fraction of PCIe speed)."""
+    import torch
+    key = (t.dtype, t.numel())
+    h = _PINNED.get(key)                  # page-locking tens of MB costs more than the copy: reuse the staging buffer
+    if h is None:
+        if len(_PINNED) > 8:
+            _PINNED.clear()
+        h = _PINNED[key] = torch.empty(t.numel(), dtype=t.dtype, pin_memory=True)
+    h.copy_(t.reshape(-1), non_blocking=True)
+    torch.cuda.current_stream(t.device).synchronize()
+    return h.numpy().reshape(tuple(t.shape)).copy()
+
+
+_PINNED = {}
 
 
 def _centre_tables(clusters, vectors, L):
@@ -102,7 +155,7 @@ def do_landmark_clustering(landmark_vectors, clustering_params, min_samples, ver
 
     # -- cluster landmarks (mcl.py:66-68)
     m2, n_iter = markov_clustering_device(graph, **params)
-    clusters = clusters_from_matrix(m2.cpu().numpy())
+    clusters = _clusters_on_device(m2)
     logger.debug("Markov clustering converged in %i iterations: %i clusters" % (n_iter, len(clusters)))
     clusters = [list(c) for c in clusters if seen_ntimes[c[0]] > 0]
     n_clusters = len(clusters)
@@ -110,13 +163,13 @@ def do_landmark_clustering(landmark_vectors, clustering_params, min_samples, ver
         raise ValueError("Markov clustering found no landmark cluster that was ever seen")
 
     # -- centres: principal eigenvector of each cluster's covariance block (mcl.py:73-80)
-    vectors = [principal_vector(cov[np.ix_(cl, cl)]) for cl in clusters]
+    vectors = [principal_vector(b) for b in _covariance_blocks(cov, clusters)]
     cid, w = _centre_tables(clusters, vectors, L)
 
     # -- pass B: best matching landmark vector per cluster (mcl.py:81-89)
     eng.set_centers(cid, w, n_clusters)
     best = new_best_table(n_clusters, eng.device)
-    eng.pass_assign(float('nan'), best=best)
+    source.assign(float('nan'), best=best)
     _, best_rows = read_best_table(best, comm)
     best_lvecs = source.rows(best_rows)                                   # (n_clusters, L) float64
     good = np.zeros(n_clusters, dtype=bool)
@@ -143,7 +196,7 @@ def do_landmark_clustering(landmark_vectors, clustering_params, min_samples, ver
     cid, w = _centre_tables(clusters, vectors, L)
     eng.set_centers(cid, w, n_clusters)
     counts = torch.zeros((n_clusters,), dtype=torch.int64, device=eng.device)
-    eng.pass_assign(predict_threshold, counts=counts)
+    source.assign(predict_threshold, counts=counts)
     if comm is not None:
         comm.allreduce_sum_(counts)
     cluster_counts = counts.cpu().numpy()
@@ -172,7 +225,7 @@ def do_landmark_clustering(landmark_vectors, clustering_params, min_samples, ver
     rep = torch.zeros((n_sites, L), dtype=torch.float64, device=eng.device)
     rep_w = torch.zeros((n_sites,), dtype=torch.float64, device=eng.device)
     site_best = new_best_table(n_sites, eng.device)
-    eng.pass_assign(predict_threshold, labels=labels, confs=confs, rep=rep, rep_w=rep_w, site_best=site_best)
+    source.assign(predict_threshold, labels=labels, confs=confs, rep=rep, rep_w=rep_w, site_best=site_best)
     if comm is not None:
         comm.allreduce_sum_(rep)
         comm.allreduce_sum_(rep_w)
@@ -184,8 +237,8 @@ def do_landmark_clustering(landmark_vectors, clustering_params, min_samples, ver
 
     return {
         CLUSTERING_CLUSTER_SIZE: kept_counts,
-        CLUSTERING_LABELS: labels.cpu().numpy(),
-        CLUSTERING_CONFIDENCES: confs.cpu().numpy(),
+        CLUSTERING_LABELS: _to_host(labels),
+        CLUSTERING_CONFIDENCES: _to_host(confs),
         CLUSTERING_LANDMARK_GROUPINGS: clusters,
         CLUSTERING_REPRESENTATIVE_LANDMARKS: reps,
         # device-side copies for the rest of LandmarkAnalysis.run (not part of the reference contract)

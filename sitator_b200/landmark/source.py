@@ -37,9 +37,22 @@ class LandmarkVectorSource(object):
         if np.any(local):
             lr = global_rows[local] - self.row0
             frames = np.unique(lr // eng.M)
-            dense = eng.fill_frames(frames, dtype=torch.float64).cpu().numpy()
-            pos = np.searchsorted(frames, lr // eng.M)
-            out[local] = dense[pos * eng.M + lr % eng.M]
+            dense = eng.fill_frames(frames, dtype=torch.float64)            # (len(frames) * M, L) on the device
+            pos = np.searchsorted(frames, lr // eng.M) * eng.M + lr % eng.M
+            sel = dense.index_select(0, torch.as_tensor(pos, device=dense.device))
+            out[local] = sel.cpu().numpy()
         if self.comm is not None:
             out = self.comm.allreduce_sum_numpy(out)
         return out
+
+    # set by the plugin's first pass when the rows were cached (engine.SparseRows)
+    sparse = None
+    cache_rows = True
+
+    def assign(self, threshold, **outputs):
+        """One assign pass over all local landmark vectors: from the cached compressed rows if present,
+        otherwise by rerunning the fused fill + assign kernel over the resident frames."""
+        if self.sparse is not None:
+            self.engine.assign_sparse(self.sparse, threshold, **outputs)
+        else:
+            self.engine.pass_assign(threshold, **outputs)
