@@ -13,7 +13,8 @@ namespace sitb {
 cudaError_t launch_tables(const Cell& cell, const double* centers, const double* ideal, const int* verts_in, int L,
                           int V, int S, double cutoff, double* svd_out, double* q_out, cudaStream_t stream);
 void build_landmark_tables(const Cell& cell, int L, int V, int Lpad, int NB, int S, double steep_log2e,
-                           const int* verts_in, const double* svd, const double* q, HostTables& out);
+                           const int* verts_in, const double* ideal, const double* svd, const double* q,
+                           HostTables& out);
 }
 
 using namespace sitb;
@@ -62,6 +63,8 @@ struct sitb_ctx {
     double* d_svd = nullptr;
     double* d_qorig = nullptr;
     uint16_t* d_orig_of = nullptr;
+    ushort4* d_chunk_atoms = nullptr;
+    float4* d_chunk_bound = nullptr;
     std::vector<int> internal_of;     // caller's landmark index -> internal
     std::vector<double> h_svd, h_qorig;
     uint16_t* d_v0 = nullptr;
@@ -90,6 +93,7 @@ static void free_ctx(sitb_ctx* c) {
     if (!c) return;
     cudaSetDevice(c->device);
     cudaFree(c->d_static_idx); cudaFree(c->d_mobile_idx); cudaFree(c->d_ideal); cudaFree(c->d_centers);
+    cudaFree(c->d_chunk_atoms); cudaFree(c->d_chunk_bound);
     cudaFree(c->d_verts_in); cudaFree(c->d_svd); cudaFree(c->d_qorig); cudaFree(c->d_orig_of); cudaFree(c->d_v0); cudaFree(c->d_b0); cudaFree(c->d_va); cudaFree(c->d_ba);
     cudaFree(c->d_q64); cudaFree(c->d_acoef); cudaFree(c->d_nverts); cudaFree(c->d_cid); cudaFree(c->d_cw); cudaFree(c->d_cid_orig); cudaFree(c->d_cw_orig); cudaFree(c->d_frames_owned); cudaFree(c->d_status);
     delete c;
@@ -208,7 +212,9 @@ extern "C" int sitb_create(const sitb_network_desc* d, int device, sitb_ctx** ou
     {
         HostTables ht;
         build_landmark_tables(c->cell, c->L, c->V, c->Lpad, c->NB, c->S, steep_log2e, d->host_verts,
-                              c->h_svd.data(), c->h_qorig.data(), ht);
+                              d->host_ideal_static, c->h_svd.data(), c->h_qorig.data(), ht);
+        CKC(upload(&c->d_chunk_atoms, ht.chunk_atoms.data(), ht.chunk_atoms.size()));
+        CKC(upload(&c->d_chunk_bound, ht.chunk_bound.data(), ht.chunk_bound.size()));
         c->internal_of = ht.internal_of;
         CKC(upload(&c->d_v0, ht.v0.data(), ht.v0.size()));
         CKC(upload(&c->d_b0, ht.b0.data(), ht.b0.size()));
@@ -328,6 +334,7 @@ static int base_params(sitb_ctx* c, int64_t begin, int64_t n, FillParams& p, con
     p.static_idx = c->d_static_idx; p.mobile_idx = c->d_mobile_idx; p.ideal = c->d_ideal;
     p.tab.v0 = c->d_v0; p.tab.b0 = c->d_b0; p.tab.va = c->d_va; p.tab.ba = c->d_ba;
     p.tab.q64 = c->d_q64; p.tab.acoef = c->d_acoef; p.tab.nverts = c->d_nverts; p.tab.orig_of = c->d_orig_of;
+    p.tab.chunk_atoms = c->d_chunk_atoms; p.tab.chunk_bound = c->d_chunk_bound;
     p.bcoef = c->bcoef; p.static_thr = c->static_thr; p.dynamic = c->dynamic; p.relaxed = c->relaxed;
     p.errkey = c->d_status; p.counters = c->d_status + 2;
     p.cid = c->d_cid; p.cw = c->d_cw; p.n_clusters = c->n_clusters;

@@ -6,12 +6,19 @@
 
 namespace sitb {
 
-// lock-protected lexicographic max of (value, first row): slot layout [C] value bits | [C] row | [C] lock
-__device__ __forceinline__ void best_update(unsigned long long* tab, int C, int c, double v, unsigned long long row) {
+// lock-protected lexicographic max of (value, first row): slot layout [C] value bits | [C] row | [C] lock.
+// cache (optional, shared memory, [C] value bits): a per-CTA lower bound of the global maximum; values
+// only grow, so a candidate below the cache is below the global table too.
+__device__ __forceinline__ void best_update(unsigned long long* tab, int C, int c, double v, unsigned long long row,
+                                            unsigned long long* cache = nullptr) {
     const unsigned long long vb = (unsigned long long)__double_as_longlong(v);     // v >= 0: bits are monotone
+    if (cache) {
+        if (vb < *((volatile unsigned long long*)(cache + c))) return;
+        atomicMax(cache + c, vb);
+    }
     volatile unsigned long long* val = tab + c;
     volatile unsigned long long* rw = tab + C + c;
-    if (vb < *val) return;                                  // values only grow: a stale read can only let us in
+    if (vb < *val) return;                                  // a stale read can only let us in
     unsigned* lock = (unsigned*)(tab + 2 * (size_t)C + c);
     while (atomicCAS(lock, 0u, 1u) != 0u) {}
     __threadfence();
@@ -27,7 +34,8 @@ __device__ __forceinline__ void best_update(unsigned long long* tab, int C, int 
 template <int NCH>
 __device__ __forceinline__ void peel_clusters(int (&myc)[NCH], double (&mypr)[NCH], int lane,
                                               unsigned long long* best_tab, int n_clusters,
-                                              unsigned long long row_global, double& bestc, int& bestid) {
+                                              unsigned long long row_global, double& bestc, int& bestid,
+                                              unsigned long long* best_cache = nullptr) {
     bestc = 0.0;
     bestid = 0;
     for (;;) {
@@ -45,7 +53,7 @@ __device__ __forceinline__ void peel_clusters(int (&myc)[NCH], double (&mypr)[NC
         for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
         const double conf = fabs(part);
         if (conf > bestc) { bestc = conf; bestid = cur; }     // ascending ids: ties keep the lower
-        if (best_tab && lane == 0) best_update(best_tab, n_clusters, cur, conf, row_global);
+        if (best_tab && lane == 0) best_update(best_tab, n_clusters, cur, conf, row_global, best_cache);
     }
 }
 

@@ -36,7 +36,7 @@ namespace sitb {
 struct SmemLayout {
     int Spad, Mpad, qstride;
     size_t off_ss, off_sm, off_ba, off_b0, off_fs, off_fm, off_wqf, off_wev, off_hist, off_lmap, off_seen,
-        off_cw, off_va, off_v0, off_cid, off_wcand, off_wek, off_task, total;
+        off_cw, off_va, off_v0, off_cid, off_wcand, off_wek, off_task, off_ca, off_cb, total;
 };
 
 __host__ __device__ inline SmemLayout make_layout(int S, int M, int L, int Lpad, int NB, int warps, int fb, int mode,
@@ -50,7 +50,9 @@ __host__ __device__ inline SmemLayout make_layout(int S, int M, int L, int Lpad,
     l.off_wev = o;   o += sizeof(double) * (size_t)warps * ENTRY_CAP;
     l.off_cw = o;    o += (mode == MODE_ASSIGN) ? sizeof(double) * (size_t)Lpad : 0;
     l.off_sm = o;    o += sizeof(double) * 3 * (size_t)M * fb;
+    o = (o + 15) & ~(size_t)15;
     l.off_ba = o;    o += sizeof(float4) * (size_t)NB * Lpad;
+    l.off_cb = o;    o += sizeof(float4) * (size_t)(Lpad / 32);
     l.off_b0 = o;    o += sizeof(float) * (size_t)Lpad;
     l.off_fs = o;    o += sizeof(float) * 3 * (size_t)l.Spad * fb;
     l.off_fm = o;    o += sizeof(float) * 3 * (size_t)l.Mpad * fb;
@@ -62,6 +64,7 @@ __host__ __device__ inline SmemLayout make_layout(int S, int M, int L, int Lpad,
     l.off_seen = o;  o += dynamic ? sizeof(unsigned) * (size_t)l.Spad * fb : 0;
     o = (o + 7) & ~(size_t)7;
     l.off_va = o;    o += sizeof(ushort4) * (size_t)NB * Lpad;
+    l.off_ca = o;    o += sizeof(ushort4) * (size_t)(Lpad / 32);
     l.off_v0 = o;    o += sizeof(uint16_t) * (size_t)Lpad;
     l.off_cid = o;   o += (mode == MODE_ASSIGN) ? sizeof(int16_t) * (size_t)Lpad : 0;
     l.off_wcand = o; o += sizeof(uint16_t) * (size_t)warps * CAND_CAP;
@@ -79,9 +82,9 @@ __host__ __device__ inline SmemLayout make_layout(int S, int M, int L, int Lpad,
 __device__ __forceinline__ double inv_root(double P, int nv) {
     switch (nv) {
         case 1: return 1.0 / P;
-        case 2: return 1.0 / sqrt(P);
-        case 3: return 1.0 / cbrt(P);
-        case 4: return 1.0 / sqrt(sqrt(P));
+        case 2: return rsqrt(P);
+        case 3: return rcbrt(P);
+        case 4: return rsqrt(sqrt(P));
         default: return pow(P, -1.0 / (double)nv);
     }
 }
@@ -102,13 +105,15 @@ __device__ __forceinline__ int warp_incl_scan(int v, int lane) {
 }
 
 template <bool DIAG, int MODE>
-__global__ void __launch_bounds__(DIAG ? 1024 : 512) k_fill(const __grid_constant__ FillParams p, const int FB) {
+__global__ void __launch_bounds__(DIAG ? 1024 : 512) k_fill(const __grid_constant__ FillParams p, const int FB,
+                                                            const __grid_constant__ SmemLayout lay) {
+    // (the layout is computed by the host and read from the constant bank: under the 64-register cap
+    // the compiler otherwise rebuilds these offsets inside the hot loops)
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
     const int nwarps = blockDim.x >> 5;
     const int S = p.S, M = p.M, L = p.L, Lpad = p.Lpad, NB = p.NB;
-    const SmemLayout lay = make_layout(S, M, L, Lpad, NB, nwarps, FB, MODE, p.n_clusters, p.dynamic);
     const int Spad = lay.Spad, Mpad = lay.Mpad;
     double* ss = (double*)(smem_raw + lay.off_ss);          // [FB][S][3] wrapped statics (double)
     double* sm = (double*)(smem_raw + lay.off_sm);          // [FB][M][3] wrapped mobiles (double)
@@ -128,8 +133,14 @@ __global__ void __launch_bounds__(DIAG ? 1024 : 512) k_fill(const __grid_constan
     uint16_t* cand = (uint16_t*)(smem_raw + lay.off_wcand) + (size_t)warp * CAND_CAP;
     uint16_t* ek = (uint16_t*)(smem_raw + lay.off_wek) + (size_t)warp * ENTRY_CAP;
     int* task_counter = (int*)(smem_raw + lay.off_task);
+    ushort4* tca = (ushort4*)(smem_raw + lay.off_ca);       // [Lpad/32] chunk skip table: atoms
+    float4* tcb = (float4*)(smem_raw + lay.off_cb);         // [Lpad/32] chunk skip table: bounds
 
     // ---- stage the landmark tables once per CTA ------------------------------------------
+    for (int i = threadIdx.x; i < (Lpad >> 5); i += blockDim.x) {
+        tca[i] = p.tab.chunk_atoms[i];
+        tcb[i] = p.tab.chunk_bound[i];
+    }
     for (int i = threadIdx.x; i < NB * Lpad; i += blockDim.x) {
         tba[i] = p.tab.ba[i];
         tva[i] = p.tab.va[i];
@@ -288,39 +299,32 @@ __global__ void __launch_bounds__(DIAG ? 1024 : 512) k_fill(const __grid_constan
             __syncwarp();
 
             int nsurv = 0, ncand = 0;
-            for (int kb = 0; kb < Lpad; kb += CAND_CAP) {
-                // 3b. first vertex of every landmark in the block: one pass bit per sub-iteration
-                // (Lpad is a multiple of 256: groups of 8 sub-iterations, fully unrolled)
-                const int ngroups = ((Lpad - kb) < CAND_CAP ? (Lpad - kb) : CAND_CAP) >> 8;
-                unsigned mask = 0u;
-                for (int g = 0; g < ngroups; ++g) {
-                    const uint16_t* v0p = tv0 + kb + 256 * g + lane;
-                    const float* b0p = tb0 + kb + 256 * g + lane;
-                    unsigned vtx[8];
-                    float bnd[8], qv[8];
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) { vtx[i] = v0p[32 * i]; bnd[i] = b0p[32 * i]; }
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) qv[i] = qfw[vtx[i]];
-                    unsigned m8 = 0u;
-#pragma unroll
-                    for (int i = 0; i < 8; ++i)
-                        if (!(qv[i] > bnd[i])) m8 |= 1u << i;
-                    mask |= m8 << (8 * g);
+            const int n_chunks = Lpad >> 5;
+            for (int c0 = 0; c0 < n_chunks; c0 += 32) {
+                // 3b. chunks of 32 landmarks (renumbered along a Morton curve of their first vertex): a lane
+                // tests one chunk -- is any of its (<= 4) first-vertex atoms within its loosest bound? --
+                // then only the active chunks (~30 %) test their 32 landmarks' first vertex.
+                bool act = false;
+                if (c0 + lane < n_chunks) {
+                    const ushort4 ca = tca[c0 + lane];
+                    const float4 cb = tcb[c0 + lane];
+                    act = !(qfw[ca.x] > cb.x) || !(qfw[ca.y] > cb.y) || !(qfw[ca.z] > cb.z) || !(qfw[ca.w] > cb.w);
                 }
-                const int cnt = __popc(mask);
-                const int incl = warp_incl_scan(cnt, lane);
-                const int total = __shfl_sync(0xffffffffu, incl, 31);
-                int pos = ncand + incl - cnt;
-                while (mask) {
-                    const int u = __ffs(mask) - 1;
-                    mask &= mask - 1u;
-                    cand[pos++] = (uint16_t)(kb + 32 * u + lane);
+                unsigned active = __ballot_sync(0xffffffffu, act);
+                for (;;) {
+                while (active) {
+                    const int c = c0 + __ffs(active) - 1;
+                    active &= active - 1u;
+                    const int k = 32 * c + lane;
+                    const bool ok = !(qfw[tv0[k]] > tb0[k]);
+                    const unsigned m = __ballot_sync(0xffffffffu, ok);
+                    if (ok) cand[ncand + __popc(m & lanemask_lt())] = (uint16_t)k;
+                    ncand += __popc(m);
+                    if (ncand + 32 > CAND_CAP) break;      // list full: resume this round after 3c
                 }
-                ncand += total;
                 __syncwarp();
-                // run 3c when the next block could overflow the candidate list, or at the end
-                if (ncand + CAND_CAP <= CAND_CAP && kb + CAND_CAP < Lpad) continue;
+                // run 3c when the list is (nearly) full or all chunks are done; otherwise keep collecting
+                if (active == 0u && c0 + 32 < n_chunks && ncand + 32 <= CAND_CAP) break;
                 // 3c. remaining vertices of the candidates -> survivors appended to ek[]
                 for (int i0 = 0; i0 < ncand; i0 += 32) {
                     const int i = i0 + lane;
@@ -345,6 +349,8 @@ __global__ void __launch_bounds__(DIAG ? 1024 : 512) k_fill(const __grid_constan
                 }
                 ncand = 0;
                 __syncwarp();
+                if (active == 0u) break;
+                }
             }
             if (nsurv > ENTRY_CAP) { if (lane == 0) ++loc_over; nsurv = ENTRY_CAP; }
 
@@ -558,7 +564,8 @@ static cudaError_t launch_one(const FillParams& p, int n_sms, cudaStream_t strea
     long long grid = (long long)n_sms * per_sm;
     if (grid > batches) grid = batches;
     if (grid < 1) return cudaSuccess;
-    kern<<<(unsigned)grid, best_w * 32, best_bytes, stream>>>(p, best_fb);
+    const SmemLayout lay = make_layout(p.S, p.M, p.L, p.Lpad, p.NB, best_w, best_fb, MODE, p.n_clusters, p.dynamic);
+    kern<<<(unsigned)grid, best_w * 32, best_bytes, stream>>>(p, best_fb, lay);
     return cudaGetLastError();
 }
 

@@ -34,6 +34,8 @@ struct LandmarkTables {
     const double* acoef;    // [Lpad][4*NB] steepness/site_vert_dist
     const uint8_t* nverts;  // [Lpad]
     const uint16_t* orig_of;// [Lpad] internal landmark number -> the caller's landmark index
+    const ushort4* chunk_atoms;  // [Lpad/32] distinct first-vertex atoms of each 32-landmark chunk (S = none)
+    const float4* chunk_bound;   // [Lpad/32] loosest first-vertex bound per such atom (-1 = none)
 };
 
 // Host-side image of the tables (sitb_tables.cu: build_landmark_tables).  Landmarks are renumbered
@@ -46,6 +48,8 @@ struct HostTables {
     std::vector<double> q64, acoef;
     std::vector<uint8_t> nverts;
     std::vector<uint16_t> orig_of;
+    std::vector<ushort4> chunk_atoms;
+    std::vector<float4> chunk_bound;
     std::vector<int> internal_of;   // [L] caller's index -> internal
 };
 

@@ -64,7 +64,8 @@ __global__ void k_colsum(const double* __restrict__ m, int n, double* __restrict
     const int j = blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= n) return;
     double s = 0.0;
-    for (int i = 0; i < n; ++i) s = __dadd_rn(s, m[(size_t)i * n + j]);
+#pragma unroll 16
+    for (int i = 0; i < n; ++i) s = __dadd_rn(s, m[(size_t)i * n + j]);     // loads pipeline, adds stay in order
     out[j] = s;
 }
 
@@ -86,6 +87,7 @@ __global__ void k_colargmax(const double* __restrict__ m, int n, int* __restrict
     if (j >= n) return;
     double best = m[j];
     int bi = 0;
+#pragma unroll 16
     for (int i = 1; i < n; ++i) {
         const double v = m[(size_t)i * n + j];
         if (v > best) { best = v; bi = i; }

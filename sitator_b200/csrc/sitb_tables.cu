@@ -87,7 +87,8 @@ static float screen_bound(const Cell& cell, double Q) {
 }
 
 void build_landmark_tables(const Cell& cell, int L, int V, int Lpad, int NB, int S, double steep_log2e,
-                           const int* verts_in, const double* svd, const double* q, HostTables& out) {
+                           const int* verts_in, const double* ideal, const double* svd, const double* q,
+                           HostTables& out) {
     const int W = 4 * NB;
     // vertex order per landmark: tightest cut-off first, the rest in the reference's order
     std::vector<int> nv(L), first(L);
@@ -100,11 +101,28 @@ void build_landmark_tables(const Cell& cell, int L, int V, int Lpad, int NB, int
             if (q[(size_t)k * V + h] < q[(size_t)k * V + best]) best = h;
         first[k] = best;
     }
-    // renumber: by first-vertex atom, then by original index
+    // renumber: by the position of the first-vertex atom along a Morton curve (so that the landmarks a
+    // mobile atom can see sit in few 32-landmark chunks), then by atom, then by original index
+    std::vector<unsigned> morton(S, 0u);
+    for (int s = 0; s < S; ++s) {
+        unsigned code = 0;
+        unsigned g[3];
+        for (int d = 0; d < 3; ++d) {
+            double f = cell.ci[3 * d] * ideal[3 * s] + cell.ci[3 * d + 1] * ideal[3 * s + 1] + cell.ci[3 * d + 2] * ideal[3 * s + 2];
+            f -= std::floor(f);
+            int v = (int)(f * 1024.0);
+            g[d] = (unsigned)(v < 0 ? 0 : (v > 1023 ? 1023 : v));
+        }
+        for (int b = 9; b >= 0; --b)
+            for (int d = 0; d < 3; ++d) code = (code << 1) | ((g[d] >> b) & 1u);
+        morton[s] = code;
+    }
     std::vector<int> order(L);
     std::iota(order.begin(), order.end(), 0);
     std::stable_sort(order.begin(), order.end(), [&](int a, int b) {
-        return verts_in[(size_t)a * V + first[a]] < verts_in[(size_t)b * V + first[b]];
+        const int va = verts_in[(size_t)a * V + first[a]], vb = verts_in[(size_t)b * V + first[b]];
+        if (morton[va] != morton[vb]) return morton[va] < morton[vb];
+        return va < vb;
     });
     out.v0.assign(Lpad, (uint16_t)S);
     out.b0.assign(Lpad, -1.0f);
@@ -141,6 +159,40 @@ void build_landmark_tables(const Cell& cell, int L, int V, int Lpad, int NB, int
         for (int blk = 0; blk < NB; ++blk) {
             out.va[(size_t)blk * Lpad + ki] = make_ushort4(vs[4 * blk], vs[4 * blk + 1], vs[4 * blk + 2], vs[4 * blk + 3]);
             out.ba[(size_t)blk * Lpad + ki] = make_float4(bs[4 * blk], bs[4 * blk + 1], bs[4 * blk + 2], bs[4 * blk + 3]);
+        }
+    }
+    // chunk skip table: per 32 consecutive landmarks, the (up to 4) distinct first-vertex atoms and, per
+    // atom, the loosest first-vertex bound among the chunk's landmarks that use it.  A chunk whose atoms
+    // all lie beyond their bound holds no candidate.  More than 4 distinct atoms: never skipped.
+    const int n_chunks = Lpad / 32;
+    out.chunk_atoms.assign(n_chunks, make_ushort4((uint16_t)S, (uint16_t)S, (uint16_t)S, (uint16_t)S));
+    out.chunk_bound.assign(n_chunks, make_float4(-1.f, -1.f, -1.f, -1.f));
+    for (int c = 0; c < n_chunks; ++c) {
+        uint16_t at[4];
+        float bd[4];
+        int n = 0;
+        bool overflow = false;
+        for (int i = 0; i < 32; ++i) {
+            const int ki = 32 * c + i;
+            if (ki >= L) break;
+            const uint16_t a = out.v0[ki];
+            const float b = out.b0[ki];
+            int j = 0;
+            while (j < n && at[j] != a) ++j;
+            if (j == n) {
+                if (n == 4) { overflow = true; break; }
+                at[n] = a; bd[n] = b; ++n;
+            } else if (b > bd[j]) {
+                bd[j] = b;
+            }
+        }
+        if (overflow) {   // dummy atom S has screen distance 0: 0 <= +inf always passes
+            out.chunk_atoms[c] = make_ushort4((uint16_t)S, (uint16_t)S, (uint16_t)S, (uint16_t)S);
+            out.chunk_bound[c] = make_float4(inf, inf, inf, inf);
+        } else {
+            for (int j = n; j < 4; ++j) { at[j] = (uint16_t)S; bd[j] = -1.f; }
+            out.chunk_atoms[c] = make_ushort4(at[0], at[1], at[2], at[3]);
+            out.chunk_bound[c] = make_float4(bd[0], bd[1], bd[2], bd[3]);
         }
     }
 }

@@ -109,20 +109,14 @@ def _covariance_blocks(cov, clusters):
 
 
 def _to_host(t):
-    """Device -> host through a pinned staging buffer (a pageable .cpu() runs at a fraction of PCIe speed)."""
+    """Device -> host into page-locked memory (a pageable .cpu() runs at a fraction of PCIe speed).  The
+    returned array owns the pinned block; torch's caching host allocator recycles it once the caller
+    drops the result, so repeated analyses do not pay for page-locking again."""
     import torch
-    key = (t.dtype, t.numel())
-    h = _PINNED.get(key)                  # page-locking tens of MB costs more than the copy: reuse the staging buffer
-    if h is None:
-        if len(_PINNED) > 8:
-            _PINNED.clear()
-        h = _PINNED[key] = torch.empty(t.numel(), dtype=t.dtype, pin_memory=True)
-    h.copy_(t.reshape(-1), non_blocking=True)
+    h = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
+    h.copy_(t, non_blocking=True)
     torch.cuda.current_stream(t.device).synchronize()
-    return h.numpy().reshape(tuple(t.shape)).copy()
-
-
-_PINNED = {}
+    return h.numpy()
 
 
 def _centre_tables(clusters, vectors, L):
