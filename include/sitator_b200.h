@@ -196,6 +196,20 @@ int sitb_jump_analysis(int device, const int64_t* dev_traj, int64_t n_frames, in
                        double* dev_n_ij, uint64_t* dev_total_time, double* dev_lag_sum, uint64_t* dev_lag_n,
                        uint64_t* dev_n_problems, void* cuda_stream);
 
+/* Tensor-core alternative for the landmark Gram (the covariance input of cluster/mcl.py:53).
+ * Staging buffers: two zero-filled fp16 arrays of lpad * ld elements (lpad % 128 == 0, ld % 64 == 0) holding the
+ *   transposed landmark vectors as value = hi + lo * 2^-12, stored as contiguous 16 KB tiles: tile (rt, kt) =
+ *   landmarks [128 rt, +128) x rows [64 kt, +64) starts at element ((rt * ld/64) + kt) * 8192 and element (r, k)
+ *   of a tile sits at r*64 + (((k >> 3) ^ (r & 7)) << 3) + (k & 7)   (the tensor core's 128-byte swizzle).
+ * sitb_pass_stage: the fused kernel writes every landmark vector of frames [begin, begin+n) into them (row =
+ *   (frame - begin) * n_mobile + mobile index; ld >= n * n_mobile); dev_seen [L] uint64 +=.
+ * sitb_gram_syrk_tc: dev_gram_upper [L][L] f64 (upper triangle) += Hi.Hi^T + 2^-12 (Hi.Lo^T + Lo.Hi^T) over the
+ *   first k_rows rows, on tcgen05 tensor cores with TMA-fed shared-memory tiles and TMEM accumulators. */
+int sitb_pass_stage(sitb_ctx* ctx, int64_t begin, int64_t n, uint64_t* dev_seen, void* dev_stage_hi,
+                    void* dev_stage_lo, int64_t ld);
+int sitb_gram_syrk_tc(int device, const void* dev_stage_hi, const void* dev_stage_lo, int32_t n_landmarks,
+                      int32_t lpad, int64_t ld, int64_t k_rows, double* dev_gram_upper, void* cuda_stream);
+
 /* Pipe micro-benchmarks for bench.py's roofline denominators: device-wide FP32 FMA, FP64 FMA and
  * SFU (ex2) operations per second (one instruction lane = one operation). No reference counterpart. */
 int sitb_microbench(int device, double* fp32_ops, double* fp64_ops, double* sfu_ops);

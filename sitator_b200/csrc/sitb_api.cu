@@ -489,6 +489,21 @@ extern "C" int sitb_assign_sparse(sitb_ctx* c, const uint64_t* dev_row_ptr, cons
     return SITB_OK;
 }
 
+// ---- staging for the tensor-core Gram (sitb_gram_tc.cu) ---------------------------------------------
+extern "C" int sitb_pass_stage(sitb_ctx* c, int64_t begin, int64_t n, uint64_t* dev_seen, void* dev_stage_hi,
+                               void* dev_stage_lo, int64_t ld) {
+    FillParams p;
+    int rc = base_params(c, begin, n, p, "sitb_pass_stage");
+    if (rc) return rc;
+    if (!dev_seen || !dev_stage_hi || !dev_stage_lo || ld < n * c->M || ld % 64 != 0)
+        return fail(SITB_E_INVALID, "sitb_pass_stage: bad argument (ld must hold n * n_mobile rows and be a multiple of 64)");
+    CK(cudaSetDevice(c->device));
+    p.seen = (unsigned long long*)dev_seen;
+    p.stage_hi = (__half*)dev_stage_hi; p.stage_lo = (__half*)dev_stage_lo; p.stage_ld = ld;
+    CK(launch_fill(p, MODE_STAGE, c->n_sms, c->stream));
+    return SITB_OK;
+}
+
 // ---- site centres (LandmarkAnalysis.py:276-287, PBCCalculator.pyx:106-139) -----------------------
 namespace sitb {
 cudaError_t launch_wrapped_rows(const Cell& cell, const double* frames, int A, int M, const int* mobile_idx,

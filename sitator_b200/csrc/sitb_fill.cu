@@ -486,8 +486,11 @@ __global__ void __launch_bounds__(DIAG ? 1024 : 512) k_fill(const __grid_constan
                     for (int e = lane; e < nent; e += 32) {
                         const double v = ev[e];
                         const __half hi = __double2half(v);
-                        const __half lo = __double2half(v - (double)__half2float(hi));
-                        const size_t o = (size_t)ek[e] * (size_t)p.stage_ld + (size_t)row_local;
+                        const __half lo = __double2half((v - (double)__half2float(hi)) * 4096.0);   // scaled: stays normal
+                        // tile (landmark / 128, row / 64), element (r, k) at the 128B-swizzled K-major position
+                        const unsigned l = ek[e], r = l & 127u, k = (unsigned)(row_local & 63);
+                        const size_t o = (((size_t)(l >> 7) * (size_t)(p.stage_ld >> 6) + (size_t)(row_local >> 6)) << 13) +
+                                         (size_t)(r * 64u + ((((k >> 3) ^ (r & 7u)) << 3) | (k & 7u)));
                         p.stage_hi[o] = hi;
                         p.stage_lo[o] = lo;
                     }

@@ -75,9 +75,9 @@ struct FillParams {
     // MODE_STATS / MODE_STAGE
     unsigned long long* seen;    // [L]
     double* gram;                // [L][L] upper triangle (+=)
-    __half* stage_hi;            // [Lpad][stage_ld]  (landmark-major: K-major operand for UMMA)
+    __half* stage_hi;            // [Lpad/128][stage_ld/64] pre-swizzled 128x64 tiles (sitb_gram_tc.cu)
     __half* stage_lo;
-    long long stage_ld;
+    long long stage_ld;          // rows the staging buffers hold (multiple of 64)
     // compressed rows (MODE_STATS / MODE_STAGE, optional): row r -> sparse_ptr[r] = offset << 8 | count,
     // entries (caller's landmark index, value) at sparse_k/v[offset ...]; ~0 marks "pool exhausted"
     unsigned long long* sparse_ptr;

@@ -213,6 +213,32 @@ class LandmarkEngine(object):
         _native.check(self._lib.sitb_pass_stats(self._ctx, begin, n, self._ptr(seen), self._ptr(gram)))
         return seen, gram
 
+    def pass_stats_tc(self, begin=0, n=None, seen=None, gram=None, block_frames=16384):
+        """Pass A with the Gram on tcgen05 tensor cores: K1 stages each block of frames as transposed fp16
+        hi/lo tiles, sitb_gram_syrk_tc accumulates them into the FP64 upper triangle.  Same outputs as
+        :meth:`pass_stats`; the Gram agrees to ~1e-7 relative (fp16 hi+lo operands drop the lo.lo term)."""
+        torch = _torch()
+        n = self.n_frames - begin if n is None else n
+        if seen is None:
+            seen = self._zeros((self.L,), torch.int64)
+        if gram is None:
+            gram = self._zeros((self.L, self.L), torch.float64)
+        block_frames = max(1, min(block_frames, n))
+        ld = -(-(block_frames * self.M) // 64) * 64
+        lpad = -(-self.L // 128) * 128
+        hi = self._empty((lpad, ld), torch.float16)
+        lo = self._empty((lpad, ld), torch.float16)
+        stream = torch.cuda.current_stream(self.device).cuda_stream
+        for b in range(begin, begin + n, block_frames):
+            nb = min(block_frames, begin + n - b)
+            hi.zero_()
+            lo.zero_()
+            _native.check(self._lib.sitb_pass_stage(self._ctx, b, nb, self._ptr(seen), self._ptr(hi), self._ptr(lo), ld))
+            _native.check(self._lib.sitb_gram_syrk_tc(self.device.index, self._ptr(hi), self._ptr(lo), self.L,
+                                                      lpad, ld, nb * self.M, self._ptr(gram),
+                                                      C.c_void_p(stream)))
+        return seen, gram
+
     def pass_stats_cached(self, seen=None, gram=None, entries_per_row=40):
         """Pass A that also caches every landmark vector compressed (SparseRows); grows the pool on overflow."""
         torch = _torch()

@@ -10,6 +10,7 @@ Valid clustering params (as in the reference):
  - ``"good_site_normed_threshold"``: minimum cosine similarity between a site's unit vector and its
    best matching landmark vector.
  - ``"good_site_projected_threshold"``: minimum inner product of the same pair.
+ - ``"gram_method"`` (not in the reference): ``'sparse'`` (exact FP64, default) or ``'tcgen05'`` (tensor cores).
  - everything else goes to :func:`sitator_b200.util.mcl.markov_clustering_device`.
 
 Device passes (A is a launch of the fused kernel K1 over the resident frames and also caches every
@@ -52,15 +53,24 @@ def principal_vector(block):
     return v[:, -1]
 
 
-def landmark_graph(source):
-    """Pass A + mcl.py:53-59.  Returns (seen (L,) int64 numpy, cov (L,L) numpy, graph torch tensor)."""
+def landmark_graph(source, gram_method='sparse'):
+    """Pass A + mcl.py:53-59.  Returns (seen (L,) int64 numpy, cov (L,L) numpy, graph torch tensor).
+
+    ``gram_method``: ``'sparse'`` (default) accumulates the Gram exactly in FP64 from the ~1.5 % dense rows and
+    caches them; ``'tcgen05'`` runs it as a dense SYRK on the tensor cores (fp16 hi/lo operands, FP32 TMEM
+    accumulators drained to FP64; agrees to ~1e-6, see tests/test_gram_tc_gpu.py) and leaves passes B-D to the
+    fused fill+assign kernel."""
     import torch
     eng = source.engine
     lib = _native.load()
+    if gram_method not in ('sparse', 'tcgen05'):
+        raise ValueError("gram_method must be 'sparse' or 'tcgen05', not %r" % (gram_method,))
     if source.gram_upper is None:
         # keep the rows compressed for the later passes when they fit comfortably (~400 B per row)
         free_bytes, _ = torch.cuda.mem_get_info(eng.device)
-        if source.cache_rows and source.n_local * 420 < 0.5 * free_bytes:
+        if gram_method == 'tcgen05':
+            seen, gram = eng.pass_stats_tc()
+        elif source.cache_rows and source.n_local * 420 < 0.5 * free_bytes:
             seen, gram, source.sparse = eng.pass_stats_cached()
         else:
             seen, gram = eng.pass_stats()
@@ -140,7 +150,7 @@ def do_landmark_clustering(landmark_vectors, clustering_params, min_samples, ver
     params = DEFAULT_PARAMS.copy()
     params.update(clustering_params)
 
-    seen_ntimes, cov, graph = landmark_graph(source)
+    seen_ntimes, cov, graph = landmark_graph(source, params.pop('gram_method', 'sparse'))
 
     predict_threshold = params.pop('assignment_threshold')
     good_site_normed_threshold = params.pop('good_site_normed_threshold', predict_threshold)
