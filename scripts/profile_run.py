@@ -16,10 +16,20 @@ for f0 in range(0, F, 20000):
     n = min(20000, F - f0); frames[f0:f0 + n] = system.trajectory(n, seed=f0 // 20000 + 1)
 sn = syn.site_network_for(system)
 T = {}
+G = {}
+ev_last = [None]
 def tick(name, t0):
-    torch.cuda.synchronize(); T[name] = T.get(name, 0) + (time.perf_counter() - t0) * 1e3; return time.perf_counter()
-for rep in range(2):
-    T.clear()
+    e = torch.cuda.Event(enable_timing=True); e.record()
+    torch.cuda.synchronize(); T[name] = T.get(name, 0) + (time.perf_counter() - t0) * 1e3
+    G[name] = G.get(name, 0) + ev_last[0].elapsed_time(e)
+    e2 = torch.cuda.Event(enable_timing=True); e2.record(); ev_last[0] = e2
+    return time.perf_counter()
+REPS = int(sys.argv[2]) if len(sys.argv) > 2 else 4
+for rep in range(REPS):
+    if rep: print("rep", rep - 1, " ".join("%s=%.1f/%.1f" % (k.split()[0], T[k], G[k]) for k in T))
+    T.clear(); G.clear()
+    torch.cuda.synchronize()
+    ev_last[0] = torch.cuda.Event(enable_timing=True); ev_last[0].record()
     t = time.perf_counter()
     eng = LandmarkEngine.from_site_network(sn); t = tick("engine+tables", t)
     eng.set_frames(frames); t = tick("H2D frames", t)
@@ -44,5 +54,5 @@ for rep in range(2):
     eng.site_centers(labels, confs, len(clusters), True, sb); t = tick("site centres", t)
 print("F =", F); tot = 0
 for k, v in T.items():
-    print("  %-32s %8.2f ms" % (k, v)); tot += v
+    print("  %-32s %8.2f ms wall %8.2f ms gpu-span" % (k, v, G[k])); tot += v
 print("  %-32s %8.2f ms" % ("total", tot))

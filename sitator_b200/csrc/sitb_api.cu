@@ -92,18 +92,20 @@ struct sitb_ctx {
 static void free_ctx(sitb_ctx* c) {
     if (!c) return;
     cudaSetDevice(c->device);
-    cudaFree(c->d_static_idx); cudaFree(c->d_mobile_idx); cudaFree(c->d_ideal); cudaFree(c->d_centers);
-    cudaFree(c->d_chunk_atoms); cudaFree(c->d_chunk_bound);
-    cudaFree(c->d_verts_in); cudaFree(c->d_svd); cudaFree(c->d_qorig); cudaFree(c->d_orig_of); cudaFree(c->d_v0); cudaFree(c->d_b0); cudaFree(c->d_va); cudaFree(c->d_ba);
-    cudaFree(c->d_q64); cudaFree(c->d_acoef); cudaFree(c->d_nverts); cudaFree(c->d_cid); cudaFree(c->d_cw); cudaFree(c->d_cid_orig); cudaFree(c->d_cw_orig); cudaFree(c->d_frames_owned); cudaFree(c->d_status);
+    cudaStreamSynchronize(c->stream);
+    pool_free(c->d_static_idx, c->stream); pool_free(c->d_mobile_idx, c->stream); pool_free(c->d_ideal, c->stream); pool_free(c->d_centers, c->stream);
+    pool_free(c->d_chunk_atoms, c->stream); pool_free(c->d_chunk_bound, c->stream);
+    pool_free(c->d_verts_in, c->stream); pool_free(c->d_svd, c->stream); pool_free(c->d_qorig, c->stream); pool_free(c->d_orig_of, c->stream); pool_free(c->d_v0, c->stream); pool_free(c->d_b0, c->stream); pool_free(c->d_va, c->stream); pool_free(c->d_ba, c->stream);
+    pool_free(c->d_q64, c->stream); pool_free(c->d_acoef, c->stream); pool_free(c->d_nverts, c->stream); pool_free(c->d_cid, c->stream); pool_free(c->d_cw, c->stream); pool_free(c->d_cid_orig, c->stream); pool_free(c->d_cw_orig, c->stream); pool_free(c->d_frames_owned, c->stream); pool_free(c->d_status, c->stream);
     delete c;
 }
 
 template <typename T>
-static cudaError_t upload(T** dst, const T* src, size_t n) {
-    cudaError_t e = cudaMalloc((void**)dst, sizeof(T) * (n ? n : 1));
+static cudaError_t upload(T** dst, const T* src, size_t n, cudaStream_t st) {
+    cudaError_t e = pool_alloc((void**)dst, sizeof(T) * n, st);
     if (e != cudaSuccess) return e;
-    if (n) e = cudaMemcpy(*dst, src, sizeof(T) * n, cudaMemcpyHostToDevice);
+    if (n) e = cudaMemcpyAsync(*dst, src, sizeof(T) * n, cudaMemcpyHostToDevice, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);      // src may be a temporary
     return e;
 }
 
@@ -192,18 +194,18 @@ extern "C" int sitb_create(const sitb_network_desc* d, int device, sitb_ctx** ou
             return fail(SITB_E_CUDA, "%s failed: %s", #call, cudaGetErrorString(e2_));     \
         }                                                                                  \
     } while (0)
-    CKC(upload(&c->d_static_idx, d->host_static_idx, (size_t)c->S));
-    CKC(upload(&c->d_mobile_idx, d->host_mobile_idx, (size_t)c->M));
-    CKC(upload(&c->d_ideal, d->host_ideal_static, (size_t)c->S * 3));
-    CKC(upload(&c->d_centers, d->host_centers, (size_t)c->L * 3));
-    CKC(upload(&c->d_verts_in, d->host_verts, LV));
-    CKC(cudaMalloc((void**)&c->d_svd, sizeof(double) * LV));
-    CKC(cudaMalloc((void**)&c->d_qorig, sizeof(double) * LV));
-    CKC(cudaMalloc((void**)&c->d_cid, sizeof(int) * (size_t)c->L));
-    CKC(cudaMalloc((void**)&c->d_cw, sizeof(double) * (size_t)c->L));
+    CKC(upload(&c->d_static_idx, d->host_static_idx, (size_t)c->S, c->stream));
+    CKC(upload(&c->d_mobile_idx, d->host_mobile_idx, (size_t)c->M, c->stream));
+    CKC(upload(&c->d_ideal, d->host_ideal_static, (size_t)c->S * 3, c->stream));
+    CKC(upload(&c->d_centers, d->host_centers, (size_t)c->L * 3, c->stream));
+    CKC(upload(&c->d_verts_in, d->host_verts, LV, c->stream));
+    CKC(pool_alloc((void**)&c->d_svd, sizeof(double) * LV, c->stream));
+    CKC(pool_alloc((void**)&c->d_qorig, sizeof(double) * LV, c->stream));
+    CKC(pool_alloc((void**)&c->d_cid, sizeof(int) * (size_t)c->L, c->stream));
+    CKC(pool_alloc((void**)&c->d_cw, sizeof(double) * (size_t)c->L, c->stream));
     CKC(cudaMemset(c->d_cid, 0xFF, sizeof(int) * (size_t)c->L));
     CKC(cudaMemset(c->d_cw, 0, sizeof(double) * (size_t)c->L));
-    CKC(cudaMalloc((void**)&c->d_status, sizeof(unsigned long long) * (2 + CNT_SLOTS)));
+    CKC(pool_alloc((void**)&c->d_status, sizeof(unsigned long long) * (2 + CNT_SLOTS), c->stream));
     CKC(launch_tables(c->cell, c->d_centers, c->d_ideal, c->d_verts_in, c->L, c->V, c->S, c->cutoff, c->d_svd,
                       c->d_qorig, 0));
     c->h_svd.resize(LV); c->h_qorig.resize(LV);
@@ -213,17 +215,17 @@ extern "C" int sitb_create(const sitb_network_desc* d, int device, sitb_ctx** ou
         HostTables ht;
         build_landmark_tables(c->cell, c->L, c->V, c->Lpad, c->NB, c->S, steep_log2e, d->host_verts,
                               d->host_ideal_static, c->h_svd.data(), c->h_qorig.data(), ht);
-        CKC(upload(&c->d_chunk_atoms, ht.chunk_atoms.data(), ht.chunk_atoms.size()));
-        CKC(upload(&c->d_chunk_bound, ht.chunk_bound.data(), ht.chunk_bound.size()));
+        CKC(upload(&c->d_chunk_atoms, ht.chunk_atoms.data(), ht.chunk_atoms.size(), c->stream));
+        CKC(upload(&c->d_chunk_bound, ht.chunk_bound.data(), ht.chunk_bound.size(), c->stream));
         c->internal_of = ht.internal_of;
-        CKC(upload(&c->d_v0, ht.v0.data(), ht.v0.size()));
-        CKC(upload(&c->d_b0, ht.b0.data(), ht.b0.size()));
-        CKC(upload(&c->d_va, ht.va.data(), ht.va.size()));
-        CKC(upload(&c->d_ba, ht.ba.data(), ht.ba.size()));
-        CKC(upload(&c->d_q64, ht.q64.data(), ht.q64.size()));
-        CKC(upload(&c->d_acoef, ht.acoef.data(), ht.acoef.size()));
-        CKC(upload(&c->d_nverts, ht.nverts.data(), ht.nverts.size()));
-        CKC(upload(&c->d_orig_of, ht.orig_of.data(), ht.orig_of.size()));
+        CKC(upload(&c->d_v0, ht.v0.data(), ht.v0.size(), c->stream));
+        CKC(upload(&c->d_b0, ht.b0.data(), ht.b0.size(), c->stream));
+        CKC(upload(&c->d_va, ht.va.data(), ht.va.size(), c->stream));
+        CKC(upload(&c->d_ba, ht.ba.data(), ht.ba.size(), c->stream));
+        CKC(upload(&c->d_q64, ht.q64.data(), ht.q64.size(), c->stream));
+        CKC(upload(&c->d_acoef, ht.acoef.data(), ht.acoef.size(), c->stream));
+        CKC(upload(&c->d_nverts, ht.nverts.data(), ht.nverts.size(), c->stream));
+        CKC(upload(&c->d_orig_of, ht.orig_of.data(), ht.orig_of.size(), c->stream));
     }
     CKC(cudaDeviceSynchronize());
 #undef CKC
@@ -263,9 +265,9 @@ extern "C" int sitb_upload_frames(sitb_ctx* c, const double* host, int64_t n, in
     CK(cudaSetDevice(c->device));
     const size_t bytes = sizeof(double) * (size_t)n * c->A * 3;
     if (bytes > c->frames_capacity) {
-        cudaFree(c->d_frames_owned);
+        pool_free(c->d_frames_owned, c->stream);
         c->d_frames_owned = nullptr; c->frames_capacity = 0;
-        CK(cudaMalloc((void**)&c->d_frames_owned, bytes));
+        CK(pool_alloc((void**)&c->d_frames_owned, bytes, c->stream));
         c->frames_capacity = bytes;
     }
     // pageable or pinned host memory both work; pinned (cudaHostRegister by the caller) is faster
@@ -388,8 +390,8 @@ extern "C" int sitb_set_centers(sitb_ctx* c, const int32_t* cid, const double* w
     CK(cudaMemcpyAsync(c->d_cid, cid_i.data(), sizeof(int) * (size_t)c->L, cudaMemcpyHostToDevice, c->stream));
     CK(cudaMemcpyAsync(c->d_cw, w_i.data(), sizeof(double) * (size_t)c->L, cudaMemcpyHostToDevice, c->stream));
     if (!c->d_cid_orig) {
-        CK(cudaMalloc((void**)&c->d_cid_orig, sizeof(int) * (size_t)c->L));
-        CK(cudaMalloc((void**)&c->d_cw_orig, sizeof(double) * (size_t)c->L));
+        CK(pool_alloc((void**)&c->d_cid_orig, sizeof(int) * (size_t)c->L, c->stream));
+        CK(pool_alloc((void**)&c->d_cw_orig, sizeof(double) * (size_t)c->L, c->stream));
     }
     CK(cudaMemcpyAsync(c->d_cid_orig, cid, sizeof(int) * (size_t)c->L, cudaMemcpyHostToDevice, c->stream));
     CK(cudaMemcpyAsync(c->d_cw_orig, w, sizeof(double) * (size_t)c->L, cudaMemcpyHostToDevice, c->stream));
@@ -426,9 +428,9 @@ extern "C" int sitb_fill_landmark_vectors_host(sitb_ctx* c, const double* host_f
     if (chunk > n_frames) chunk = n_frames;
     double* d_in = nullptr;
     double* d_out = nullptr;
-    CK(cudaMalloc((void**)&d_in, in_bytes * (size_t)chunk));
-    cudaError_t e = cudaMalloc((void**)&d_out, row_bytes * (size_t)chunk);
-    if (e != cudaSuccess) { cudaFree(d_in); return fail(SITB_E_CUDA, "cudaMalloc: %s", cudaGetErrorString(e)); }
+    CK(pool_alloc((void**)&d_in, in_bytes * (size_t)chunk, c->stream));
+    cudaError_t e = pool_alloc((void**)&d_out, row_bytes * (size_t)chunk, c->stream);
+    if (e != cudaSuccess) { pool_free(d_in, c->stream); return fail(SITB_E_CUDA, "device allocation: %s", cudaGetErrorString(e)); }
     const double* saved_frames = c->d_frames; const long long saved_n = c->n_frames, saved_f0 = c->frame0;
     rc = SITB_OK;
     for (long long f0 = 0; f0 < n_frames && rc == SITB_OK; f0 += chunk) {
@@ -443,7 +445,7 @@ extern "C" int sitb_fill_landmark_vectors_host(sitb_ctx* c, const double* host_f
         if (e != cudaSuccess) { rc = fail(SITB_E_CUDA, "D2H: %s", cudaGetErrorString(e)); break; }
     }
     c->d_frames = saved_frames; c->n_frames = saved_n; c->frame0 = saved_f0;
-    cudaFree(d_in); cudaFree(d_out);
+    pool_free(d_in, c->stream); pool_free(d_out, c->stream);
     if (rc) return rc;
     if (status) return sitb_get_status(c, status);
     return SITB_OK;

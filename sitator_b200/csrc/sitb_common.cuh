@@ -12,6 +12,30 @@
 
 namespace sitb {
 
+// Device scratch and context buffers come from the device's stream-ordered memory pool, kept warm (release
+// threshold = everything): after the first analysis no call goes back to the driver's cudaMalloc/cudaFree,
+// which synchronise the device and take milliseconds for trajectory-sized blocks.
+inline cudaError_t pool_alloc(void** p, size_t bytes, cudaStream_t st) {
+    static bool warmed[64] = {};
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    if (dev >= 0 && dev < 64 && !warmed[dev]) {
+        cudaMemPool_t pool;
+        e = cudaDeviceGetDefaultMemPool(&pool, dev);
+        if (e != cudaSuccess) return e;
+        unsigned long long keep = ~0ull;
+        e = cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+        if (e != cudaSuccess) return e;
+        warmed[dev] = true;
+    }
+    return cudaMallocAsync(p, bytes ? bytes : 1, st);
+}
+inline void pool_free(void* p, cudaStream_t st) {
+    if (p) cudaFreeAsync(p, st);
+}
+
+
 struct Cell {
     double c[9];    // cellmat  = cell^T, row major   (PBCCalculator.pyx:33)
     double ci[9];   // cellmat^-1, row major          (PBCCalculator.pyx:34)

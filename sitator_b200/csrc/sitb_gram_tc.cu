@@ -21,6 +21,7 @@
 // accumulator (double-buffered in TMEM, so the MMAs never wait for the drain) is drained into FP64
 // registers every DRAIN_K rows, which bounds the error independently of the trajectory length.
 #include "../../include/sitator_b200.h"
+#include "sitb_common.cuh"
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -268,8 +269,8 @@ extern "C" int sitb_gram_syrk_tc(int device, const void* dev_stage_hi, const voi
     if (e != cudaSuccess) return set_error(SITB_E_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
     cudaStream_t st = (cudaStream_t)cuda_stream;
     int* abort_flag = nullptr;
-    e = cudaMalloc((void**)&abort_flag, sizeof(int));
-    if (e != cudaSuccess) return set_error(SITB_E_CUDA, "cudaMalloc: %s", cudaGetErrorString(e));
+    e = pool_alloc((void**)&abort_flag, sizeof(int), st);
+    if (e != cudaSuccess) return set_error(SITB_E_CUDA, "device allocation: %s", cudaGetErrorString(e));
     cudaMemsetAsync(abort_flag, 0, sizeof(int), st);
     // K split: fill whole waves of SMs (one CTA per SM), slices a multiple of the drain length and not too short
     int n_sms = 148;
@@ -294,7 +295,7 @@ extern "C" int sitb_gram_syrk_tc(int device, const void* dev_stage_hi, const voi
     int h_abort = 0;
     if (e == cudaSuccess) e = cudaMemcpyAsync(&h_abort, abort_flag, sizeof(int), cudaMemcpyDeviceToHost, st);
     if (e == cudaSuccess) e = cudaStreamSynchronize(st);
-    cudaFree(abort_flag);
+    pool_free(abort_flag, st);
     if (e != cudaSuccess) return set_error(SITB_E_CUDA, "sitb_gram_syrk_tc: %s", cudaGetErrorString(e));
     if (h_abort) return set_error(SITB_E_CUDA, "sitb_gram_syrk_tc: pipeline watchdog fired (an mbarrier never completed)");
     return SITB_OK;

@@ -9,6 +9,7 @@
 // L is ~10^3: the GEMM is 2 L^3 = 7 GFLOP per iteration, a millisecond on the FP64 pipe, so a
 // plain shared-memory tiled DFMA kernel is used (the FP64 tensor path would save microseconds).
 #include "../../include/sitator_b200.h"
+#include "sitb_common.cuh"
 #include <cuda_runtime.h>
 #include <math_constants.h>
 #include <cstdio>
@@ -173,12 +174,12 @@ extern "C" int sitb_markov_clustering(int device, const double* dev_graph, int32
     int it = 0, conv = 0;
     {
         CKM(cudaSetDevice(device));
-        CKM(cudaMalloc((void**)&m1, bytes));
-        CKM(cudaMalloc((void**)&z, bytes));
-        CKM(cudaMalloc((void**)&tmp, bytes));
-        CKM(cudaMalloc((void**)&colsum, sizeof(double) * n));
-        CKM(cudaMalloc((void**)&arg, sizeof(int) * n));
-        CKM(cudaMalloc((void**)&flag, sizeof(int)));
+        CKM(sitb::pool_alloc((void**)&m1, bytes, st));
+        CKM(sitb::pool_alloc((void**)&z, bytes, st));
+        CKM(sitb::pool_alloc((void**)&tmp, bytes, st));
+        CKM(sitb::pool_alloc((void**)&colsum, sizeof(double) * n, st));
+        CKM(sitb::pool_alloc((void**)&arg, sizeof(int) * n, st));
+        CKM(sitb::pool_alloc((void**)&flag, sizeof(int), st));
         m2 = dev_result;
         // m1 = graph / colsum (util/mcl.py:22-25)
         CKM(cudaMemcpyAsync(m1, dev_graph, bytes, cudaMemcpyDeviceToDevice, st));
@@ -202,7 +203,7 @@ extern "C" int sitb_markov_clustering(int device, const double* dev_graph, int32
                 double* res = m2;
                 std::vector<double*> spare;
                 double* res_tmp = nullptr;
-                CKM(cudaMalloc((void**)&res_tmp, bytes));
+                CKM(sitb::pool_alloc((void**)&res_tmp, bytes, st));
                 while (e > 0) {
                     if (!have_z) { CKM(cudaMemcpyAsync(zc, m1, bytes, cudaMemcpyDeviceToDevice, st)); have_z = true; }
                     else { k_dgemm<<<gg, 256, 0, st>>>(zc, zc, zn, n); double* t = zc; zc = zn; zn = t; }
@@ -214,7 +215,7 @@ extern "C" int sitb_markov_clustering(int device, const double* dev_graph, int32
                     }
                 }
                 CKM(cudaStreamSynchronize(st));
-                cudaFree(res_tmp);
+                sitb::pool_free(res_tmp, st);
             }
             k_power<<<eb, 256, 0, st>>>(m2, cnt, inflation);                 // :34
             k_colsum<<<cb, 128, 0, st>>>(m2, n, colsum);                      // :35
@@ -232,7 +233,7 @@ extern "C" int sitb_markov_clustering(int device, const double* dev_graph, int32
         CKM(cudaStreamSynchronize(st));
     }
 done:
-    cudaFree(m1); cudaFree(z); cudaFree(tmp); cudaFree(colsum); cudaFree(arg); cudaFree(flag);
+    sitb::pool_free(m1, st); sitb::pool_free(z, st); sitb::pool_free(tmp, st); sitb::pool_free(colsum, st); sitb::pool_free(arg, st); sitb::pool_free(flag, st);
     if (n_iterations) *n_iterations = it;
     if (converged) *converged = conv;
     return rc;

@@ -395,8 +395,8 @@ extern "C" int sitb_jump_scan(int device, const int64_t* dev_traj, int64_t n_fra
     cudaStream_t st = (cudaStream_t)cuda_stream;
     const long long n_chunks = (n_frames + CHUNK - 1) / CHUNK;
     int *chunk_last = nullptr, *carry = nullptr;
-    CKT(cudaMalloc((void**)&chunk_last, sizeof(int) * n_chunks * n_mobile));
-    CKT(cudaMalloc((void**)&carry, sizeof(int) * n_chunks * n_mobile));
+    CKT(pool_alloc((void**)&chunk_last, sizeof(int) * n_chunks * n_mobile, st));
+    CKT(pool_alloc((void**)&carry, sizeof(int) * n_chunks * n_mobile, st));
     k_chunk_last<<<(unsigned)n_chunks, 128, 0, st>>>((const long long*)dev_traj, n_frames, n_mobile, chunk_last);
     k_chunk_carry<<<(n_mobile + 127) / 128, 128, 0, st>>>(chunk_last, n_chunks, n_mobile, (const long long*)dev_carry_in, carry);
     k_jump_from<<<(unsigned)n_chunks, 128, 0, st>>>((const long long*)dev_traj, n_frames, n_mobile, carry, unknown_as_jump,
@@ -404,7 +404,7 @@ extern "C" int sitb_jump_scan(int device, const int64_t* dev_traj, int64_t n_fra
                                                     (unsigned long long*)dev_total);
     cudaError_t e = cudaGetLastError();
     if (e == cudaSuccess) e = cudaStreamSynchronize(st);
-    cudaFree(chunk_last); cudaFree(carry);
+    pool_free(chunk_last, st); pool_free(carry, st);
     if (e != cudaSuccess) return set_error(SITB_E_CUDA, "sitb_jump_scan: %s", cudaGetErrorString(e));
     return SITB_OK;
 }
@@ -419,15 +419,15 @@ extern "C" int sitb_jump_compact(int device, const int64_t* dev_traj, const int3
     const long long n = n_frames * n_mobile, n_blocks = (n + CBLOCK - 1) / CBLOCK;
     unsigned* bc = nullptr;
     unsigned long long* bo = nullptr;
-    CKT(cudaMalloc((void**)&bc, sizeof(unsigned) * n_blocks));
-    CKT(cudaMalloc((void**)&bo, sizeof(unsigned long long) * n_blocks));
+    CKT(pool_alloc((void**)&bc, sizeof(unsigned) * n_blocks, st));
+    CKT(pool_alloc((void**)&bo, sizeof(unsigned long long) * n_blocks, st));
     k_jump_count<<<(unsigned)n_blocks, CBLOCK, 0, st>>>(dev_from, n, bc);
     k_block_scan<<<1, 1024, 0, st>>>(bc, n_blocks, bo);
     k_jump_write<<<(unsigned)n_blocks, CBLOCK, 0, st>>>((const long long*)dev_traj, dev_from, n, n_mobile, frame0, bo,
                                                        (long long*)dev_out, capacity);
     cudaError_t e = cudaGetLastError();
     if (e == cudaSuccess) e = cudaStreamSynchronize(st);
-    cudaFree(bc); cudaFree(bo);
+    pool_free(bc, st); pool_free(bo, st);
     if (e != cudaSuccess) return set_error(SITB_E_CUDA, "sitb_jump_compact: %s", cudaGetErrorString(e));
     return SITB_OK;
 }
@@ -446,11 +446,11 @@ extern "C" int sitb_jump_analysis(int device, const int64_t* dev_traj, int64_t n
     JaSummary* sum = nullptr;
     int2* carry = nullptr;
     int *la = nullptr, *ca = nullptr, *ta = nullptr;
-    CKT(cudaMalloc((void**)&sum, sizeof(JaSummary) * n_chunks * n_mobile));
-    CKT(cudaMalloc((void**)&carry, sizeof(int2) * n_chunks * n_mobile));
-    CKT(cudaMalloc((void**)&la, sizeof(int) * n));
-    CKT(cudaMalloc((void**)&ca, sizeof(int) * n));
-    CKT(cudaMalloc((void**)&ta, sizeof(int) * n));
+    CKT(pool_alloc((void**)&sum, sizeof(JaSummary) * n_chunks * n_mobile, st));
+    CKT(pool_alloc((void**)&carry, sizeof(int2) * n_chunks * n_mobile, st));
+    CKT(pool_alloc((void**)&la, sizeof(int) * n, st));
+    CKT(pool_alloc((void**)&ca, sizeof(int) * n, st));
+    CKT(pool_alloc((void**)&ta, sizeof(int) * n, st));
     k_ja_summary<<<(unsigned)n_chunks, 128, 0, st>>>((const long long*)dev_traj, n_frames, n_mobile, sum);
     k_ja_carry<<<(n_mobile + 127) / 128, 128, 0, st>>>(sum, n_chunks, n_mobile, (const long long*)dev_carry_label,
                                                       (const long long*)dev_carry_jump, carry);
@@ -462,7 +462,7 @@ extern "C" int sitb_jump_analysis(int device, const int64_t* dev_traj, int64_t n
         (unsigned long long*)dev_lag_n, (unsigned long long*)dev_n_problems);
     cudaError_t e = cudaGetLastError();
     if (e == cudaSuccess) e = cudaStreamSynchronize(st);
-    cudaFree(sum); cudaFree(carry); cudaFree(la); cudaFree(ca); cudaFree(ta);
+    pool_free(sum, st); pool_free(carry, st); pool_free(la, st); pool_free(ca, st); pool_free(ta, st);
     if (e != cudaSuccess) return set_error(SITB_E_CUDA, "sitb_jump_analysis: %s", cudaGetErrorString(e));
     return SITB_OK;
 }
