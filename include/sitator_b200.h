@@ -94,6 +94,10 @@ int sitb_get_tables(sitb_ctx* ctx, double* host_site_vert_dists, double* host_q_
  * frame0 = global index of the first frame (frame-sharded runs). */
 int sitb_upload_frames(sitb_ctx* ctx, const double* host_frames, int64_t n_frames, int64_t frame0);
 int sitb_borrow_frames(sitb_ctx* ctx, const double* dev_frames, int64_t n_frames, int64_t frame0);
+/* sitb_upload_frames copies in chunks on its own stream and returns at once when host_frames is page-locked (the
+ * caller keeps it alive and unchanged until the passes reading it have run); a pass waits only for the chunks
+ * it reads, so passes launched chunk by chunk overlap the copy.  *frames_per_chunk = 0 for borrowed frames. */
+int sitb_upload_chunk_frames(sitb_ctx* ctx, int64_t* frames_per_chunk);
 
 int sitb_reset_status(sitb_ctx* ctx);
 int sitb_get_status(sitb_ctx* ctx, sitb_status* out);

@@ -28,7 +28,7 @@ class SiteTrajectory(object):
 
     SITE_UNKNOWN = -1
 
-    def __init__(self, site_network, particle_assignments, confidences=None):
+    def __init__(self, site_network, particle_assignments, confidences=None, _copy=True):
         """
         :param SiteNetwork site_network:
         :param ndarray (n_frames, n_mobile) particle_assignments:
@@ -39,7 +39,7 @@ class SiteTrajectory(object):
         if particle_assignments.shape[1] != site_network.n_mobile:
             raise ValueError("particle_assignments has wrong shape %s" % (particle_assignments.shape,))
         self._sn = site_network
-        self._traj = particle_assignments.copy()
+        self._traj = particle_assignments.copy() if _copy else particle_assignments
         if confidences is not None:
             if confidences.shape != particle_assignments.shape:
                 raise ValueError("confidences has wrong shape %s; should be %s" %

@@ -85,6 +85,13 @@ struct sitb_ctx {
     double* d_frames_owned = nullptr;
     size_t frames_capacity = 0;      // bytes
     long long n_frames = 0, frame0 = 0;
+    // the upload runs chunk by chunk on its own stream; a pass waits only for the chunks it reads, so the
+    // first pass over a fresh trajectory overlaps the host -> device copy
+    cudaStream_t copy_stream = nullptr;
+    cudaEvent_t order_event = nullptr;
+    std::vector<cudaEvent_t> up_events;   // one per chunk of up_chunk frames
+    long long up_chunk = 0;
+    size_t up_waited = 0;                 // chunks the compute stream already waits for
     // status
     unsigned long long* d_status = nullptr;   // [2] error keys + [CNT_SLOTS] counters
 };
@@ -93,6 +100,9 @@ static void free_ctx(sitb_ctx* c) {
     if (!c) return;
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
+    if (c->copy_stream) { cudaStreamSynchronize(c->copy_stream); cudaStreamDestroy(c->copy_stream); }
+    if (c->order_event) cudaEventDestroy(c->order_event);
+    for (cudaEvent_t ev : c->up_events) cudaEventDestroy(ev);
     pool_free(c->d_static_idx, c->stream); pool_free(c->d_mobile_idx, c->stream); pool_free(c->d_ideal, c->stream); pool_free(c->d_centers, c->stream);
     pool_free(c->d_chunk_atoms, c->stream); pool_free(c->d_chunk_bound, c->stream);
     pool_free(c->d_verts_in, c->stream); pool_free(c->d_svd, c->stream); pool_free(c->d_qorig, c->stream); pool_free(c->d_orig_of, c->stream); pool_free(c->d_v0, c->stream); pool_free(c->d_b0, c->stream); pool_free(c->d_va, c->stream); pool_free(c->d_ba, c->stream);
@@ -146,10 +156,12 @@ extern "C" int sitb_create(const sitb_network_desc* d, int device, sitb_ctx** ou
     sitb_ctx* c = new (std::nothrow) sitb_ctx();
     if (!c) return fail(SITB_E_INVALID, "out of host memory");
     c->device = device;
-    cudaDeviceProp prop;
-    e = cudaGetDeviceProperties(&prop, device);
-    if (e != cudaSuccess) { free_ctx(c); return fail(SITB_E_CUDA, "cudaGetDeviceProperties: %s", cudaGetErrorString(e)); }
-    c->n_sms = prop.multiProcessorCount; c->cc_major = prop.major; c->cc_minor = prop.minor;
+    // three attribute reads, not cudaGetDeviceProperties (which also queries clocks and PCI state and can take
+    // tens of milliseconds on a virtualised GPU)
+    e = cudaDeviceGetAttribute(&c->n_sms, cudaDevAttrMultiProcessorCount, device);
+    if (e == cudaSuccess) e = cudaDeviceGetAttribute(&c->cc_major, cudaDevAttrComputeCapabilityMajor, device);
+    if (e == cudaSuccess) e = cudaDeviceGetAttribute(&c->cc_minor, cudaDevAttrComputeCapabilityMinor, device);
+    if (e != cudaSuccess) { free_ctx(c); return fail(SITB_E_CUDA, "cudaDeviceGetAttribute: %s", cudaGetErrorString(e)); }
     c->A = d->n_atoms; c->S = d->n_static; c->M = d->n_mobile; c->L = d->n_landmarks; c->V = d->max_verts;
     c->Lpad = (c->L + 255) & ~255;   // K1 screens landmarks in unrolled groups of 8 x 32
     c->NB = (c->V + 3) / 4;
@@ -227,7 +239,7 @@ extern "C" int sitb_create(const sitb_network_desc* d, int device, sitb_ctx** ou
         CKC(upload(&c->d_nverts, ht.nverts.data(), ht.nverts.size(), c->stream));
         CKC(upload(&c->d_orig_of, ht.orig_of.data(), ht.orig_of.size(), c->stream));
     }
-    CKC(cudaDeviceSynchronize());
+    CKC(cudaStreamSynchronize(c->stream));
 #undef CKC
     *out = c;
     int rc = sitb_reset_status(c);
@@ -240,6 +252,7 @@ extern "C" void sitb_destroy(sitb_ctx* ctx) { free_ctx(ctx); }
 extern "C" int sitb_set_stream(sitb_ctx* c, void* s) {
     if (!c) return fail(SITB_E_INVALID, "null context");
     c->stream = (cudaStream_t)s;
+    c->up_waited = 0;                 // a new compute stream has to wait for the upload again
     return SITB_OK;
 }
 
@@ -263,16 +276,59 @@ extern "C" int sitb_get_tables(sitb_ctx* c, double* svd, double* q) {
 extern "C" int sitb_upload_frames(sitb_ctx* c, const double* host, int64_t n, int64_t frame0) {
     if (!c || !host || n <= 0) return fail(SITB_E_INVALID, "sitb_upload_frames: bad argument");
     CK(cudaSetDevice(c->device));
-    const size_t bytes = sizeof(double) * (size_t)n * c->A * 3;
+    const size_t frame_bytes = sizeof(double) * (size_t)c->A * 3;
+    const size_t bytes = frame_bytes * (size_t)n;
     if (bytes > c->frames_capacity) {
         pool_free(c->d_frames_owned, c->stream);
         c->d_frames_owned = nullptr; c->frames_capacity = 0;
         CK(pool_alloc((void**)&c->d_frames_owned, bytes, c->stream));
         c->frames_capacity = bytes;
     }
-    // pageable or pinned host memory both work; pinned (cudaHostRegister by the caller) is faster
-    CK(cudaMemcpyAsync(c->d_frames_owned, host, bytes, cudaMemcpyHostToDevice, c->stream));
+    if (!c->copy_stream) {
+        CK(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+        CK(cudaEventCreateWithFlags(&c->order_event, cudaEventDisableTiming));
+    }
+    // the copy may start once everything queued on the compute stream (allocation, older passes) is done
+    CK(cudaEventRecord(c->order_event, c->stream));
+    CK(cudaStreamWaitEvent(c->copy_stream, c->order_event, 0));
+    // host memory should be page-locked (then the copies are asynchronous; the caller keeps it alive and
+    // unchanged until the passes that read it have run); pageable memory works but copies synchronously
+    c->up_chunk = (long long)((32ull << 20) / frame_bytes);
+    if (c->up_chunk < 1) c->up_chunk = 1;
+    const size_t n_chunks = (size_t)((n + c->up_chunk - 1) / c->up_chunk);
+    while (c->up_events.size() < n_chunks) {
+        cudaEvent_t ev;
+        CK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+        c->up_events.push_back(ev);
+    }
+    for (size_t k = 0; k < n_chunks; ++k) {
+        const long long f0 = (long long)k * c->up_chunk;
+        const long long nf = (n - f0 < c->up_chunk) ? (n - f0) : c->up_chunk;
+        CK(cudaMemcpyAsync(c->d_frames_owned + (size_t)f0 * c->A * 3, host + (size_t)f0 * c->A * 3, frame_bytes * (size_t)nf,
+                           cudaMemcpyHostToDevice, c->copy_stream));
+        CK(cudaEventRecord(c->up_events[k], c->copy_stream));
+    }
+    c->up_waited = 0;
     c->d_frames = c->d_frames_owned; c->n_frames = n; c->frame0 = frame0;
+    return SITB_OK;
+}
+
+// Make the compute stream wait for the uploaded chunks that cover frames [0, end).
+static int wait_for_frames(sitb_ctx* c, long long end) {
+    if (c->d_frames != c->d_frames_owned || c->up_chunk <= 0) return SITB_OK;
+    const size_t n_chunks = (size_t)((c->n_frames + c->up_chunk - 1) / c->up_chunk);
+    size_t need = (size_t)((end + c->up_chunk - 1) / c->up_chunk);
+    if (need > n_chunks) need = n_chunks;
+    if (need > c->up_waited) {
+        CK(cudaStreamWaitEvent(c->stream, c->up_events[need - 1], 0));   // copies complete in order
+        c->up_waited = need;
+    }
+    return SITB_OK;
+}
+
+extern "C" int sitb_upload_chunk_frames(sitb_ctx* c, int64_t* frames_per_chunk) {
+    if (!c || !frames_per_chunk) return fail(SITB_E_INVALID, "sitb_upload_chunk_frames: null argument");
+    *frames_per_chunk = (c->d_frames && c->d_frames == c->d_frames_owned) ? c->up_chunk : 0;
     return SITB_OK;
 }
 
@@ -326,6 +382,10 @@ static int base_params(sitb_ctx* c, int64_t begin, int64_t n, FillParams& p, con
                     (long long)(begin + n), (long long)c->n_frames);
     if ((unsigned long long)(c->frame0 + c->n_frames) * (unsigned long long)c->M >= 0xFFFFFFFFull)
         return fail(SITB_E_LIMIT, "%s: more than 2^32 landmark vectors", who);
+    {
+        const int wrc = wait_for_frames(c, n > 0 ? begin + n : c->n_frames);   // n == 0: a frame-list pass
+        if (wrc) return wrc;
+    }
     memset(&p, 0, sizeof(p));
     p.cell = c->cell;
     p.frames = c->d_frames + (size_t)begin * c->A * 3;
@@ -523,6 +583,7 @@ cudaError_t launch_first_row(const long long* labels, long long n, long long row
 extern "C" int sitb_wrapped_mobile_rows(sitb_ctx* c, const int64_t* dev_rows, int32_t n, double* dev_out) {
     if (!c || !dev_rows || !dev_out || n < 0) return fail(SITB_E_INVALID, "sitb_wrapped_mobile_rows: bad argument");
     if (!c->d_frames) return fail(SITB_E_STATE, "sitb_wrapped_mobile_rows: no frames resident");
+    { const int wrc = wait_for_frames(c, c->n_frames); if (wrc) return wrc; }
     CK(cudaSetDevice(c->device));
     CK(launch_wrapped_rows(c->cell, c->d_frames, c->A, c->M, c->d_mobile_idx, c->frame0, c->n_frames,
                            (const long long*)dev_rows, n, dev_out, c->stream));
@@ -542,6 +603,7 @@ extern "C" int sitb_site_accumulate(sitb_ctx* c, const int64_t* dev_labels, cons
     if (!c || !dev_labels || !dev_offsets || !dev_sums || n_sites <= 0 || (weighted && !dev_confs))
         return fail(SITB_E_INVALID, "sitb_site_accumulate: bad argument");
     if (!c->d_frames) return fail(SITB_E_STATE, "sitb_site_accumulate: no frames resident");
+    { const int wrc = wait_for_frames(c, c->n_frames); if (wrc) return wrc; }
     CK(cudaSetDevice(c->device));
     CK(launch_site_accumulate(c->cell, c->d_frames, c->A, c->M, c->d_mobile_idx, c->n_frames,
                               (const long long*)dev_labels, dev_confs, dev_offsets, n_sites, weighted, dev_sums,

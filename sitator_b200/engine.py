@@ -102,6 +102,7 @@ class LandmarkEngine(object):
         self._ctx = C.c_void_p()
         _native.check(self._lib.sitb_create(C.byref(d), self.device.index, C.byref(self._ctx)))
         self._frames_keepalive = None
+        self.frames_bytes = 0          # device bytes the native context holds for uploaded frames
         self.n_frames = 0
         self.frame0 = 0
         self.n_clusters = 0
@@ -120,8 +121,9 @@ class LandmarkEngine(object):
 
     def close(self):
         if getattr(self, "_ctx", None) is not None and self._ctx.value:
-            self._lib.sitb_destroy(self._ctx)
+            self._lib.sitb_destroy(self._ctx)      # synchronises the compute and copy streams first
             self._ctx = C.c_void_p()
+            self._frames_keepalive = None
 
     def __del__(self):
         try:
@@ -162,6 +164,7 @@ class LandmarkEngine(object):
                 raise ValueError("Wrong shape %s for frames." % (tuple(frames.shape),))
             _native.check(self._lib.sitb_borrow_frames(self._ctx, self._ptr(frames), frames.shape[0], frame0))
             self._frames_keepalive = frames
+            self.frames_bytes = 0
         else:
             frames = np.asarray(frames)
             if frames.dtype != np.float64:
@@ -169,11 +172,19 @@ class LandmarkEngine(object):
             if frames.shape[1:] != (self.n_atoms, 3):
                 raise ValueError("Wrong shape %s for frames." % (frames.shape,))
             frames = np.ascontiguousarray(frames)
+            # asynchronous when the host array is page-locked: the passes wait for the chunks they read, and the
+            # array is kept alive here until the next set_frames()/close()
             _native.check(self._lib.sitb_upload_frames(self._ctx, frames.ctypes.data, frames.shape[0], frame0))
-            torch.cuda.current_stream(self.device).synchronize()
-            self._frames_keepalive = None
+            self._frames_keepalive = frames
+            self.frames_bytes = max(self.frames_bytes, int(frames.nbytes))
         self.n_frames = int(frames.shape[0])
         self.frame0 = int(frame0)
+
+    def upload_chunk_frames(self):
+        """Frames per chunk of the last set_frames() upload (0: frames borrowed from a device tensor)."""
+        n = C.c_int64()
+        _native.check(self._lib.sitb_upload_chunk_frames(self._ctx, C.byref(n)))
+        return int(n.value)
 
     def reset_status(self):
         _native.check(self._lib.sitb_reset_status(self._ctx))
@@ -253,9 +264,14 @@ class LandmarkEngine(object):
                               self._empty((cap,), torch.float64), self._zeros((1,), torch.int64), cap, n_rows,
                               self.frame0 * self.M)
             seen_try, gram_try = seen.clone(), gram.clone()
-            _native.check(self._lib.sitb_pass_stats_cached(
-                self._ctx, 0, self.n_frames, self._ptr(seen_try), self._ptr(gram_try), self._ptr(rows.ptr),
-                self._ptr(rows.k), self._ptr(rows.v), self._ptr(rows.cursor), cap))
+            # launched per upload chunk: each launch waits only for its own chunk of the host -> device copy
+            step = self.upload_chunk_frames() or self.n_frames
+            for b in range(0, self.n_frames, step):
+                nb = min(step, self.n_frames - b)
+                _native.check(self._lib.sitb_pass_stats_cached(
+                    self._ctx, b, nb, self._ptr(seen_try), self._ptr(gram_try),
+                    C.c_void_p(rows.ptr.data_ptr() + 8 * b * self.M), self._ptr(rows.k), self._ptr(rows.v),
+                    self._ptr(rows.cursor), cap))
             used = int(rows.cursor.item())
             if used <= cap:
                 seen.copy_(seen_try); gram.copy_(gram_try)

@@ -238,7 +238,10 @@ class LandmarkAnalysis(object):
             rep_lvecs = np.asarray(rep_lvecs)
             assert rep_lvecs.shape == (len(cluster_counts), engine.L)
 
-        n_unassigned = int(np.sum(lmk_lbls < 0))
+        if clustering.get('_dev_labels') is not None:
+            n_unassigned = int((clustering['_dev_labels'] < 0).sum().item())      # counted where the labels already are
+        else:
+            n_unassigned = int(np.sum(lmk_lbls < 0))
         n_rows = len(lmk_lbls)
         if comm is not None:
             n_unassigned = comm.allreduce_sum_scalar(n_unassigned)
@@ -272,7 +275,7 @@ class LandmarkAnalysis(object):
         if landmark_clusters is not None:
             out_sn.vertices = [set.union(*[set(sn.vertices[l]) for l in lclust]) for lclust in landmark_clusters]
 
-        out_st = SiteTrajectory(out_sn, lmk_lbls, lmk_confs)
+        out_st = SiteTrajectory(out_sn, lmk_lbls, lmk_confs, _copy=False)     # the arrays are this run's own
         out_st.frame0 = frame0
         out_st._comm = comm
 

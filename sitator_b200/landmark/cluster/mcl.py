@@ -67,7 +67,9 @@ def landmark_graph(source, gram_method='sparse'):
         raise ValueError("gram_method must be 'sparse' or 'tcgen05', not %r" % (gram_method,))
     if source.gram_upper is None:
         # keep the rows compressed for the later passes when they fit comfortably (~400 B per row)
-        free_bytes, _ = torch.cuda.mem_get_info(eng.device)
+        # (torch's cached totals, not cudaMemGetInfo: that driver query can take tens of milliseconds)
+        free_bytes = (torch.cuda.get_device_properties(eng.device).total_memory
+                      - torch.cuda.memory_reserved(eng.device) - eng.frames_bytes)
         if gram_method == 'tcgen05':
             seen, gram = eng.pass_stats_tc()
         elif source.cache_rows and source.n_local * 420 < 0.5 * free_bytes:
