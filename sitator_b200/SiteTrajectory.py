@@ -184,6 +184,10 @@ class SiteTrajectory(object):
             frame, site = key >> 32, key & 0xFFFFFFFF
             local = frame - self.frame0
             mobile = np.where(self._traj[local] == site)[0] if 0 <= local < self.n_frames else np.array([], dtype=int)
+            if self._comm is not None:      # only the shard that owns the frame knows the atoms: one-hot sum over ranks
+                mask = np.zeros(self._sn.n_mobile, dtype=np.int64)
+                mask[mobile] = 1
+                mobile = np.where(self._comm.allreduce_sum_numpy(mask) > 0)[0]
             raise MultipleOccupancyError(mobile=mobile, site=site, frame=frame)
         n_more, n_assigned, n_distinct = (int(x) for x in out.cpu().numpy())
         return n_more, n_assigned / n_distinct
