@@ -20,14 +20,33 @@ namespace sitb {
 // ---- C = A * B, n x n row-major doubles -------------------------------------------------------
 constexpr int GB = 64, GK = 16;
 
+// 1 where a (th x tw) tile of the n x n matrix holds a non-zero (or non-finite) entry.  MCL iterates are sparse
+// (a landmark correlates with few others, and pruning re-sparsifies every iteration), and a product
+// tile with an all-zero operand tile adds exact zeros: skipping it changes no bit of the result.
+__global__ void __launch_bounds__(256) k_tilemap(const double* __restrict__ m, int n, int th, int tw,
+                                                 unsigned char* __restrict__ map) {
+    const int r0 = blockIdx.y * th, c0 = blockIdx.x * tw;
+    int any = 0;
+    for (int i = threadIdx.x; i < th * tw; i += 256) {
+        const int r = r0 + i / tw, c = c0 + i % tw;
+        if (r < n && c < n && m[(size_t)r * n + c] != 0.0) any = 1;
+    }
+    any = __syncthreads_or(any);
+    if (threadIdx.x == 0) map[blockIdx.y * gridDim.x + blockIdx.x] = (unsigned char)any;
+}
+
 __global__ void __launch_bounds__(256) k_dgemm(const double* __restrict__ A, const double* __restrict__ B,
-                                               double* __restrict__ C, int n) {
+                                               double* __restrict__ C, int n, const unsigned char* __restrict__ amap,
+                                               const unsigned char* __restrict__ bmap) {
     __shared__ double As[GK][GB + 1];
     __shared__ double Bs[GK][GB];
     const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
     const int row0 = blockIdx.y * GB, col0 = blockIdx.x * GB;
+    const int kt = (n + GK - 1) / GK;
     double acc[4][4] = {};
     for (int k0 = 0; k0 < n; k0 += GK) {
+        // amap: [n/64][n/16] tiles of A, bmap: [n/16][n/64] tiles of B (block-uniform test)
+        if (!amap[blockIdx.y * kt + k0 / GK] || !bmap[(k0 / GK) * gridDim.x + blockIdx.x]) continue;
         for (int i = threadIdx.x; i < GB * GK; i += 256) {
             const int r = i / GK, c = i % GK;                    // A tile: 64 rows x 16 k
             const int gr = row0 + r, gc = k0 + c;
@@ -65,7 +84,7 @@ __global__ void k_colsum(const double* __restrict__ m, int n, double* __restrict
     const int j = blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= n) return;
     double s = 0.0;
-#pragma unroll 16
+#pragma unroll 32
     for (int i = 0; i < n; ++i) s = __dadd_rn(s, m[(size_t)i * n + j]);     // loads pipeline, adds stay in order
     out[j] = s;
 }
@@ -82,18 +101,31 @@ __global__ void k_power(double* __restrict__ m, size_t count, double r) {
     m[idx] = pow(m[idx], r);
 }
 
-// first row index of the column maximum (np.argmax(m, axis=0))
-__global__ void k_colargmax(const double* __restrict__ m, int n, int* __restrict__ arg) {
-    const int j = blockIdx.x * blockDim.x + threadIdx.x;
-    if (j >= n) return;
-    double best = m[j];
-    int bi = 0;
-#pragma unroll 16
-    for (int i = 1; i < n; ++i) {
-        const double v = m[(size_t)i * n + j];
-        if (v > best) { best = v; bi = i; }
+// first row index of the column maximum (np.argmax(m, axis=0)); block = 32 columns x 8 interleaved row groups
+__global__ void __launch_bounds__(256) k_colargmax(const double* __restrict__ m, int n, int* __restrict__ arg) {
+    __shared__ double sv[8][32];
+    __shared__ int si[8][32];
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const int j = blockIdx.x * 32 + tx;
+    double best = -CUDART_INF;
+    int bi = 0x7FFFFFFF;
+    if (j < n) {
+#pragma unroll 8
+        for (int i = ty; i < n; i += 8) {
+            const double v = m[(size_t)i * n + j];
+            if (v > best || bi == 0x7FFFFFFF) { best = v; bi = i; }     // NaN-free input; first maximum of this group
+        }
     }
-    arg[j] = bi;
+    sv[ty][tx] = best; si[ty][tx] = bi;
+    __syncthreads();
+    if (ty == 0 && j < n) {
+        for (int g = 1; g < 8; ++g) {
+            const double v = sv[g][tx];
+            const int i = si[g][tx];
+            if (i != 0x7FFFFFFF && (v > best || (v == best && i < bi))) { best = v; bi = i; }
+        }
+        arg[j] = bi;
+    }
 }
 
 // prune (util/mcl.py:37-40) and compare with the previous iterate (np.allclose, :42) in one pass
@@ -169,7 +201,8 @@ extern "C" int sitb_markov_clustering(int device, const double* dev_graph, int32
     const size_t cnt = (size_t)n * n, bytes = cnt * sizeof(double);
     double *m1 = nullptr, *m2 = nullptr, *z = nullptr, *tmp = nullptr, *colsum = nullptr;
     int *arg = nullptr, *flag = nullptr;
-    const unsigned eb = (unsigned)((cnt + 255) / 256), cb = (unsigned)((n + 127) / 128);
+    unsigned char *amap = nullptr, *bmap = nullptr;
+    const unsigned eb = (unsigned)((cnt + 255) / 256), cb = (unsigned)((n + 31) / 32);
     const dim3 gg((n + GB - 1) / GB, (n + GB - 1) / GB);
     int it = 0, conv = 0;
     {
@@ -180,20 +213,28 @@ extern "C" int sitb_markov_clustering(int device, const double* dev_graph, int32
         CKM(sitb::pool_alloc((void**)&colsum, sizeof(double) * n, st));
         CKM(sitb::pool_alloc((void**)&arg, sizeof(int) * n, st));
         CKM(sitb::pool_alloc((void**)&flag, sizeof(int), st));
+        const int kt = (n + GK - 1) / GK;
+        CKM(sitb::pool_alloc((void**)&amap, (size_t)gg.y * kt, st));
+        CKM(sitb::pool_alloc((void**)&bmap, (size_t)kt * gg.x, st));
+        auto gemm = [&](const double* X, const double* Y, double* Z) {
+            k_tilemap<<<dim3(kt, gg.y), 256, 0, st>>>(X, n, GB, GK, amap);
+            k_tilemap<<<dim3(gg.x, kt), 256, 0, st>>>(Y, n, GK, GB, bmap);
+            k_dgemm<<<gg, 256, 0, st>>>(X, Y, Z, n, amap, bmap);
+        };
         m2 = dev_result;
         // m1 = graph / colsum (util/mcl.py:22-25)
         CKM(cudaMemcpyAsync(m1, dev_graph, bytes, cudaMemcpyDeviceToDevice, st));
-        k_colsum<<<cb, 128, 0, st>>>(m1, n, colsum);
+        k_colsum<<<cb, 32, 0, st>>>(m1, n, colsum);
         k_coldiv<<<eb, 256, 0, st>>>(m1, n, colsum);
         for (it = 0; it < iterlimit; ++it) {
             // expansion: np.linalg.matrix_power(m1, expansion) with NumPy's multiplication order
             if (expansion == 1) {
                 CKM(cudaMemcpyAsync(m2, m1, bytes, cudaMemcpyDeviceToDevice, st));
             } else if (expansion == 2) {
-                k_dgemm<<<gg, 256, 0, st>>>(m1, m1, m2, n);
+                gemm(m1, m1, m2);
             } else if (expansion == 3) {
-                k_dgemm<<<gg, 256, 0, st>>>(m1, m1, tmp, n);
-                k_dgemm<<<gg, 256, 0, st>>>(tmp, m1, m2, n);
+                gemm(m1, m1, tmp);
+                gemm(tmp, m1, m2);
             } else {
                 // binary decomposition: z = a, a^2, a^4, ...; result *= z for set bits
                 int e = expansion;
@@ -206,21 +247,21 @@ extern "C" int sitb_markov_clustering(int device, const double* dev_graph, int32
                 CKM(sitb::pool_alloc((void**)&res_tmp, bytes, st));
                 while (e > 0) {
                     if (!have_z) { CKM(cudaMemcpyAsync(zc, m1, bytes, cudaMemcpyDeviceToDevice, st)); have_z = true; }
-                    else { k_dgemm<<<gg, 256, 0, st>>>(zc, zc, zn, n); double* t = zc; zc = zn; zn = t; }
+                    else { gemm(zc, zc, zn); double* t = zc; zc = zn; zn = t; }
                     const int bit = e & 1;
                     e >>= 1;
                     if (bit) {
                         if (!have_r) { CKM(cudaMemcpyAsync(res, zc, bytes, cudaMemcpyDeviceToDevice, st)); have_r = true; }
-                        else { k_dgemm<<<gg, 256, 0, st>>>(res, zc, res_tmp, n); CKM(cudaMemcpyAsync(res, res_tmp, bytes, cudaMemcpyDeviceToDevice, st)); }
+                        else { gemm(res, zc, res_tmp); CKM(cudaMemcpyAsync(res, res_tmp, bytes, cudaMemcpyDeviceToDevice, st)); }
                     }
                 }
                 CKM(cudaStreamSynchronize(st));
                 sitb::pool_free(res_tmp, st);
             }
             k_power<<<eb, 256, 0, st>>>(m2, cnt, inflation);                 // :34
-            k_colsum<<<cb, 128, 0, st>>>(m2, n, colsum);                      // :35
+            k_colsum<<<cb, 32, 0, st>>>(m2, n, colsum);                      // :35
             k_coldiv<<<eb, 256, 0, st>>>(m2, n, colsum);
-            k_colargmax<<<cb, 128, 0, st>>>(m2, n, arg);                      // :39
+            k_colargmax<<<cb, 256, 0, st>>>(m2, n, arg);                      // :39
             CKM(cudaMemsetAsync(flag, 0, sizeof(int), st));
             k_prune_compare<<<eb, 256, 0, st>>>(m2, m1, n, arg, pruning_threshold, flag);   // :37-42
             int h_flag = 1;
@@ -234,6 +275,7 @@ extern "C" int sitb_markov_clustering(int device, const double* dev_graph, int32
     }
 done:
     sitb::pool_free(m1, st); sitb::pool_free(z, st); sitb::pool_free(tmp, st); sitb::pool_free(colsum, st); sitb::pool_free(arg, st); sitb::pool_free(flag, st);
+    sitb::pool_free(amap, st); sitb::pool_free(bmap, st);
     if (n_iterations) *n_iterations = it;
     if (converged) *converged = conv;
     return rc;

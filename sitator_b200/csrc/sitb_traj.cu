@@ -317,26 +317,47 @@ __global__ void k_wrapped_rows(Cell cell, const double* __restrict__ frames, int
 }
 
 // sums[s][0..2] += w * wrap(p + offset[s]),  sums[s][3] += w   (PBCCalculator.pyx:124-132)
+// A thread follows one mobile atom through SITE_CHUNK consecutive frames and keeps the running sums of the
+// site it currently sits at in registers: an atom stays at a site for many frames, so the global atomics drop
+// from four per row to four per residence (a warp = 32 neighbouring atoms of one frame: coalesced loads).
+constexpr int SITE_CHUNK = 64;
 __global__ void k_site_accumulate(Cell cell, const double* __restrict__ frames, int A, int M,
                                   const int* __restrict__ mobile_idx, long long n_frames,
                                   const long long* __restrict__ labels, const double* __restrict__ confs,
                                   const double* __restrict__ offset, int C, int weighted, double* __restrict__ sums) {
-    const long long n = n_frames * M;
-    for (long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x; r < n; r += (long long)gridDim.x * blockDim.x) {
-        const long long s = labels[r];
-        if (s < 0 || s >= C) continue;
-        const long long f = r / M;
-        const int j = (int)(r % M);
-        const double* p = frames + ((size_t)f * A + mobile_idx[j]) * 3;
-        double x = p[0], y = p[1], z = p[2];
-        if (cell.diag) wrap_point<true, false>(cell, x, y, z); else wrap_point<false, false>(cell, x, y, z);
-        x = __dadd_rn(x, offset[3 * s]); y = __dadd_rn(y, offset[3 * s + 1]); z = __dadd_rn(z, offset[3 * s + 2]);
-        if (cell.diag) wrap_point<true, false>(cell, x, y, z); else wrap_point<false, false>(cell, x, y, z);
-        const double w = weighted ? confs[r] : 1.0;
-        atomicAdd(&sums[4 * s + 0], w * x);
-        atomicAdd(&sums[4 * s + 1], w * y);
-        atomicAdd(&sums[4 * s + 2], w * z);
-        atomicAdd(&sums[4 * s + 3], w);
+    const long long n_chunks = (n_frames + SITE_CHUNK - 1) / SITE_CHUNK;
+    const long long total = n_chunks * M;
+    for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+        const int j = (int)(t % M);
+        const long long f0 = (t / M) * SITE_CHUNK;
+        const long long f1 = f0 + SITE_CHUNK < n_frames ? f0 + SITE_CHUNK : n_frames;
+        const int atom = mobile_idx[j];
+        long long cur = -1;
+        double sx = 0.0, sy = 0.0, sz = 0.0, sw = 0.0, ox = 0.0, oy = 0.0, oz = 0.0;
+        for (long long f = f0; f < f1; ++f) {
+            const long long r = f * M + j;
+            const long long s = labels[r];
+            if (s < 0 || s >= C) continue;
+            if (s != cur) {
+                if (cur >= 0) {
+                    atomicAdd(&sums[4 * cur + 0], sx); atomicAdd(&sums[4 * cur + 1], sy);
+                    atomicAdd(&sums[4 * cur + 2], sz); atomicAdd(&sums[4 * cur + 3], sw);
+                }
+                cur = s; sx = sy = sz = sw = 0.0;
+                ox = offset[3 * s]; oy = offset[3 * s + 1]; oz = offset[3 * s + 2];
+            }
+            const double* p = frames + ((size_t)f * A + atom) * 3;
+            double x = p[0], y = p[1], z = p[2];
+            if (cell.diag) wrap_point<true, false>(cell, x, y, z); else wrap_point<false, false>(cell, x, y, z);
+            x = __dadd_rn(x, ox); y = __dadd_rn(y, oy); z = __dadd_rn(z, oz);
+            if (cell.diag) wrap_point<true, false>(cell, x, y, z); else wrap_point<false, false>(cell, x, y, z);
+            const double w = weighted ? confs[r] : 1.0;
+            sx += w * x; sy += w * y; sz += w * z; sw += w;
+        }
+        if (cur >= 0) {
+            atomicAdd(&sums[4 * cur + 0], sx); atomicAdd(&sums[4 * cur + 1], sy);
+            atomicAdd(&sums[4 * cur + 2], sz); atomicAdd(&sums[4 * cur + 3], sw);
+        }
     }
 }
 

@@ -19,6 +19,7 @@ landmark vector in compressed form; B-D then stream those ~230-byte rows, or rer
   B  best matching landmark vector per cluster (max |centre . x|, first row)       (mcl.py:81-89)
   C  predict + bincount                      -> min_samples filter                  (DotProdClassifier.pyx:86-108)
   D  predict with the kept centres + representative landmark vectors + per-site max-confidence row
+     (C already produces D's outputs; D only reruns when the filter dropped a cluster)
 """
 import ctypes as C
 import logging
@@ -198,11 +199,26 @@ def do_landmark_clustering(landmark_vectors, clustering_params, min_samples, ver
     if n_clusters == 0:
         raise ValueError("`min_samples` too large; all 0 clusters under threshold.")
 
-    # -- pass C: predict + bincount, then the min_samples filter (DotProdClassifier.pyx:86-115)
+    # -- pass C: predict + bincount, then the min_samples filter (DotProdClassifier.pyx:86-115).  The pass also
+    # writes everything the final predict needs: when the filter removes no cluster (the usual case) the
+    # centres of pass D are the same and its outputs would be bit-identical, so pass D is skipped.
     cid, w = _centre_tables(clusters, vectors, L)
     eng.set_centers(cid, w, n_clusters)
-    counts = torch.zeros((n_clusters,), dtype=torch.int64, device=eng.device)
-    source.assign(predict_threshold, counts=counts)
+    N = source.n_local
+
+    def final_predict(n_c, with_counts):
+        out = dict(labels=torch.empty((N,), dtype=torch.int64, device=eng.device),
+                   confs=torch.empty((N,), dtype=torch.float64, device=eng.device),
+                   rep=torch.zeros((n_c, L), dtype=torch.float64, device=eng.device),
+                   rep_w=torch.zeros((n_c,), dtype=torch.float64, device=eng.device),
+                   site_best=new_best_table(n_c, eng.device))
+        if with_counts:
+            out['counts'] = torch.zeros((n_c,), dtype=torch.int64, device=eng.device)
+        source.assign(predict_threshold, **out)
+        return out
+
+    res = final_predict(n_clusters, True)
+    counts = res.pop('counts')
     if comm is not None:
         comm.allreduce_sum_(counts)
     cluster_counts = counts.cpu().numpy()
@@ -223,15 +239,11 @@ def do_landmark_clustering(landmark_vectors, clustering_params, min_samples, ver
     n_sites = len(clusters)
 
     # -- pass D: final predict + representative landmark vectors (mcl.py:114-122) + per-site best row
-    cid, w = _centre_tables(clusters, vectors, L)
-    eng.set_centers(cid, w, n_sites)
-    N = source.n_local
-    labels = torch.empty((N,), dtype=torch.int64, device=eng.device)
-    confs = torch.empty((N,), dtype=torch.float64, device=eng.device)
-    rep = torch.zeros((n_sites, L), dtype=torch.float64, device=eng.device)
-    rep_w = torch.zeros((n_sites,), dtype=torch.float64, device=eng.device)
-    site_best = new_best_table(n_sites, eng.device)
-    source.assign(predict_threshold, labels=labels, confs=confs, rep=rep, rep_w=rep_w, site_best=site_best)
+    if not np.all(count_mask):
+        cid, w = _centre_tables(clusters, vectors, L)
+        eng.set_centers(cid, w, n_sites)
+        res = final_predict(n_sites, False)
+    labels, confs, rep, rep_w, site_best = res['labels'], res['confs'], res['rep'], res['rep_w'], res['site_best']
     if comm is not None:
         comm.allreduce_sum_(rep)
         comm.allreduce_sum_(rep_w)
