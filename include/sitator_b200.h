@@ -112,11 +112,18 @@ int sitb_fill_dense_frames(sitb_ctx* ctx, const int64_t* dev_frame_list, int64_t
 int sitb_pass_stats(sitb_ctx* ctx, int64_t frame_begin, int64_t n, uint64_t* dev_seen, double* dev_gram_upper);
 
 /* sitb_pass_stats that also keeps every landmark vector in compressed form (they are ~1.5 % dense):
+ * dev_gram_upper may be NULL (then build the Gram with sitb_gram_from_cached);
  * dev_row_ptr[n*M] = offset << 8 | count (all ones: pool exhausted, grow and rerun), entries
  * (landmark index uint16, value float64) at dev_pool_k/v[offset ...], *dev_cursor = entries used. */
 int sitb_pass_stats_cached(sitb_ctx* ctx, int64_t frame_begin, int64_t n, uint64_t* dev_seen, double* dev_gram_upper,
                            uint64_t* dev_row_ptr, uint16_t* dev_pool_k, double* dev_pool_v, uint64_t* dev_cursor,
                            uint64_t capacity);
+/* The Gram of rows cached by sitb_pass_stats_cached (pass dev_gram_upper = NULL there): dev_gram_upper [L][L] += the
+ * upper triangle of sum_rows lv^T lv over the n_frames * n_mobile cached rows, accumulated per (mobile atom, window
+ * of consecutive frames) in shared memory before it touches the matrix.  Fails with SITB_E_CUDA
+ * (invalid configuration) when n_landmarks is too large for the shared-memory tables (> ~9000). */
+int sitb_gram_from_cached(sitb_ctx* ctx, const uint64_t* dev_row_ptr, const uint16_t* dev_pool_k,
+                          const double* dev_pool_v, int64_t n_frames, double* dev_gram_upper);
 /* sitb_pass_assign over rows cached by sitb_pass_stats_cached (same outputs, same semantics); row0 = global
  * index of the first row.  The later passes of the clustering plugin (cluster/mcl.py:81-83, :98-122) stream the
  * compressed rows instead of recomputing them. */

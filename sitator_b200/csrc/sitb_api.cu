@@ -526,7 +526,7 @@ extern "C" int sitb_pass_stats_cached(sitb_ctx* c, int64_t begin, int64_t n, uin
     FillParams p;
     int rc = base_params(c, begin, n, p, "sitb_pass_stats_cached");
     if (rc) return rc;
-    if (!dev_seen || !dev_gram || !dev_row_ptr || !dev_pool_k || !dev_pool_v || !dev_cursor)
+    if (!dev_seen || !dev_row_ptr || !dev_pool_k || !dev_pool_v || !dev_cursor)      // dev_gram may be null
         return fail(SITB_E_INVALID, "sitb_pass_stats_cached: null output");
     CK(cudaSetDevice(c->device));
     p.seen = (unsigned long long*)dev_seen; p.gram = dev_gram;
@@ -548,6 +548,21 @@ extern "C" int sitb_assign_sparse(sitb_ctx* c, const uint64_t* dev_row_ptr, cons
                             c->d_cid_orig, c->d_cw_orig, c->n_clusters, thr, (long long*)labels, confs,
                             (unsigned long long*)counts, (unsigned long long*)best, rep, rep_w,
                             (unsigned long long*)site_best, c->n_sms, c->stream));
+    return SITB_OK;
+}
+
+// ---- Gram from the cached rows (sitb_gram_sparse.cu) -------------------------------------------------
+namespace sitb {
+cudaError_t launch_gram_sparse(const unsigned long long* row_ptr, const uint16_t* pk, const double* pv, long long n_frames,
+                               int M, int L, double* gram, int n_sms, cudaStream_t st);
+}
+extern "C" int sitb_gram_from_cached(sitb_ctx* c, const uint64_t* dev_row_ptr, const uint16_t* dev_pool_k,
+                                     const double* dev_pool_v, int64_t n_frames, double* dev_gram) {
+    if (!c || !dev_row_ptr || !dev_pool_k || !dev_pool_v || !dev_gram || n_frames < 0)
+        return fail(SITB_E_INVALID, "sitb_gram_from_cached: bad argument");
+    CK(cudaSetDevice(c->device));
+    CK(launch_gram_sparse((const unsigned long long*)dev_row_ptr, dev_pool_k, dev_pool_v, n_frames, c->M, c->L, dev_gram,
+                          c->n_sms, c->stream));
     return SITB_OK;
 }
 

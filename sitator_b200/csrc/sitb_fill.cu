@@ -470,8 +470,9 @@ __global__ void __launch_bounds__(DIAG ? 1024 : 512) k_fill(const __grid_constan
                         for (int e = lane; e < nent; e += 32) o[ek[e]] = (float)ev[e];
                     }
                 }
-                if (MODE == MODE_STATS) {
-                    // upper triangle of the outer product
+                if (MODE == MODE_STATS && p.gram) {
+                    // upper triangle of the outer product (when the rows are cached, sitb_gram_sparse.cu
+                    // builds the Gram from them with far fewer atomics and p.gram is null here)
                     for (int a = 0; a < nent; ++a) {
                         const unsigned ka = ek[a];
                         const double va = ev[a];

@@ -1,0 +1,195 @@
+// sitator_b200 -- K2s: the landmark Gram  G = sum over rows of lv^T lv  (cluster/mcl.py:54) in FP64 from the
+// cached compressed rows (sitb_fill.cu, sparse_ptr/k/v).
+//
+// A row has ~22 non-zero components: 253 pair products, and adding each straight into the L x L matrix costs
+// 253 L2 atomics per row (1.4e9 per 10^5 LLZO frames; that was 9 of pass A's 25 ms).  But one mobile atom sees
+// almost the same landmarks from frame to frame (union over 16 consecutive frames: ~34 landmarks), so:
+//   one warp per (mobile atom, window of GW_T = 16 consecutive frames)
+//     1. union of the window's landmarks as a bitmap in shared memory -> local slot of every landmark
+//     2. scatter the window's rows into a dense GW_T x slots FP64 matrix X in shared memory
+//     3. X^T X on the FP64 tensor cores (mma.sync m8n8k4.f64, 8x8 tiles of the upper triangle, K = the 16 frames)
+//     4. add the non-zero entries of the tiles into G straight from the accumulator registers:
+//        ~35 atomics per row instead of 253, and ~50 instructions per row instead of ~300
+//   windows whose union exceeds GW_CAP slots (an atom in transit through many sites) add directly.
+// The sums are the same FP64 products in a different association; G is exact to rounding either way.
+#include "../../include/sitator_b200.h"
+#include "sitb_common.cuh"
+
+namespace sitb {
+
+constexpr int GW_T = 16;         // frames per window = K of the local product (4 mma k-steps)
+constexpr int GW_CAP = 48;       // landmark slots per window (6 tiles of 8)
+constexpr int GW_STRIDE = 52;    // row stride of X in doubles: = 4 mod 16, so the 4 x 8 fragment loads are conflict-free
+constexpr int GW_WARPS = 14;     // warps per CTA (two CTAs per SM)
+constexpr int GW_NT = GW_CAP / 8;
+
+__device__ __forceinline__ void gram_row_direct(const uint16_t* __restrict__ pk, const double* __restrict__ pv,
+                                                unsigned long long off, int n, int lane, int L,
+                                                double* __restrict__ gram) {
+    for (int a = 0; a < n; ++a) {
+        const unsigned ka = pk[off + a];
+        const double va = pv[off + a];
+        for (int b = a + lane; b < n; b += 32) {
+            const unsigned kb = pk[off + b];
+            const unsigned lo = ka < kb ? ka : kb, hi = ka < kb ? kb : ka;
+            atomicAdd(&gram[(size_t)lo * L + hi], va * pv[off + b]);
+        }
+    }
+}
+
+// D(8x8) += A(8x4, row) * B(4x8, col) in FP64 on the tensor cores
+__device__ __forceinline__ void dmma(double (&d)[2], double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0, %1}, {%2}, {%3}, {%0, %1};"
+                 : "+d"(d[0]), "+d"(d[1]) : "d"(a), "d"(b));
+}
+
+__host__ __device__ inline size_t gram_warp_bytes(int words) {
+    return ((sizeof(double) * GW_T * GW_STRIDE + 4 * (size_t)words + 2 * (size_t)words + 2 * GW_CAP) + 15) & ~(size_t)15;
+}
+
+__global__ void __launch_bounds__(GW_WARPS * 32, 2)
+k_gram_windows(const unsigned long long* __restrict__ row_ptr, const uint16_t* __restrict__ pk,
+               const double* __restrict__ pv, long long n_frames, int M, int L, int words,
+               double* __restrict__ gram) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    // per warp: X [GW_T][GW_STRIDE] f64 | bitmap [words] u32 | slot offset of each word [words] u16 | ids [GW_CAP] u16
+    unsigned char* base = smem_raw + (size_t)warp * gram_warp_bytes(words);
+    double* X = (double*)base;
+    unsigned* bits = (unsigned*)(base + sizeof(double) * GW_T * GW_STRIDE);
+    uint16_t* wofs = (uint16_t*)(bits + words);
+    uint16_t* ids = wofs + words;
+    const int r4 = lane & 3, c8 = lane >> 2;
+
+    const long long n_windows = (n_frames + GW_T - 1) / GW_T;
+    const long long n_tasks = n_windows * M;
+    for (long long t = (long long)blockIdx.x * GW_WARPS + warp; t < n_tasks; t += (long long)gridDim.x * GW_WARPS) {
+        const int j = (int)(t % M);
+        const long long f0 = (t / M) * GW_T;
+        const int nf = (int)((n_frames - f0 < GW_T) ? (n_frames - f0) : GW_T);
+        // lane i holds row i of the window
+        unsigned long long my_off = 0;
+        int my_n = 0;
+        if (lane < nf) {
+            const unsigned long long e = row_ptr[(f0 + lane) * M + j];
+            my_off = e >> 8; my_n = (int)(e & 0xFFull);
+        }
+        const bool long_rows = __any_sync(0xffffffffu, my_n > 32);
+        // 1. union bitmap (the first 32 entries of all rows are fetched together; longer rows are rare)
+        for (int w = lane; w < words; w += 32) bits[w] = 0u;
+        for (int i = lane; i < GW_T * GW_STRIDE; i += 32) X[i] = 0.0;
+        __syncwarp();
+        unsigned kk[GW_T];
+#pragma unroll
+        for (int i = 0; i < GW_T; ++i) {
+            const unsigned long long off = __shfl_sync(0xffffffffu, my_off, i);
+            const int n = __shfl_sync(0xffffffffu, my_n, i);
+            kk[i] = (lane < n) ? (unsigned)pk[off + lane] : 0xFFFFFFFFu;
+        }
+#pragma unroll
+        for (int i = 0; i < GW_T; ++i)
+            if (kk[i] != 0xFFFFFFFFu) atomicOr(&bits[kk[i] >> 5], 1u << (kk[i] & 31u));
+        if (long_rows) {
+            for (int i = 0; i < nf; ++i) {
+                const unsigned long long off = __shfl_sync(0xffffffffu, my_off, i);
+                const int n = __shfl_sync(0xffffffffu, my_n, i);
+                for (int e = 32 + lane; e < n; e += 32) {
+                    const unsigned k = pk[off + e];
+                    atomicOr(&bits[k >> 5], 1u << (k & 31u));
+                }
+            }
+        }
+        __syncwarp();
+        // slot offsets: exclusive prefix of the words' popcounts
+        int carry = 0;
+        for (int w0 = 0; w0 < words; w0 += 32) {
+            const int w = w0 + lane;
+            const int c = (w < words) ? __popc(bits[w]) : 0;
+            int incl = c;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int v = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= o) incl += v;
+            }
+            if (w < words) wofs[w] = (uint16_t)(carry + incl - c);
+            carry += __shfl_sync(0xffffffffu, incl, 31);
+        }
+        const int u = carry;
+        __syncwarp();
+        if (u > GW_CAP) {
+            for (int i = 0; i < nf; ++i)
+                gram_row_direct(pk, pv, __shfl_sync(0xffffffffu, my_off, i), __shfl_sync(0xffffffffu, my_n, i), lane, L, gram);
+            continue;
+        }
+        for (int w = lane; w < words; w += 32) {
+            unsigned b = bits[w];
+            int s = wofs[w];
+            while (b) { ids[s++] = (uint16_t)(w * 32 + __ffs(b) - 1); b &= b - 1u; }
+        }
+        // 2. X[row][slot] = value
+#pragma unroll
+        for (int i = 0; i < GW_T; ++i) {
+            const unsigned long long off = __shfl_sync(0xffffffffu, my_off, i);
+            if (kk[i] != 0xFFFFFFFFu) {
+                const unsigned k = kk[i];
+                const int s = wofs[k >> 5] + __popc(bits[k >> 5] & ((1u << (k & 31u)) - 1u));
+                X[i * GW_STRIDE + s] = pv[off + lane];
+            }
+        }
+        if (long_rows) {
+            for (int i = 0; i < nf; ++i) {
+                const unsigned long long off = __shfl_sync(0xffffffffu, my_off, i);
+                const int n = __shfl_sync(0xffffffffu, my_n, i);
+                for (int e = 32 + lane; e < n; e += 32) {
+                    const unsigned k = pk[off + e];
+                    const int s = wofs[k >> 5] + __popc(bits[k >> 5] & ((1u << (k & 31u)) - 1u));
+                    X[i * GW_STRIDE + s] = pv[off + e];
+                }
+            }
+        }
+        __syncwarp();
+        // 3. + 4. upper-triangular tiles of X^T X, flushed from the accumulators
+        const int nt = (u + 7) >> 3;
+        for (int ti = 0; ti < nt; ++ti) {
+            double acc[GW_NT][2];
+#pragma unroll
+            for (int d = 0; d < GW_NT; ++d) acc[d][0] = acc[d][1] = 0.0;
+#pragma unroll
+            for (int ks = 0; ks < GW_T / 4; ++ks) {
+                const double* xr = X + (ks * 4 + r4) * GW_STRIDE + c8;
+                const double a = xr[ti * 8];
+#pragma unroll
+                for (int d = 0; d < GW_NT; ++d)
+                    if (ti + d < nt) dmma(acc[d], a, xr[(ti + d) * 8]);
+            }
+            const int r = ti * 8 + c8;                    // accumulator row (slot)
+            if (r < u) {
+                const size_t ra = (size_t)ids[r] * L;
+#pragma unroll
+                for (int d = 0; d < GW_NT; ++d) {
+                    if (ti + d >= nt) break;
+#pragma unroll
+                    for (int q = 0; q < 2; ++q) {
+                        const int c = (ti + d) * 8 + r4 * 2 + q;
+                        if (c < u && c >= r && acc[d][q] != 0.0) atomicAdd(&gram[ra + ids[c]], acc[d][q]);
+                    }
+                }
+            }
+        }
+        __syncwarp();
+    }
+}
+
+cudaError_t launch_gram_sparse(const unsigned long long* row_ptr, const uint16_t* pk, const double* pv, long long n_frames,
+                               int M, int L, double* gram, int n_sms, cudaStream_t st) {
+    if (n_frames <= 0) return cudaSuccess;
+    const int words = (L + 31) / 32;
+    const size_t smem = gram_warp_bytes(words) * GW_WARPS;
+    if (smem > 110 * 1024) return cudaErrorInvalidConfiguration;      // L > ~9000: the caller keeps the in-kernel Gram
+    cudaError_t e = cudaFuncSetAttribute(k_gram_windows, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    k_gram_windows<<<n_sms * 2, GW_WARPS * 32, smem, st>>>(row_ptr, pk, pv, n_frames, M, L, words, gram);
+    return cudaGetLastError();
+}
+
+}  // namespace sitb

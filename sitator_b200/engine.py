@@ -250,8 +250,12 @@ class LandmarkEngine(object):
                                                       C.c_void_p(stream)))
         return seen, gram
 
-    def pass_stats_cached(self, seen=None, gram=None, entries_per_row=40):
-        """Pass A that also caches every landmark vector compressed (SparseRows); grows the pool on overflow."""
+    def pass_stats_cached(self, seen=None, gram=None, entries_per_row=40, gram_from_rows=None):
+        """Pass A that also caches every landmark vector compressed (SparseRows); grows the pool on overflow.
+        ``gram_from_rows`` (default: whenever the shared-memory tables fit, L <= 8192): build the Gram from the
+        cached rows per (atom, window of frames) instead of with one atomic per pair product inside K1."""
+        if gram_from_rows is None:
+            gram_from_rows = self.L <= 8192
         torch = _torch()
         n_rows = self.n_frames * self.M
         if seen is None:
@@ -263,7 +267,8 @@ class LandmarkEngine(object):
             rows = SparseRows(self._empty((n_rows,), torch.int64), self._empty((cap,), torch.int16),
                               self._empty((cap,), torch.float64), self._zeros((1,), torch.int64), cap, n_rows,
                               self.frame0 * self.M)
-            seen_try, gram_try = seen.clone(), gram.clone()
+            seen_try = seen.clone()
+            gram_try = None if gram_from_rows else gram.clone()
             # launched per upload chunk: each launch waits only for its own chunk of the host -> device copy
             step = self.upload_chunk_frames() or self.n_frames
             for b in range(0, self.n_frames, step):
@@ -274,7 +279,12 @@ class LandmarkEngine(object):
                     self._ptr(rows.cursor), cap))
             used = int(rows.cursor.item())
             if used <= cap:
-                seen.copy_(seen_try); gram.copy_(gram_try)
+                seen.copy_(seen_try)
+                if gram_from_rows:
+                    _native.check(self._lib.sitb_gram_from_cached(self._ctx, self._ptr(rows.ptr), self._ptr(rows.k),
+                                                                  self._ptr(rows.v), self.n_frames, self._ptr(gram)))
+                else:
+                    gram.copy_(gram_try)
                 rows.used = used
                 return seen, gram, rows
             entries_per_row = used / float(n_rows) * 1.05 + 1     # exact requirement is known now

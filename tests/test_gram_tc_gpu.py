@@ -91,3 +91,21 @@ def test_run_with_tensor_core_gram_reproduces_reference_sites(name):
     assert np.array_equal(st.traj, g["labels"])
     assert np.max(np.abs(st.confidences - g["confs"])) < 1e-6
     assert np.array_equal(st.jump_array(), g["jumps"])
+
+
+@pytest.mark.parametrize("name,frames", [("toy_bcc", 300), ("llzo", 100), ("lgps_dynamic", 70)])
+def test_windowed_gram_from_cached_rows_matches_direct(name, frames):
+    """sitb_gram_from_cached (per atom-and-window shared-memory tables) against the one-atomic-per-product Gram
+    of sitb_pass_stats: the same FP64 products in another association, so equal to rounding (1e-13)."""
+    import torch
+    system, cfg = syn.make_config(name)
+    eng = U.engine_for(system, dynamic_lattice_mapping=cfg["dynamic"])
+    eng.set_frames(system.trajectory(frames))
+    seen, gram = eng.pass_stats()
+    for from_rows in (True, False):
+        seen_c, gram_c, rows = eng.pass_stats_cached(gram_from_rows=from_rows)
+        torch.cuda.synchronize()
+        assert torch.equal(seen, seen_c)
+        g, gc = np.triu(gram.cpu().numpy()), np.triu(gram_c.cpu().numpy())
+        assert np.array_equal(g != 0, gc != 0)
+        assert np.max(np.abs(g - gc) / np.maximum(np.abs(g), 1e-300)) < 1e-13
