@@ -80,13 +80,40 @@ __global__ void __launch_bounds__(256) k_dgemm(const double* __restrict__ A, con
 }
 
 // ---- column sums in the row order NumPy uses for axis=0 on a C-contiguous matrix ----------------
-__global__ void k_colsum(const double* __restrict__ m, int n, double* __restrict__ out) {
-    const int j = blockIdx.x * blockDim.x + threadIdx.x;
-    if (j >= n) return;
+// The additions of one column must stay in row order (bit-compatible with NumPy's reduction), so a column is
+// one thread's serial chain; what is parallel is the fetching: 8 warps bring 64 rows x 32 columns at a time
+// into shared memory (double-buffered), warp 0 then adds them in order.
+constexpr int CS_ROWS = 64;
+__global__ void __launch_bounds__(256) k_colsum(const double* __restrict__ m, int n, double* __restrict__ out) {
+    __shared__ double buf[2][CS_ROWS][32];
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const int j = blockIdx.x * 32 + tx;
+    const bool live = j < n;
     double s = 0.0;
-#pragma unroll 32
-    for (int i = 0; i < n; ++i) s = __dadd_rn(s, m[(size_t)i * n + j]);     // loads pipeline, adds stay in order
-    out[j] = s;
+    const int n_chunks = (n + CS_ROWS - 1) / CS_ROWS;
+    auto fetch = [&](int chunk, int first, int step) {
+        double (*b)[32] = buf[chunk & 1];
+        const int r0 = chunk * CS_ROWS;
+#pragma unroll 8
+        for (int r = first; r < CS_ROWS; r += step) {
+            const int i = r0 + r;
+            b[r][tx] = (live && i < n) ? m[(size_t)i * n + j] : 0.0;
+        }
+    };
+    fetch(0, ty, 8);
+    __syncthreads();
+    for (int c = 0; c < n_chunks; ++c) {
+        if (ty != 0) {
+            if (c + 1 < n_chunks) fetch(c + 1, ty - 1, 7);      // warps 1..7 fetch while warp 0 adds
+        } else {
+            const double (*b)[32] = buf[c & 1];
+            const int rows = (n - c * CS_ROWS < CS_ROWS) ? (n - c * CS_ROWS) : CS_ROWS;
+#pragma unroll 8
+            for (int r = 0; r < rows; ++r) s = __dadd_rn(s, b[r][tx]);
+        }
+        __syncthreads();
+    }
+    if (ty == 0 && live) out[j] = s;
 }
 
 __global__ void k_coldiv(double* __restrict__ m, int n, const double* __restrict__ colsum) {
@@ -129,16 +156,74 @@ __global__ void __launch_bounds__(256) k_colargmax(const double* __restrict__ m,
 }
 
 // prune (util/mcl.py:37-40) and compare with the previous iterate (np.allclose, :42) in one pass
+// flags[0] = "not close", flags[1] += number of non-zero entries left in m2 (picks the product kernel of the next
+// iteration)
 __global__ void k_prune_compare(double* __restrict__ m2, const double* __restrict__ m1, int n,
-                                const int* __restrict__ arg, double thr, int* __restrict__ not_close) {
+                                const int* __restrict__ arg, double thr, unsigned long long* __restrict__ flags) {
     const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= (size_t)n * n) return;
-    const int i = (int)(idx / n), j = (int)(idx % n);
-    double v = m2[idx];
-    if (v < thr && i != arg[j]) { v = 0.0; m2[idx] = 0.0; }
-    const double a = m1[idx];
-    // np.allclose(a, b): |a - b| <= atol + rtol * |b|, atol 1e-8, rtol 1e-5; NaN never close
-    if (!(fabs(a - v) <= 1e-8 + 1e-5 * fabs(v))) *not_close = 1;
+    bool nz = false;
+    if (idx < (size_t)n * n) {
+        const int i = (int)(idx / n), j = (int)(idx % n);
+        double v = m2[idx];
+        if (v < thr && i != arg[j]) { v = 0.0; m2[idx] = 0.0; }
+        const double a = m1[idx];
+        // np.allclose(a, b): |a - b| <= atol + rtol * |b|, atol 1e-8, rtol 1e-5; NaN never close
+        if (!(fabs(a - v) <= 1e-8 + 1e-5 * fabs(v))) flags[0] = 1ull;
+        nz = v != 0.0;
+    }
+    const unsigned m = __ballot_sync(0xffffffffu, nz);
+    if ((threadIdx.x & 31) == 0 && m) atomicAdd(&flags[1], (unsigned long long)__popc(m));
+}
+
+__global__ void k_count_nonzero(const double* __restrict__ m, size_t count, unsigned long long* __restrict__ out) {
+    const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const unsigned b = __ballot_sync(0xffffffffu, idx < count && m[idx] != 0.0);
+    if ((threadIdx.x & 31) == 0 && b) atomicAdd(out, (unsigned long long)__popc(b));
+}
+
+// C = A * B for a sparse A (MCL iterates after pruning: a few dozen entries per row).  One CTA per row i of A:
+// the row's non-zeros are compacted in ascending k, 256 at a time, and every thread accumulates its columns
+// over that list -- the same fma chain in the same k order as k_dgemm (a zero a_ik leaves an fma chain
+// unchanged), so both kernels give bit-identical products.
+constexpr int SP_COLS = 8;          // columns per thread and pass: 2048 columns per pass
+__global__ void __launch_bounds__(256) k_spgemm_rows(const double* __restrict__ A, const double* __restrict__ B,
+                                                     double* __restrict__ C, int n) {
+    __shared__ unsigned short lk[256];
+    __shared__ double la[256];
+    __shared__ int wcount[8];
+    const int i = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const double* arow = A + (size_t)i * n;
+    for (int c0 = 0; c0 < n; c0 += 256 * SP_COLS) {
+        double acc[SP_COLS];
+#pragma unroll
+        for (int c = 0; c < SP_COLS; ++c) acc[c] = 0.0;
+        for (int k0 = 0; k0 < n; k0 += 256) {
+            const int k = k0 + tid;
+            const double a = (k < n) ? arow[k] : 0.0;
+            const unsigned m = __ballot_sync(0xffffffffu, a != 0.0);
+            if (lane == 0) wcount[warp] = __popc(m);
+            __syncthreads();
+            int base = 0, total = 0;
+#pragma unroll
+            for (int w = 0; w < 8; ++w) { if (w < warp) base += wcount[w]; total += wcount[w]; }
+            if (a != 0.0) {
+                const int pos = base + __popc(m & ((1u << lane) - 1u));
+                lk[pos] = (unsigned short)(k - k0); la[pos] = a;
+            }
+            __syncthreads();
+            for (int e = 0; e < total; ++e) {
+                const double av = la[e];
+                const double* brow = B + (size_t)(k0 + lk[e]) * n + c0 + tid;
+#pragma unroll
+                for (int c = 0; c < SP_COLS; ++c)
+                    if (c0 + tid + 256 * c < n) acc[c] = fma(av, brow[256 * c], acc[c]);
+            }
+            __syncthreads();
+        }
+#pragma unroll
+        for (int c = 0; c < SP_COLS; ++c)
+            if (c0 + tid + 256 * c < n) C[(size_t)i * n + c0 + tid + 256 * c] = acc[c];
+    }
 }
 
 // cluster/mcl.py:54-59 from the un-normalised upper-triangular Gram
@@ -200,7 +285,8 @@ extern "C" int sitb_markov_clustering(int device, const double* dev_graph, int32
     cudaStream_t st = (cudaStream_t)cuda_stream;
     const size_t cnt = (size_t)n * n, bytes = cnt * sizeof(double);
     double *m1 = nullptr, *m2 = nullptr, *z = nullptr, *tmp = nullptr, *colsum = nullptr;
-    int *arg = nullptr, *flag = nullptr;
+    int* arg = nullptr;
+    unsigned long long* flag = nullptr;      // [0] not close, [1] non-zeros of the pruned iterate
     unsigned char *amap = nullptr, *bmap = nullptr;
     const unsigned eb = (unsigned)((cnt + 255) / 256), cb = (unsigned)((n + 31) / 32);
     const dim3 gg((n + GB - 1) / GB, (n + GB - 1) / GB);
@@ -212,11 +298,16 @@ extern "C" int sitb_markov_clustering(int device, const double* dev_graph, int32
         CKM(sitb::pool_alloc((void**)&tmp, bytes, st));
         CKM(sitb::pool_alloc((void**)&colsum, sizeof(double) * n, st));
         CKM(sitb::pool_alloc((void**)&arg, sizeof(int) * n, st));
-        CKM(sitb::pool_alloc((void**)&flag, sizeof(int), st));
+        CKM(sitb::pool_alloc((void**)&flag, 2 * sizeof(unsigned long long), st));
         const int kt = (n + GK - 1) / GK;
         CKM(sitb::pool_alloc((void**)&amap, (size_t)gg.y * kt, st));
         CKM(sitb::pool_alloc((void**)&bmap, (size_t)kt * gg.x, st));
+        long long m1_nnz = -1;                     // non-zeros of m1 when known
         auto gemm = [&](const double* X, const double* Y, double* Z) {
+            if (X == m1 && m1_nnz >= 0 && (double)m1_nnz < 0.06 * (double)cnt) {
+                k_spgemm_rows<<<n, 256, 0, st>>>(X, Y, Z, n);
+                return;
+            }
             k_tilemap<<<dim3(kt, gg.y), 256, 0, st>>>(X, n, GB, GK, amap);
             k_tilemap<<<dim3(gg.x, kt), 256, 0, st>>>(Y, n, GK, GB, bmap);
             k_dgemm<<<gg, 256, 0, st>>>(X, Y, Z, n, amap, bmap);
@@ -224,8 +315,16 @@ extern "C" int sitb_markov_clustering(int device, const double* dev_graph, int32
         m2 = dev_result;
         // m1 = graph / colsum (util/mcl.py:22-25)
         CKM(cudaMemcpyAsync(m1, dev_graph, bytes, cudaMemcpyDeviceToDevice, st));
-        k_colsum<<<cb, 32, 0, st>>>(m1, n, colsum);
+        k_colsum<<<cb, 256, 0, st>>>(m1, n, colsum);
         k_coldiv<<<eb, 256, 0, st>>>(m1, n, colsum);
+        {
+            unsigned long long h_nnz = 0;
+            CKM(cudaMemsetAsync(flag, 0, 2 * sizeof(unsigned long long), st));
+            k_count_nonzero<<<eb, 256, 0, st>>>(m1, cnt, flag + 1);
+            CKM(cudaMemcpyAsync(&h_nnz, flag + 1, sizeof(h_nnz), cudaMemcpyDeviceToHost, st));
+            CKM(cudaStreamSynchronize(st));
+            m1_nnz = (long long)h_nnz;
+        }
         for (it = 0; it < iterlimit; ++it) {
             // expansion: np.linalg.matrix_power(m1, expansion) with NumPy's multiplication order
             if (expansion == 1) {
@@ -259,16 +358,17 @@ extern "C" int sitb_markov_clustering(int device, const double* dev_graph, int32
                 sitb::pool_free(res_tmp, st);
             }
             k_power<<<eb, 256, 0, st>>>(m2, cnt, inflation);                 // :34
-            k_colsum<<<cb, 32, 0, st>>>(m2, n, colsum);                      // :35
+            k_colsum<<<cb, 256, 0, st>>>(m2, n, colsum);                      // :35
             k_coldiv<<<eb, 256, 0, st>>>(m2, n, colsum);
             k_colargmax<<<cb, 256, 0, st>>>(m2, n, arg);                      // :39
-            CKM(cudaMemsetAsync(flag, 0, sizeof(int), st));
+            CKM(cudaMemsetAsync(flag, 0, 2 * sizeof(unsigned long long), st));
             k_prune_compare<<<eb, 256, 0, st>>>(m2, m1, n, arg, pruning_threshold, flag);   // :37-42
-            int h_flag = 1;
-            CKM(cudaMemcpyAsync(&h_flag, flag, sizeof(int), cudaMemcpyDeviceToHost, st));
+            unsigned long long h_flag[2] = {1ull, 0ull};
+            CKM(cudaMemcpyAsync(h_flag, flag, sizeof(h_flag), cudaMemcpyDeviceToHost, st));
             CKM(cudaStreamSynchronize(st));
             CKM(cudaGetLastError());
-            if (!h_flag) { conv = 1; ++it; break; }
+            if (!h_flag[0]) { conv = 1; ++it; break; }
+            m1_nnz = (long long)h_flag[1];
             CKM(cudaMemcpyAsync(m1, m2, bytes, cudaMemcpyDeviceToDevice, st));   // :46
         }
         CKM(cudaStreamSynchronize(st));

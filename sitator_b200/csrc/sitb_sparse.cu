@@ -136,18 +136,32 @@ __global__ void __launch_bounds__(256) k_assign_sparse(
     }
 }
 
-// merge per-CTA (value, row) tables into the caller's table: max value, then lowest row
-__global__ void k_merge_best(const unsigned long long* __restrict__ scratch, int n_cta, int C,
-                             unsigned long long* __restrict__ tab) {
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= C) return;
-    unsigned long long bv = tab[c], br = tab[C + c];
-    for (int b = 0; b < n_cta; ++b) {
-        const unsigned long long v = scratch[((size_t)b * 2) * C + c], r = scratch[((size_t)b * 2 + 1) * C + c];
-        if (v > bv || (v == bv && r < br)) { bv = v; br = r; }
+// merge per-CTA (value, row) tables into the caller's table: max value, then lowest row.
+// Block (32 clusters x 8 slices of the CTA list): coalesced reads, 8-way parallel over the list.
+__global__ void __launch_bounds__(256) k_merge_best(const unsigned long long* __restrict__ scratch, int n_cta, int C,
+                                                    unsigned long long* __restrict__ tab) {
+    __shared__ unsigned long long sv[8][32], sr[8][32];
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const int c = blockIdx.x * 32 + tx;
+    unsigned long long bv = 0ull, br = ~0ull;
+    if (c < C) {
+#pragma unroll 4
+        for (int b = ty; b < n_cta; b += 8) {
+            const unsigned long long v = scratch[((size_t)b * 2) * C + c], r = scratch[((size_t)b * 2 + 1) * C + c];
+            if (v > bv || (v == bv && r < br)) { bv = v; br = r; }
+        }
     }
-    tab[c] = bv;
-    tab[C + c] = br;
+    sv[ty][tx] = bv; sr[ty][tx] = br;
+    __syncthreads();
+    if (ty == 0 && c < C) {
+        bv = tab[c]; br = tab[C + c];
+        for (int g = 0; g < 8; ++g) {
+            const unsigned long long v = sv[g][tx], r = sr[g][tx];
+            if (v > bv || (v == bv && r < br)) { bv = v; br = r; }
+        }
+        tab[c] = bv;
+        tab[C + c] = br;
+    }
 }
 
 cudaError_t launch_assign_sparse(const unsigned long long* row_ptr, const uint16_t* pk, const double* pv,
@@ -169,8 +183,8 @@ cudaError_t launch_assign_sparse(const unsigned long long* row_ptr, const uint16
     if (site_best) { e = cudaMallocAsync((void**)&ss, sizeof(unsigned long long) * 2 * (size_t)grid * C, st); if (e != cudaSuccess) return e; }
     k_assign_sparse<<<grid, warps * 32, smem, st>>>(row_ptr, pk, pv, n_rows, row0, L, cid, cw, n_clusters, thr, labels, confs,
                                             counts, sb, rep, rep_w, ss);
-    if (best) { k_merge_best<<<(C + 127) / 128, 128, 0, st>>>(sb, grid, n_clusters, best); cudaFreeAsync(sb, st); }
-    if (site_best) { k_merge_best<<<(C + 127) / 128, 128, 0, st>>>(ss, grid, n_clusters, site_best); cudaFreeAsync(ss, st); }
+    if (best) { k_merge_best<<<(C + 31) / 32, 256, 0, st>>>(sb, grid, n_clusters, best); cudaFreeAsync(sb, st); }
+    if (site_best) { k_merge_best<<<(C + 31) / 32, 256, 0, st>>>(ss, grid, n_clusters, site_best); cudaFreeAsync(ss, st); }
     return cudaGetLastError();
 }
 

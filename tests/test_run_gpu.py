@@ -105,13 +105,13 @@ def test_integer_kernels_against_oracle_on_adversarial_tables():
         assert np.array_equal(getattr(sn, key), ja[key]), key
 
 
-def test_mcl_kernels_against_oracle():
+@pytest.mark.parametrize("n", [150, 640])        # 640: sparse enough for the sparse-row product from iteration 1
+def test_mcl_kernels_against_oracle(n):
     from oracle import landmark_oracle as orc
     from sitator_b200.util.mcl import markov_clustering
     rng = np.random.default_rng(1)
-    n = 150
     # noisy block structure with weak cross links
-    blocks = np.repeat(np.arange(15), 10)
+    blocks = np.repeat(np.arange(n // 10), 10)
     g = (blocks[:, None] == blocks[None, :]).astype(float) * rng.uniform(0.3, 1.0, (n, n))
     g += rng.uniform(0, 0.02, (n, n)) * (rng.random((n, n)) < 0.05)
     g = (g + g.T) / 2
