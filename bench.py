@@ -64,27 +64,76 @@ def dist_env():
 # clocks
 # ----------------------------------------------------------------------------------------------
 class ClockSampler(object):
+    """SM clock and throttle reasons sampled DURING the timed region: an in-process NVML thread (a sample every
+    ~2 ms), or `nvidia-smi -lms 20` when the NVML binding is unavailable."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
+    REASONS = (("hw_slowdown", 0x8), ("sw_thermal_slowdown", 0x20), ("hw_thermal_slowdown", 0x40),
+               ("sw_power_cap", 0x4))
 
     def __init__(self, gpu_index):
         self.gpu = gpu_index
         self.proc = None
         self.path = None
+        self.thread = None
+        self.samples = []
+        self.mask = 0
+        self.max_mhz = None
+        self._stop = False
+
+    def _nvml_loop(self, nv, handle):
+        while not self._stop:
+            try:
+                self.samples.append(float(nv.nvmlDeviceGetClockInfo(handle, nv.NVML_CLOCK_SM)))
+                try:
+                    self.mask |= int(nv.nvmlDeviceGetCurrentClocksEventReasons(handle))
+                except Exception:
+                    self.mask |= int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(handle))
+            except Exception:
+                break
+            time.sleep(0.002)
 
     def start(self):
+        try:
+            import pynvml as nv
+            import threading
+            nv.nvmlInit()
+            # NVML enumerates physical GPUs; honour CUDA_VISIBLE_DEVICES if it remaps them
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = self.gpu
+            if vis:
+                ids = [v.strip() for v in vis.split(",") if v.strip()]
+                if self.gpu < len(ids) and ids[self.gpu].isdigit():
+                    phys = int(ids[self.gpu])
+            handle = nv.nvmlDeviceGetHandleByIndex(phys)
+            self.max_mhz = float(nv.nvmlDeviceGetMaxClockInfo(handle, nv.NVML_CLOCK_SM))
+            self.thread = threading.Thread(target=self._nvml_loop, args=(nv, handle), daemon=True)
+            self.thread.start()
+            return
+        except Exception:
+            self.thread = None
         try:
             fd, self.path = tempfile.mkstemp(suffix=".csv")
             os.close(fd)
             self.proc = subprocess.Popen(
-                ["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "100"],
+                ["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "20"],
                 stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
         except Exception:
             self.proc = None
 
     def stop(self):
         out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        if self.thread is not None:
+            self._stop = True
+            self.thread.join(timeout=2)
+            if self.samples:
+                out["sm_mhz"] = float(np.median(self.samples))
+                out["sm_max_mhz"] = self.max_mhz
+                out["samples"] = len(self.samples)
+                out["source"] = "nvml"
+            out["reasons"] = sorted(n for n, bit in self.REASONS if self.mask & bit)
+            return out
         if self.proc is None:
             return out
         try:
@@ -100,6 +149,7 @@ class ClockSampler(object):
                 out["sm_mhz"] = float(np.median(sm))
                 out["sm_max_mhz"] = float(max(mx))
                 out["samples"] = len(sm)
+                out["source"] = "nvidia-smi"
             names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
             seen = set()
             for r in rows:
