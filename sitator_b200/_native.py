@@ -36,6 +36,7 @@ class Status(C.Structure):
         ("zero_error", C.c_int32), ("zero_index", C.c_int32), ("zero_frame", C.c_int64),
         ("n_zero_rows", C.c_uint64), ("n_duplicate_nearest", C.c_uint64),
         ("n_list_overflow", C.c_uint64), ("nnz", C.c_uint64), ("n_screen_rejects", C.c_uint64),
+        ("n_full_walk_frames", C.c_uint64),
     ]
 
 
@@ -47,6 +48,8 @@ SIGNATURES = {
     "sitb_create": (C.c_int, [C.POINTER(NetworkDesc), C.c_int, C.POINTER(_P)]),
     "sitb_destroy": (None, [_P]),
     "sitb_set_stream": (C.c_int, [_P, _P]),
+    "sitb_set_candidate_grid": (C.c_int, [_P, C.c_double]),
+    "sitb_candidate_grid_info": (C.c_int, [_P, C.POINTER(C.c_int32), C.POINTER(C.c_double), C.POINTER(C.c_uint64)]),
     "sitb_device_info": (C.c_int, [_P, C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
     "sitb_get_tables": (C.c_int, [_P, _P, _P]),
     "sitb_upload_frames": (C.c_int, [_P, _P, C.c_int64, C.c_int64]),

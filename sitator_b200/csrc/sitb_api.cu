@@ -6,6 +6,8 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <cstdlib>
+#include <algorithm>
 #include <new>
 #include <vector>
 
@@ -15,6 +17,9 @@ cudaError_t launch_tables(const Cell& cell, const double* centers, const double*
 void build_landmark_tables(const Cell& cell, int L, int V, int Lpad, int NB, int S, double steep_log2e,
                            const int* verts_in, const double* ideal, const double* svd, const double* q,
                            HostTables& out);
+cudaError_t launch_grid_lists(const Cell& cell, const double* ideal, const ushort4* va, const double* q64, int L,
+                              int Lpad, int NB, int S, int gx, int gy, int gz, double margin, const unsigned* ptr,
+                              unsigned* count, uint16_t* list, cudaStream_t stream);
 }
 
 using namespace sitb;
@@ -74,6 +79,12 @@ struct sitb_ctx {
     double* d_q64 = nullptr;
     double* d_acoef = nullptr;
     uint8_t* d_nverts = nullptr;
+    // candidate grid (orthorhombic cells)
+    unsigned* d_grid_ptr = nullptr;
+    uint16_t* d_grid_list = nullptr;
+    int gx = 0, gy = 0, gz = 0;
+    double grid_margin = 0.0;
+    unsigned long long grid_entries = 0;
     // centres
     int* d_cid = nullptr;
     double* d_cw = nullptr;
@@ -105,6 +116,7 @@ static void free_ctx(sitb_ctx* c) {
     for (cudaEvent_t ev : c->up_events) cudaEventDestroy(ev);
     pool_free(c->d_static_idx, c->stream); pool_free(c->d_mobile_idx, c->stream); pool_free(c->d_ideal, c->stream); pool_free(c->d_centers, c->stream);
     pool_free(c->d_chunk_atoms, c->stream); pool_free(c->d_chunk_bound, c->stream);
+    pool_free(c->d_grid_ptr, c->stream); pool_free(c->d_grid_list, c->stream);
     pool_free(c->d_verts_in, c->stream); pool_free(c->d_svd, c->stream); pool_free(c->d_qorig, c->stream); pool_free(c->d_orig_of, c->stream); pool_free(c->d_v0, c->stream); pool_free(c->d_b0, c->stream); pool_free(c->d_va, c->stream); pool_free(c->d_ba, c->stream);
     pool_free(c->d_q64, c->stream); pool_free(c->d_acoef, c->stream); pool_free(c->d_nverts, c->stream); pool_free(c->d_cid, c->stream); pool_free(c->d_cw, c->stream); pool_free(c->d_cid_orig, c->stream); pool_free(c->d_cw_orig, c->stream); pool_free(c->d_frames_owned, c->stream); pool_free(c->d_status, c->stream);
     delete c;
@@ -118,6 +130,9 @@ static cudaError_t upload(T** dst, const T* src, size_t n, cudaStream_t st) {
     if (e == cudaSuccess) e = cudaStreamSynchronize(st);      // src may be a temporary
     return e;
 }
+
+static int build_grid(sitb_ctx* c, double margin);
+extern "C" int sitb_reset_status(sitb_ctx* c);
 
 extern "C" const char* sitb_last_error(void) { return g_err; }
 extern "C" int sitb_version(void) { return 100; }
@@ -243,7 +258,74 @@ extern "C" int sitb_create(const sitb_network_desc* d, int device, sitb_ctx** ou
 #undef CKC
     *out = c;
     int rc = sitb_reset_status(c);
+    if (rc == SITB_OK) {
+        // default margin 0.5 A (thermal displacements of a static lattice are a few tenths of an Angstrom);
+        // SITB_GRID_MARGIN overrides it, <= 0 disables the grid
+        double margin = 0.5;
+        if (const char* env = getenv("SITB_GRID_MARGIN")) margin = atof(env);
+        rc = build_grid(c, margin);
+    }
     if (rc != SITB_OK) { free_ctx(c); *out = nullptr; return rc; }
+    return SITB_OK;
+}
+
+// (Re)build the candidate grid for a static-atom margin (Angstrom); margin <= 0 or a triclinic cell: no grid.
+static int build_grid(sitb_ctx* c, double margin) {
+    CK(cudaSetDevice(c->device));
+    CK(cudaStreamSynchronize(c->stream));
+    pool_free(c->d_grid_ptr, c->stream); pool_free(c->d_grid_list, c->stream);
+    c->d_grid_ptr = nullptr; c->d_grid_list = nullptr; c->gx = c->gy = c->gz = 0; c->grid_margin = 0.0; c->grid_entries = 0;
+    if (!(margin > 0.0) || !c->cell.diag) return SITB_OK;
+    const double len[3] = {std::fabs(c->cell.c[0]), std::fabs(c->cell.c[4]), std::fabs(c->cell.c[8])};
+    if (c->cell.c[0] <= 0.0 || c->cell.c[4] <= 0.0 || c->cell.c[8] <= 0.0) return SITB_OK;
+    // boxes of ~0.8 A (about a quarter of a cut-off radius), at most 64 per axis and ~2e8 (box, landmark) tests
+    double side = 0.8;
+    int g[3];
+    for (;;) {
+        double cells = 1.0;
+        for (int d = 0; d < 3; ++d) {
+            int n = (int)std::floor(len[d] / side + 0.5);
+            g[d] = n < 1 ? 1 : (n > 64 ? 64 : n);
+            cells *= g[d];
+        }
+        if (cells * (double)c->L <= 2.0e8 || (g[0] == 1 && g[1] == 1 && g[2] == 1)) break;
+        side *= 1.26;
+    }
+    const size_t cells = (size_t)g[0] * g[1] * g[2];
+    // margin: the caller's bound on static displacements + the float rounding of the box lookup in K1
+    const double lmax = std::max(len[0], std::max(len[1], len[2]));
+    const double eps = 1e-5 * lmax + 1e-9;
+    unsigned* d_count = nullptr;
+    CK(pool_alloc((void**)&d_count, sizeof(unsigned) * cells, c->stream));
+    cudaError_t e = launch_grid_lists(c->cell, c->d_ideal, c->d_va, c->d_q64, c->L, c->Lpad, c->NB, c->S, g[0], g[1], g[2],
+                                      margin + eps, nullptr, d_count, nullptr, c->stream);
+    std::vector<unsigned> ptr(cells + 1, 0u);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(ptr.data() + 1, d_count, sizeof(unsigned) * cells, cudaMemcpyDeviceToHost, c->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+    pool_free(d_count, c->stream);
+    if (e != cudaSuccess) return fail(SITB_E_CUDA, "candidate grid (count): %s", cudaGetErrorString(e));
+    unsigned long long total = 0;
+    for (size_t i = 1; i <= cells; ++i) { total += ptr[i]; ptr[i] = (unsigned)total; }
+    if (total >= 0xFFFFFFFFull) return SITB_OK;              // absurdly large: keep the full walk
+    CK(upload(&c->d_grid_ptr, ptr.data(), cells + 1, c->stream));
+    CK(pool_alloc((void**)&c->d_grid_list, sizeof(uint16_t) * (size_t)(total ? total : 1), c->stream));
+    CK(launch_grid_lists(c->cell, c->d_ideal, c->d_va, c->d_q64, c->L, c->Lpad, c->NB, c->S, g[0], g[1], g[2], margin + eps,
+                         c->d_grid_ptr, nullptr, c->d_grid_list, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    c->gx = g[0]; c->gy = g[1]; c->gz = g[2]; c->grid_margin = margin; c->grid_entries = total;
+    return SITB_OK;
+}
+
+extern "C" int sitb_set_candidate_grid(sitb_ctx* c, double static_margin) {
+    if (!c) return fail(SITB_E_INVALID, "null context");
+    return build_grid(c, static_margin);
+}
+
+extern "C" int sitb_candidate_grid_info(sitb_ctx* c, int32_t* dims, double* static_margin, uint64_t* n_entries) {
+    if (!c) return fail(SITB_E_INVALID, "null context");
+    if (dims) { dims[0] = c->gx; dims[1] = c->gy; dims[2] = c->gz; }
+    if (static_margin) *static_margin = c->grid_margin;
+    if (n_entries) *n_entries = c->grid_entries;
     return SITB_OK;
 }
 
@@ -371,6 +453,7 @@ extern "C" int sitb_get_status(sitb_ctx* c, sitb_status* out) {
     out->n_list_overflow = h[2 + CNT_LIST_OVERFLOW];
     out->nnz = h[2 + CNT_NNZ];
     out->n_screen_rejects = h[2 + CNT_SCREEN_REJECT];
+    out->n_full_walk_frames = h[2 + CNT_FULL_WALK_FRAMES];
     return SITB_OK;
 }
 
@@ -398,6 +481,8 @@ static int base_params(sitb_ctx* c, int64_t begin, int64_t n, FillParams& p, con
     p.tab.q64 = c->d_q64; p.tab.acoef = c->d_acoef; p.tab.nverts = c->d_nverts; p.tab.orig_of = c->d_orig_of;
     p.tab.chunk_atoms = c->d_chunk_atoms; p.tab.chunk_bound = c->d_chunk_bound;
     p.bcoef = c->bcoef; p.static_thr = c->static_thr; p.dynamic = c->dynamic; p.relaxed = c->relaxed;
+    p.grid_ptr = c->d_grid_ptr; p.grid_list = c->d_grid_list; p.gx = c->gx; p.gy = c->gy; p.gz = c->gz;
+    p.grid_margin_sq = c->grid_margin * c->grid_margin;
     p.errkey = c->d_status; p.counters = c->d_status + 2;
     p.cid = c->d_cid; p.cw = c->d_cw; p.n_clusters = c->n_clusters;
     return SITB_OK;

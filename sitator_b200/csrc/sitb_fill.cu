@@ -36,7 +36,7 @@ namespace sitb {
 struct SmemLayout {
     int Spad, Mpad, qstride;
     size_t off_ss, off_sm, off_ba, off_b0, off_fs, off_fm, off_wqf, off_wev, off_hist, off_lmap, off_seen,
-        off_cw, off_va, off_v0, off_cid, off_wcand, off_wek, off_task, off_ca, off_cb, total;
+        off_cw, off_va, off_v0, off_cid, off_wcand, off_wek, off_task, off_flag, off_ca, off_cb, total;
 };
 
 __host__ __device__ inline SmemLayout make_layout(int S, int M, int L, int Lpad, int NB, int warps, int fb, int mode,
@@ -71,6 +71,7 @@ __host__ __device__ inline SmemLayout make_layout(int S, int M, int L, int Lpad,
     l.off_wek = o;   o += sizeof(uint16_t) * (size_t)warps * ENTRY_CAP;
     o = (o + 3) & ~(size_t)3;
     l.off_task = o;  o += sizeof(int);
+    l.off_flag = o;  o += sizeof(int) * (size_t)fb;
     l.total = (o + 15) & ~(size_t)15;
     return l;
 }
@@ -133,6 +134,7 @@ __global__ void __launch_bounds__(DIAG ? 1024 : 512) k_fill(const __grid_constan
     uint16_t* cand = (uint16_t*)(smem_raw + lay.off_wcand) + (size_t)warp * CAND_CAP;
     uint16_t* ek = (uint16_t*)(smem_raw + lay.off_wek) + (size_t)warp * ENTRY_CAP;
     int* task_counter = (int*)(smem_raw + lay.off_task);
+    int* full_walk = (int*)(smem_raw + lay.off_flag);      // [FB] frame has a static atom beyond the grid margin
     ushort4* tca = (ushort4*)(smem_raw + lay.off_ca);       // [Lpad/32] chunk skip table: atoms
     float4* tcb = (float4*)(smem_raw + lay.off_cb);         // [Lpad/32] chunk skip table: bounds
 
@@ -161,7 +163,8 @@ __global__ void __launch_bounds__(DIAG ? 1024 : 512) k_fill(const __grid_constan
     if (lane == 0) qfw[S] = 0.f;                            // dummy vertex: passes every screen
     __syncthreads();
 
-    unsigned long long loc_zero = 0, loc_nnz = 0, loc_rej = 0, loc_over = 0, loc_dup = 0;
+    unsigned long long loc_zero = 0, loc_nnz = 0, loc_rej = 0, loc_over = 0, loc_dup = 0, loc_full = 0;
+    const bool have_grid = DIAG && p.grid_ptr != nullptr;
     const Cell& cell = p.cell;
     const float Lx = (float)cell.c[0], Ly = (float)cell.c[4], Lz = (float)cell.c[8];
     const int W = 4 * NB;
@@ -195,6 +198,7 @@ __global__ void __launch_bounds__(DIAG ? 1024 : 512) k_fill(const __grid_constan
         if (p.dynamic)
             for (int t = threadIdx.x; t < nb * Spad; t += blockDim.x) seen_all[t] = 0u;
         if (threadIdx.x == 0) *task_counter = 0;
+        if (threadIdx.x < FB) full_walk[threadIdx.x] = have_grid ? 0 : 1;
         __syncthreads();
 
         // ---- 2. static lattice (helpers.pyx:55-92) ---------------------------------------
@@ -209,6 +213,7 @@ __global__ void __launch_bounds__(DIAG ? 1024 : 512) k_fill(const __grid_constan
                 const double q = shifted_dist2<DIAG, false>(cell, pt[0], pt[1], pt[2], ox, oy, oz);
                 if (__dsqrt_rn(q) > p.static_thr)
                     atomicMin(p.errkey, make_error_key(gframe, PHASE_STATIC_MOVED, (unsigned)s));
+                if (q > p.grid_margin_sq) full_walk[b] = 1;
             }
         } else {
             for (int t = warp; t < nb * S; t += nwarps) {
@@ -233,6 +238,7 @@ __global__ void __launch_bounds__(DIAG ? 1024 : 512) k_fill(const __grid_constan
                 if (lane == 0) {
                     atomicAdd(&seen_all[(size_t)b * Spad + bj], 1u);
                     lmap_all[(size_t)b * Spad + li] = (unsigned)bj;
+                    if (__dmul_rn(bd, bd) > p.grid_margin_sq) full_walk[b] = 1;
                     if (bd > p.static_thr)
                         atomicMin(p.errkey, make_error_key(gframe, PHASE_STATIC_MOVED, (unsigned)li));
                 }
@@ -249,6 +255,8 @@ __global__ void __launch_bounds__(DIAG ? 1024 : 512) k_fill(const __grid_constan
             }
         }
         __syncthreads();
+        if (threadIdx.x == 0)
+            for (int b = 0; b < nb; ++b) loc_full += (unsigned long long)full_walk[b];
 
         // ---- 3. one warp per mobile atom, claimed from a per-batch counter ------------------
         for (;;) {
@@ -256,8 +264,7 @@ __global__ void __launch_bounds__(DIAG ? 1024 : 512) k_fill(const __grid_constan
             if (lane == 0) jj = atomicAdd(task_counter, 1);
             jj = __shfl_sync(0xffffffffu, jj, 0);
             if (jj >= nb * M) break;
-            int b = 0, j = jj;
-            while (j >= M) { j -= M; ++b; }
+            const int b = jj / M, j = jj - b * M;
             const long long fl = p.frame_list ? p.frame_list[w0 + b] : (w0 + b);
             const long long gframe = p.frame0 + fl;
             const long long row_local = (w0 + b) * M + j;            // row in this launch's outputs
@@ -269,10 +276,11 @@ __global__ void __launch_bounds__(DIAG ? 1024 : 512) k_fill(const __grid_constan
             const double oz = __dsub_rn(cell.cen[2], sm[((size_t)b * M + j) * 3 + 2]);
 
             // 3a. screen distances static -> mobile (helpers.pyx:99-103, :174-178)
+            float mx = 0.f, my = 0.f, mz = 0.f;
             if (DIAG) {
                 const float* fsb = fs + (size_t)b * 3 * Spad;
                 const float* fmb = fm + (size_t)b * 3 * Mpad;
-                const float mx = fmb[j], my = fmb[Mpad + j], mz = fmb[2 * Mpad + j];
+                mx = fmb[j]; my = fmb[Mpad + j]; mz = fmb[2 * Mpad + j];
                 for (int s = lane; s < S; s += 32) {
                     const int src = p.dynamic ? (int)lmap[s] : s;
                     const float cx = centre_frac(fsb[src] - mx) * Lx;
@@ -300,6 +308,38 @@ __global__ void __launch_bounds__(DIAG ? 1024 : 512) k_fill(const __grid_constan
 
             int nsurv = 0, ncand = 0;
             const int n_chunks = Lpad >> 5;
+            if (DIAG && !full_walk[b]) {
+                // 3b'. candidates = the list of the grid box the mobile atom is in (sitb_tables.cu: k_grid_lists);
+                // every vertex of a candidate is screened at once (3c)
+                int ix = (int)(mx * (float)p.gx), iy = (int)(my * (float)p.gy), iz = (int)(mz * (float)p.gz);
+                ix = ix < 0 ? 0 : (ix >= p.gx ? p.gx - 1 : ix);
+                iy = iy < 0 ? 0 : (iy >= p.gy ? p.gy - 1 : iy);
+                iz = iz < 0 ? 0 : (iz >= p.gz ? p.gz - 1 : iz);
+                const int box = (ix * p.gy + iy) * p.gz + iz;
+                const unsigned beg = __ldg(p.grid_ptr + box), end = __ldg(p.grid_ptr + box + 1);
+                for (unsigned i0 = beg; i0 < end; i0 += 32) {
+                    const unsigned i = i0 + lane;
+                    bool ok = i < end;
+                    const int k = ok ? (int)__ldg(p.grid_list + i) : 0;
+                    if (ok) {
+                        const ushort4 vv = tva[k];
+                        const float4 bb = tba[k];
+                        ok = !(qfw[vv.x] > bb.x) && !(qfw[vv.y] > bb.y) && !(qfw[vv.z] > bb.z) && !(qfw[vv.w] > bb.w);
+                        for (int blk = 1; blk < NB && ok; ++blk) {
+                            const ushort4 v2 = tva[(size_t)blk * Lpad + k];
+                            const float4 b2 = tba[(size_t)blk * Lpad + k];
+                            ok = !(qfw[v2.x] > b2.x) && !(qfw[v2.y] > b2.y) && !(qfw[v2.z] > b2.z) && !(qfw[v2.w] > b2.w);
+                        }
+                    }
+                    const unsigned m = __ballot_sync(0xffffffffu, ok);
+                    if (ok) {
+                        const int q = nsurv + __popc(m & lanemask_lt());
+                        if (q < ENTRY_CAP) ek[q] = (uint16_t)k;
+                    }
+                    nsurv += __popc(m);
+                }
+                __syncwarp();
+            } else
             for (int c0 = 0; c0 < n_chunks; c0 += 32) {
                 // 3b. chunks of 32 landmarks (renumbered along a Morton curve of their first vertex): a lane
                 // tests one chunk -- is any of its (<= 4) first-vertex atoms within its loosest bound? --
@@ -522,6 +562,7 @@ __global__ void __launch_bounds__(DIAG ? 1024 : 512) k_fill(const __grid_constan
             if (loc_over) atomicAdd(&p.counters[CNT_LIST_OVERFLOW], loc_over);
             if (loc_rej) atomicAdd(&p.counters[CNT_SCREEN_REJECT], loc_rej);
             if (loc_dup) atomicAdd(&p.counters[CNT_DUP_NEAREST], loc_dup);
+            if (loc_full) atomicAdd(&p.counters[CNT_FULL_WALK_FRAMES], loc_full);
         }
     }
 }

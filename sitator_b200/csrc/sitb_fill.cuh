@@ -20,7 +20,7 @@ static constexpr int MAX_VERTS = 8;
 
 // counters[] slots
 enum : int { CNT_ZERO_ROWS = 0, CNT_DUP_NEAREST = 1, CNT_LIST_OVERFLOW = 2, CNT_NNZ = 3,
-             CNT_SCREEN_REJECT = 4, CNT_ROWS = 5, CNT_SLOTS = 8 };
+             CNT_SCREEN_REJECT = 4, CNT_ROWS = 5, CNT_FULL_WALK_FRAMES = 6, CNT_SLOTS = 8 };
 
 // Landmark tables (built by sitb_tables.cu).  Vertex ids index the static lattice; a missing
 // vertex (the reference's -1 padding) is the dummy id S, whose screen distance is 0 and whose
@@ -67,6 +67,13 @@ struct FillParams {
     double bcoef;                // steepness*midpoint
     double static_thr;           // static_movement_threshold
     int dynamic, relaxed;
+    // candidate lists per box of a gx*gy*gz grid over the (orthorhombic) cell (sitb_tables.cu: k_grid_lists); null: none.
+    // A frame whose static atoms all lie within sqrt(grid_margin_sq) of their ideal positions tests only the
+    // list of the box the mobile atom is in; other frames walk all landmarks.
+    const unsigned* grid_ptr;    // [gx*gy*gz + 1]
+    const uint16_t* grid_list;   // internal landmark ids, ascending within a box
+    int gx, gy, gz;
+    double grid_margin_sq;
     unsigned long long* errkey;  // [2] atomicMin of make_error_key: [0] lattice errors, [1] zero landmark vectors
     unsigned long long* counters;
     // MODE_DENSE

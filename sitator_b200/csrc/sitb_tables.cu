@@ -68,6 +68,70 @@ cudaError_t launch_tables(const Cell& cell, const double* centers, const double*
     return cudaGetLastError();
 }
 
+// ---- cell grid of candidate landmarks (orthorhombic cells) ---------------------------------------
+// A landmark's component is non-zero only if the mobile atom lies within R_h = sqrt(Q_h) of every vertex
+// atom (helpers.pyx:197-203).  For a frame whose static atoms all sit within `margin` of their ideal
+// positions (measured anyway by the static-lattice check, helpers.pyx:57-67), that region is contained in
+// the intersection of the balls of radius R_h + margin about the IDEAL vertex positions (the per-axis
+// minimum-image metric of an orthorhombic cell obeys the triangle inequality).  The cell is cut into
+// gx*gy*gz boxes; a box lists every landmark whose balls all reach it.  K1 then tests only the list of the
+// box the mobile atom is in (~6 % of the landmarks at the LLZO shape) instead of walking all of them; a
+// frame with a static atom beyond the margin walks all landmarks as before.  One warp per box; lists
+// are in ascending internal landmark order, the same order the full walk produces.
+__global__ void k_grid_lists(Cell cell, const double* __restrict__ ideal, const ushort4* __restrict__ va,
+                             const double* __restrict__ q64, int L, int Lpad, int NB, int S, int gx, int gy, int gz,
+                             double margin, const unsigned* __restrict__ ptr, unsigned* __restrict__ count,
+                             uint16_t* __restrict__ list) {
+    const int lane = threadIdx.x & 31;
+    const long long id = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (id >= (long long)gx * gy * gz) return;
+    const int iz = (int)(id % gz), iy = (int)((id / gz) % gy), ix = (int)(id / ((long long)gz * gy));
+    const double len[3] = {cell.c[0], cell.c[4], cell.c[8]};
+    const double half[3] = {0.5 * len[0] / gx, 0.5 * len[1] / gy, 0.5 * len[2] / gz};
+    const double mid[3] = {(2 * ix + 1) * half[0], (2 * iy + 1) * half[1], (2 * iz + 1) * half[2]};
+    const int W = 4 * NB;
+    const unsigned base = ptr ? ptr[id] : 0u;
+    unsigned n = 0;
+    for (int k0 = 0; k0 < L; k0 += 32) {
+        const int k = k0 + lane;
+        bool in = k < L;
+        for (int blk = 0; blk < NB && in; ++blk) {
+            const ushort4 vv = va[(size_t)blk * Lpad + k];
+            const unsigned vs[4] = {vv.x, vv.y, vv.z, vv.w};
+            for (int h = 0; h < 4 && in; ++h) {
+                if (vs[h] == (unsigned)S) continue;
+                const double Q = q64[(size_t)k * W + 4 * blk + h];
+                if (!(Q >= 0.0)) { in = false; break; }           // degenerate landmark: never non-zero
+                const double r = sqrt(Q) + margin;
+                double d2 = 0.0;
+                for (int d = 0; d < 3; ++d) {
+                    double f = cell.ci[4 * d] * ideal[3 * vs[h] + d];
+                    f -= floor(f);
+                    double x = f * len[d] - mid[d];
+                    x -= len[d] * rint(x / len[d]);
+                    const double a = fmax(fabs(x) - half[d], 0.0);
+                    d2 += a * a;
+                }
+                if (d2 > r * r) in = false;
+            }
+        }
+        const unsigned m = __ballot_sync(0xffffffffu, in);
+        if (ptr && in) list[base + n + __popc(m & lanemask_lt())] = (uint16_t)k;
+        n += __popc(m);
+    }
+    if (!ptr && lane == 0) count[id] = n;
+}
+
+cudaError_t launch_grid_lists(const Cell& cell, const double* ideal, const ushort4* va, const double* q64, int L,
+                              int Lpad, int NB, int S, int gx, int gy, int gz, double margin, const unsigned* ptr,
+                              unsigned* count, uint16_t* list, cudaStream_t stream) {
+    const long long cells = (long long)gx * gy * gz;
+    const int wpb = 8;
+    k_grid_lists<<<(unsigned)((cells + wpb - 1) / wpb), wpb * 32, 0, stream>>>(cell, ideal, va, q64, L, Lpad, NB, S, gx, gy,
+                                                                          gz, margin, ptr, count, list);
+    return cudaGetLastError();
+}
+
 // Float screen bound (sitb_fill.cu steps 3a-3c).  Orthorhombic cells: the screen distance is
 // computed in FP32 from float fractional coordinates as |(u - round(u)) * L|^2; each Cartesian
 // component is then off by at most ~1.8e-7 * L (two float conversions, one subtract, one

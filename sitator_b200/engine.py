@@ -33,6 +33,7 @@ class EngineStatus(object):
         self.n_list_overflow = int(s.n_list_overflow)
         self.nnz = int(s.nnz)
         self.n_screen_rejects = int(s.n_screen_rejects)
+        self.n_full_walk_frames = int(s.n_full_walk_frames)
 
     def first_error(self, check_for_zeros):
         """(code, frame, index) of the first error in the reference's iteration order, or None."""
@@ -60,7 +61,7 @@ def vertex_table(vertices):
 class LandmarkEngine(object):
     def __init__(self, cell, static_idx, mobile_idx, n_atoms, ideal_static, centers, vertices,
                  cutoff_midpoint=1.5, cutoff_steepness=30.0, static_movement_threshold=1.0,
-                 dynamic_lattice_mapping=False, relaxed_lattice_checks=False, device=None):
+                 dynamic_lattice_mapping=False, relaxed_lattice_checks=False, device=None, candidate_grid_margin=None):
         torch = _torch()
         if not torch.cuda.is_available():
             raise RuntimeError("sitator_b200 needs a CUDA device (B200, sm_100a); there is no CPU path")
@@ -110,6 +111,19 @@ class LandmarkEngine(object):
         _native.check(self._lib.sitb_device_info(self._ctx, C.byref(n_sms), C.byref(maj), C.byref(mnr)))
         self.n_sms, self.compute_capability = n_sms.value, (maj.value, mnr.value)
         self.use_current_stream()
+        if candidate_grid_margin is not None:
+            self.set_candidate_grid(candidate_grid_margin)
+
+    def set_candidate_grid(self, static_margin):
+        """Rebuild the fill kernel's candidate grid for static atoms within ``static_margin`` Angstrom of their
+        ideal positions (<= 0: none, every landmark is walked).  Results do not depend on it, speed does."""
+        _native.check(self._lib.sitb_set_candidate_grid(self._ctx, float(static_margin)))
+
+    def candidate_grid_info(self):
+        dims = (C.c_int32 * 3)()
+        margin, n = C.c_double(), C.c_uint64()
+        _native.check(self._lib.sitb_candidate_grid_info(self._ctx, dims, C.byref(margin), C.byref(n)))
+        return {"dims": tuple(dims), "static_margin": margin.value, "entries": n.value}
 
     @classmethod
     def from_site_network(cls, sn, **kw):

@@ -181,3 +181,39 @@ def test_assign_matches_oracle_predict():
     same = ~diff
     assert np.max(np.abs(confs[same] - want_c[same])) < U.CONF_ATOL
     assert np.array_equal(counts, np.bincount(labels[labels >= 0], minlength=C))
+
+
+@pytest.mark.parametrize("name,n_frames,dynamic", [("llzo", 200, False), ("lgps_dynamic", 60, True), ("toy_bcc", 200, False)])
+def test_candidate_grid_does_not_change_results(name, n_frames, dynamic):
+    """The grid of candidate lists (sitb_tables.cu: k_grid_lists) only prunes the landmark walk: rows, their
+    entry order and every statistic are identical with the grid, without it, and with a margin so small that
+    most frames fall back to the full walk."""
+    import torch
+    system, cfg = syn.make_config(name)
+    frames = system.trajectory(n_frames)
+    results = []
+    for margin in (0.5, 0.0, 0.08):
+        eng = U.engine_for(system, dynamic_lattice_mapping=dynamic, candidate_grid_margin=margin)
+        info = eng.candidate_grid_info()
+        assert (info["entries"] > 0) == (margin > 0)
+        eng.set_frames(frames)
+        eng.reset_status()
+        seen, gram, sp = eng.pass_stats_cached()
+        st = eng.status()
+        assert st.error_code == 0 and st.n_list_overflow == 0
+        ptr = sp.ptr.cpu().numpy().view(np.uint64)
+        off = (ptr >> np.uint64(8)).astype(np.int64)
+        cnt = (ptr & np.uint64(0xFF)).astype(np.int64)
+        k = sp.k.cpu().numpy().view(np.uint16)
+        v = sp.v.cpu().numpy()
+        rows = [(k[o:o + n].copy(), v[o:o + n].copy()) for o, n in zip(off, cnt)]
+        results.append((st, seen.cpu().numpy(), rows))
+    st_grid, st_none, st_tight = results[0][0], results[1][0], results[2][0]
+    assert st_grid.n_full_walk_frames == 0
+    assert st_none.n_full_walk_frames == n_frames
+    assert 0 < st_tight.n_full_walk_frames <= n_frames        # sigma_static = 0.05 A: most frames exceed 0.08 A
+    for st, seen, rows in results[1:]:
+        assert st.nnz == st_grid.nnz and st.n_zero_rows == st_grid.n_zero_rows
+        assert np.array_equal(seen, results[0][1])
+        for (k0, v0), (k1, v1) in zip(results[0][2], rows):
+            assert np.array_equal(k0, k1) and np.array_equal(v0, v1)
