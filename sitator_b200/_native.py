@@ -5,7 +5,8 @@ There is no fallback: if the library is missing or a call fails, an exception is
 import ctypes as C
 import os
 
-_LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "lib", "libsitator_b200.so")
+# SITB_LIB: developer override, to time an experimental build of the same ABI against the in-tree one
+_LIB_PATH = os.environ.get("SITB_LIB") or os.path.join(os.path.dirname(os.path.abspath(__file__)), "lib", "libsitator_b200.so")
 _lib = None
 
 

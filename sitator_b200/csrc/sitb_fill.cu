@@ -76,18 +76,64 @@ __host__ __device__ inline SmemLayout make_layout(int S, int M, int L, int Lpad,
     return l;
 }
 
-// (prod of (1 + exp(steep*(d/svd - mid))))^(-1/n): the landmark component (helpers.pyx:205-212) from
-// the product P of the logistic denominators.  Everything in double: values agree with the
-// reference's libm evaluation to ~1e-15, which is what its own argmax-over-rows decisions
-// (cluster/mcl.py:83) need -- near saturation neighbouring rows differ by ~1e-8 only.
-__device__ __forceinline__ double inv_root(double P, int nv) {
-    switch (nv) {
-        case 1: return 1.0 / P;
-        case 2: return rsqrt(P);
-        case 3: return rcbrt(P);
-        case 4: return rsqrt(sqrt(P));
-        default: return pow(P, -1.0 / (double)nv);
+// ---- float64 kernels of step 3d ------------------------------------------------------------------
+// The landmark component is (prod_h (1 + exp(steep*(d_h/svd_h - mid))))^(-1/n) (helpers.pyx:197-212).  It is
+// evaluated in double: the reference's own argmax-over-rows decisions (cluster/mcl.py:83) separate rows whose
+// components differ by ~1e-8 relative, and the parity tolerance is 1e-12.  The library exp/sqrt/cbrt carry
+// range checks, slow paths and 64-bit immediates (two moves per polynomial coefficient); the arguments here
+// have a known range, so the three functions are written out with their constants in the constant bank.
+// Each agrees with the correctly rounded result to ~1 ulp.
+__constant__ double c_exp[14] = {
+    1.4426950408889634074,        // [0] log2(e)
+    6755399441055744.0,           // [1] 1.5 * 2^52: adding it leaves rint(t) in the low word
+    -6.93147180369123816490e-01,  // [2] -ln2, high part (32 significant bits)
+    -1.90821492927058770002e-10,  // [3] -ln2, low part
+    // exp(r) = 1 + r + r^2 Q(r) on |r| <= ln2/2: Q = Chebyshev interpolant of degree 9 (max rel. error 1.6e-17)
+    2.510038549551032e-08, 2.7620088445409746e-07, 2.7557268459997064e-06, 2.4801521295954376e-05,
+    0.00019841269863053618, 0.0013888888917213717, 0.0083333333333300615, 0.041666666666624129,
+    0.16666666666666669, 0.50000000000000011};
+
+// exp(x) for |x| < 700 (no overflow / underflow handling)
+__device__ __forceinline__ double exp_bounded(double x) {
+    const double t = fma(x, c_exp[0], c_exp[1]);
+    const int n = __double2loint(t);
+    const double nf = t - c_exp[1];
+    double r = fma(nf, c_exp[2], x);
+    r = fma(nf, c_exp[3], r);
+    double q = c_exp[4];
+#pragma unroll
+    for (int i = 5; i < 14; ++i) q = fma(q, r, c_exp[i]);
+    q = fma(q * r, r, r);                 // r + r^2 Q(r)
+    q = q + 1.0;
+    return __hiloint2double(__double2hiint(q) + n * 1048576, __double2loint(q));
+}
+
+// sqrt(q) for 1e-30 < q < 1e30: float reciprocal-square-root seed, two coupled Newton steps, one correction
+__device__ __forceinline__ double sqrt_bounded(double q) {
+    const double y = (double)rsqrtf((float)q);
+    double g = q * y, h = 0.5 * y;
+    double r = fma(-g, h, 0.5);
+    g = fma(g, r, g); h = fma(h, r, h);
+    r = fma(-g, h, 0.5);
+    g = fma(g, r, g); h = fma(h, r, h);
+    return fma(fma(-g, g, q), h, g);
+}
+
+// P^(-1/n) for 1 <= P < 3e38, 1 <= n <= 8: float seed, two Newton steps on y^-n = P (same code for every n)
+__device__ __forceinline__ double inv_root(double P, int n) {
+    const float rn = __fdividef(1.0f, (float)n);     // approximate is enough: it only scales the Newton step
+    double y = (double)exp2f(-__log2f((float)P) * rn);
+    const double rnd = (double)rn;
+#pragma unroll
+    for (int it = 0; it < 2; ++it) {
+        const double y2 = y * y, y4 = y2 * y2;
+        double t = (n & 1) ? y : 1.0;
+        if (n & 2) t *= y2;
+        if (n & 4) t *= y4;
+        if (n & 8) t = y4 * y4;
+        y = fma(y * fma(-P, t, 1.0), rnd, y);
     }
+    return y;
 }
 
 // u - round(u) for |u| < 2^22, two adds
@@ -106,7 +152,10 @@ __device__ __forceinline__ int warp_incl_scan(int v, int lane) {
 }
 
 template <bool DIAG, int MODE>
-__global__ void __launch_bounds__(DIAG ? 1024 : 512) k_fill(const __grid_constant__ FillParams p, const int FB,
+#ifndef SITB_K1_WARPS
+#define SITB_K1_WARPS 32
+#endif
+__global__ void __launch_bounds__(DIAG ? SITB_K1_WARPS * 32 : 512) k_fill(const __grid_constant__ FillParams p, const int FB,
                                                             const __grid_constant__ SmemLayout lay) {
     // (the layout is computed by the host and read from the constant bank: under the 64-register cap
     // the compiler otherwise rebuilds these offsets inside the hot loops)
@@ -319,17 +368,16 @@ __global__ void __launch_bounds__(DIAG ? 1024 : 512) k_fill(const __grid_constan
                 const unsigned beg = __ldg(p.grid_ptr + box), end = __ldg(p.grid_ptr + box + 1);
                 for (unsigned i0 = beg; i0 < end; i0 += 32) {
                     const unsigned i = i0 + lane;
-                    bool ok = i < end;
-                    const int k = ok ? (int)__ldg(p.grid_list + i) : 0;
-                    if (ok) {
-                        const ushort4 vv = tva[k];
-                        const float4 bb = tba[k];
-                        ok = !(qfw[vv.x] > bb.x) && !(qfw[vv.y] > bb.y) && !(qfw[vv.z] > bb.z) && !(qfw[vv.w] > bb.w);
-                        for (int blk = 1; blk < NB && ok; ++blk) {
-                            const ushort4 v2 = tva[(size_t)blk * Lpad + k];
-                            const float4 b2 = tba[(size_t)blk * Lpad + k];
-                            ok = !(qfw[v2.x] > b2.x) && !(qfw[v2.y] > b2.y) && !(qfw[v2.z] > b2.z) && !(qfw[v2.w] > b2.w);
-                        }
+                    const bool in = i < end;
+                    const int k = in ? (int)__ldg(p.grid_list + i) : 0;
+                    const ushort4 vv = tva[k];
+                    const float4 bb = tba[k];
+                    // (no short-circuit: four independent gathers and compares, no branches)
+                    bool ok = in & !(qfw[vv.x] > bb.x) & !(qfw[vv.y] > bb.y) & !(qfw[vv.z] > bb.z) & !(qfw[vv.w] > bb.w);
+                    for (int blk = 1; blk < NB; ++blk) {
+                        const ushort4 v2 = tva[(size_t)blk * Lpad + k];
+                        const float4 b2 = tba[(size_t)blk * Lpad + k];
+                        ok = ok & !(qfw[v2.x] > b2.x) & !(qfw[v2.y] > b2.y) & !(qfw[v2.z] > b2.z) & !(qfw[v2.w] > b2.w);
                     }
                     const unsigned m = __ballot_sync(0xffffffffu, ok);
                     if (ok) {
@@ -398,12 +446,12 @@ __global__ void __launch_bounds__(DIAG ? 1024 : 512) k_fill(const __grid_constan
             int nent = 0;
             for (int i0 = 0; i0 < nsurv; i0 += 32) {
                 const int i = i0 + lane;
-                bool alive = i < nsurv;
-                const int k = alive ? (int)ek[i] : 0;
-                double val = 0.0;
-                if (alive) {
-                    double P = 1.0;
-                    int nv = 0;
+                const bool in = i < nsurv;
+                const int k = in ? (int)ek[i] : 0;
+                bool alive = in;
+                double P = 1.0;
+                int nv = 0;
+                if (in) {
                     for (int blk = 0; blk < NB; ++blk) {
                         const ushort4 vv = tva[(size_t)blk * Lpad + k];
                         const double2* q2 = (const double2*)(p.tab.q64 + (size_t)k * W + 4 * blk);
@@ -419,14 +467,14 @@ __global__ void __launch_bounds__(DIAG ? 1024 : 512) k_fill(const __grid_constan
                                 const double q = shifted_dist2<DIAG, true>(cell, sb[3 * src], sb[3 * src + 1], sb[3 * src + 2], ox, oy, oz);
                                 if (q > qs[h]) alive = false;                 // helpers.pyx:199-203, exact
                                 // 1 + exp(steep*(d/svd - mid))                 helpers.pyx:197,205
-                                P *= 1.0 + exp(fma(__dsqrt_rn(q), as[h], -p.bcoef));
+                                P *= 1.0 + exp_bounded(fmax(fma((q > 1e-30) ? sqrt_bounded(q) : 0.0, as[h], -p.bcoef), -700.0));
                                 ++nv;
                             }
                         }
                     }
-                    if (alive) val = inv_root(P, nv);                         // helpers.pyx:212
-                    else ++loc_rej;
+                    if (!alive) ++loc_rej;
                 }
+                const double val = inv_root(P, nv > 0 ? nv : 1);                // helpers.pyx:212
                 const unsigned m = __ballot_sync(0xffffffffu, alive);
                 if (alive) {
                     const int q = nent + __popc(m & lanemask_lt());
@@ -576,7 +624,7 @@ static cudaError_t launch_one(const FillParams& p, int n_sms, cudaStream_t strea
     // CTAs per SM x warps per CTA x frames per batch: maximise resident warps per SM within the
     // 227 KB of shared memory (tables are per CTA, lists per warp, frame buffers per batch); mobile
     // atoms are claimed dynamically inside a batch, so want >= 3 tasks per warp and batch
-    const int max_w = DIAG ? 32 : 16;
+    const int max_w = DIAG ? SITB_K1_WARPS : 16;
     int best_w = 0, best_fb = 1;
     size_t best_bytes = 0;
     double best_score = -1.0;
