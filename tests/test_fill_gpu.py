@@ -217,3 +217,43 @@ def test_candidate_grid_does_not_change_results(name, n_frames, dynamic):
         assert np.array_equal(seen, results[0][1])
         for (k0, v0), (k1, v1) in zip(results[0][2], rows):
             assert np.array_equal(k0, k1) and np.array_equal(v0, v1)
+
+
+def test_dense_lattice_with_far_reaching_landmarks():
+    """A dense lattice with far-reaching landmarks: dozens of static atoms inside every cut-off radius, long
+    candidate lists per grid box (the opposite regime of the LLZO-shaped cases)."""
+    import torch
+    from oracle import landmark_oracle as orc
+    from sitator_b200.engine import LandmarkEngine
+    rng = np.random.default_rng(11)
+    cell = np.diag([9.0, 10.0, 11.0])
+    n_static, n_mobile, n_landmarks, n_frames = 260, 5, 120, 6
+    static = rng.random((n_static, 3)) * np.diag(cell)
+    centers = rng.random((n_landmarks, 3)) * np.diag(cell)
+    pbc = orc.PBC(cell)
+    verts = []
+    for c in centers:
+        d = pbc.distances(c, static)
+        order = np.argsort(d, kind="stable")
+        nv = int(rng.integers(2, 5))
+        verts.append(sorted(int(x) for x in order[8:8 + nv]))      # far vertices: cut-off radius ~ 4-5 A
+    A = n_static + n_mobile
+    static_idx = np.arange(n_static)
+    mobile_idx = np.arange(n_static, A)
+    frames = np.empty((n_frames, A, 3))
+    frames[:, static_idx] = static[None] + rng.normal(0, 0.03, (n_frames, n_static, 3))
+    pick = rng.integers(0, n_landmarks, (n_frames, n_mobile))
+    frames[:, mobile_idx] = centers[pick] + rng.normal(0, 0.2, (n_frames, n_mobile, 3))
+    want, nzero, _ = orc.fill_landmark_vectors(cell, static, static_idx, mobile_idx, centers, verts, frames,
+                                               check_for_zeros=False)
+    # the premise: some mobile atom has more than 48 static atoms inside the loosest cut-off radius
+    svd_max = max(np.max(pbc.distances(c, static[v])) for c, v in zip(centers, verts))
+    reach = 1.8070080122325283 * svd_max
+    n_near = max(int(np.sum(pbc.distances(m, frames[f, static_idx]) < 0.8 * reach))
+                 for f in range(n_frames) for m in frames[f, mobile_idx])
+    assert n_near > 48, n_near
+    eng = LandmarkEngine(cell, static_idx, mobile_idx, A, static, centers, verts)
+    eng.set_frames(frames)
+    got = eng.fill_dense(dtype=torch.float64).cpu().numpy()
+    assert np.count_nonzero(want) > 100
+    _compare_lv(got, want)
