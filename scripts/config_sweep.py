@@ -1,0 +1,74 @@
+"""Developer tool: every BASELINE config shape on one GPU -- landmark-vector parity on a slice (NumPy oracle), the
+fused fill+assign pass timed with CUDA events, and a whole LandmarkAnalysis.run.  Writes gpurun_out/config_sweep.json."""
+import json, sys, time
+import numpy as np, torch
+sys.path.insert(0, ".")
+from sitator_b200 import synthetic as syn
+from sitator_b200.landmark import LandmarkAnalysis
+from tests import _util as U
+from oracle import landmark_oracle as orc
+
+CASES = [("toy_bcc", 2000), ("llzo", 20000), ("lgps_dynamic", 20000), ("laso", 4000)]
+if len(sys.argv) > 1:
+    CASES = [(a.split(":")[0], int(a.split(":")[1])) for a in sys.argv[1:]]
+out = []
+for name, F in CASES:
+    system, cfg = syn.make_config(name)
+    frames = system.trajectory(F)
+    dyn = bool(cfg["dynamic"])
+    rec = {"config": name, "frames": F, "n_static": system.n_static, "n_mobile": system.n_mobile,
+           "n_landmarks": system.n_landmarks, "dynamic_lattice_mapping": dyn}
+    # parity of the landmark vectors on the first frames
+    nchk = 3
+    want, nzero, _ = orc.fill_landmark_vectors(system.cell, system.static_pos, system.static_idx, system.mobile_idx,
+                                               system.lm_centers, system.lm_vertices, frames[:nchk], check_for_zeros=False,
+                                               dynamic_lattice_mapping=dyn)
+    eng = U.engine_for(system, dynamic_lattice_mapping=dyn)
+    eng.set_frames(frames)
+    got = eng.fill_dense(begin=0, n=nchk, dtype=torch.float64).cpu().numpy()
+    nz = want != 0
+    rec["lv_support_equal"] = bool(np.array_equal(got != 0, nz))
+    rec["lv_max_rel_err"] = float(np.max(np.abs(got[nz] - want[nz]) / want[nz])) if nz.any() else 0.0
+    rec["grid"] = eng.candidate_grid_info()
+    # fused fill + assign pass with plausible centres (landmarks within 2 A of a true site)
+    d = system.lm_centers[:, None, :] - system.site_pos[None, :, :]
+    d -= system.lengths * np.round(d / system.lengths)
+    dist = np.sqrt((d ** 2).sum(-1))
+    cid = np.where(dist.min(1) < 2.0, dist.argmin(1), -1).astype(np.int32)
+    eng.set_centers(cid, np.ones(system.n_landmarks), len(system.site_pos))
+    N = F * system.n_mobile
+    labels = torch.empty(N, dtype=torch.int64, device="cuda"); confs = torch.empty(N, dtype=torch.float64, device="cuda")
+    counts = torch.zeros(len(system.site_pos), dtype=torch.int64, device="cuda")
+    eng.reset_status()
+    ts = []
+    for it in range(4):
+        a = torch.cuda.Event(enable_timing=True); b = torch.cuda.Event(enable_timing=True)
+        a.record(); eng.pass_assign(0.7, labels=labels, confs=confs, counts=counts); b.record(); torch.cuda.synchronize()
+        ts.append(a.elapsed_time(b))
+    st = eng.status()
+    rec["assign_pass_ms"] = min(ts[1:])
+    rec["frame_atoms_per_s"] = F * system.n_total / min(ts[1:]) * 1e3
+    rec["nnz_per_row"] = st.nnz / (4.0 * N)
+    rec["full_walk_frames"] = st.n_full_walk_frames // 4
+    rec["list_overflow"] = st.n_list_overflow
+    eng.close()
+    # whole run
+    for rep in range(2):
+        kw = U.analysis_kwargs(cfg)
+        # long synthetic trajectories: three atoms meet on one LGPS site / LASO atoms stray from the 3000 kept landmarks;
+        # the reference would raise the same errors, so the sweep relaxes the two checks
+        kw["max_mobile_per_site"] = max(3, kw["max_mobile_per_site"])
+        kw["check_for_zero_landmarks"] = False
+        la = LandmarkAnalysis(clustering_algorithm="mcl", verbose=False, **kw)
+        t = time.perf_counter()
+        try:
+            st_ = la.run(syn.site_network_for(system), frames)
+            rec["run_ms"] = (time.perf_counter() - t) * 1e3
+            rec["n_sites"] = int(st_.site_network.n_sites)
+            rec["unassigned_frac"] = float(np.mean(st_.traj < 0))
+        except Exception as e:       # reported, not hidden
+            rec["run_error"] = "%s: %s" % (type(e).__name__, e)
+            break
+    print(json.dumps(rec)); sys.stdout.flush()
+    out.append(rec)
+json.dump(out, open("gpurun_out/config_sweep.json", "w"), indent=1)

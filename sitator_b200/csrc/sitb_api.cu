@@ -17,6 +17,9 @@ cudaError_t launch_tables(const Cell& cell, const double* centers, const double*
 void build_landmark_tables(const Cell& cell, int L, int V, int Lpad, int NB, int S, double steep_log2e,
                            const int* verts_in, const double* ideal, const double* svd, const double* q,
                            HostTables& out);
+cudaError_t launch_grid_static_lists(const Cell& cell, const double* ideal, const double* rmax, int S, int gx, int gy,
+                                     int gz, double margin, const unsigned* ptr, unsigned* count, uint16_t* list,
+                                     cudaStream_t stream);
 cudaError_t launch_grid_lists(const Cell& cell, const double* ideal, const ushort4* va, const double* q64, int L,
                               int Lpad, int NB, int S, int gx, int gy, int gz, double margin, const unsigned* ptr,
                               unsigned* count, uint16_t* list, cudaStream_t stream);
@@ -82,6 +85,10 @@ struct sitb_ctx {
     // candidate grid (orthorhombic cells)
     unsigned* d_grid_ptr = nullptr;
     uint16_t* d_grid_list = nullptr;
+    unsigned* d_grid_sptr = nullptr;
+    uint16_t* d_grid_slist = nullptr;
+    double* d_rmax = nullptr;
+    unsigned long long grid_static_entries = 0;
     int gx = 0, gy = 0, gz = 0;
     double grid_margin = 0.0;
     unsigned long long grid_entries = 0;
@@ -117,6 +124,7 @@ static void free_ctx(sitb_ctx* c) {
     pool_free(c->d_static_idx, c->stream); pool_free(c->d_mobile_idx, c->stream); pool_free(c->d_ideal, c->stream); pool_free(c->d_centers, c->stream);
     pool_free(c->d_chunk_atoms, c->stream); pool_free(c->d_chunk_bound, c->stream);
     pool_free(c->d_grid_ptr, c->stream); pool_free(c->d_grid_list, c->stream);
+    pool_free(c->d_grid_sptr, c->stream); pool_free(c->d_grid_slist, c->stream); pool_free(c->d_rmax, c->stream);
     pool_free(c->d_verts_in, c->stream); pool_free(c->d_svd, c->stream); pool_free(c->d_qorig, c->stream); pool_free(c->d_orig_of, c->stream); pool_free(c->d_v0, c->stream); pool_free(c->d_b0, c->stream); pool_free(c->d_va, c->stream); pool_free(c->d_ba, c->stream);
     pool_free(c->d_q64, c->stream); pool_free(c->d_acoef, c->stream); pool_free(c->d_nverts, c->stream); pool_free(c->d_cid, c->stream); pool_free(c->d_cw, c->stream); pool_free(c->d_cid_orig, c->stream); pool_free(c->d_cw_orig, c->stream); pool_free(c->d_frames_owned, c->stream); pool_free(c->d_status, c->stream);
     delete c;
@@ -244,6 +252,7 @@ extern "C" int sitb_create(const sitb_network_desc* d, int device, sitb_ctx** ou
                               d->host_ideal_static, c->h_svd.data(), c->h_qorig.data(), ht);
         CKC(upload(&c->d_chunk_atoms, ht.chunk_atoms.data(), ht.chunk_atoms.size(), c->stream));
         CKC(upload(&c->d_chunk_bound, ht.chunk_bound.data(), ht.chunk_bound.size(), c->stream));
+        CKC(upload(&c->d_rmax, ht.rmax.data(), ht.rmax.size(), c->stream));
         c->internal_of = ht.internal_of;
         CKC(upload(&c->d_v0, ht.v0.data(), ht.v0.size(), c->stream));
         CKC(upload(&c->d_b0, ht.b0.data(), ht.b0.size(), c->stream));
@@ -274,7 +283,9 @@ static int build_grid(sitb_ctx* c, double margin) {
     CK(cudaSetDevice(c->device));
     CK(cudaStreamSynchronize(c->stream));
     pool_free(c->d_grid_ptr, c->stream); pool_free(c->d_grid_list, c->stream);
-    c->d_grid_ptr = nullptr; c->d_grid_list = nullptr; c->gx = c->gy = c->gz = 0; c->grid_margin = 0.0; c->grid_entries = 0;
+    pool_free(c->d_grid_sptr, c->stream); pool_free(c->d_grid_slist, c->stream);
+    c->d_grid_ptr = nullptr; c->d_grid_list = nullptr; c->d_grid_sptr = nullptr; c->d_grid_slist = nullptr;
+    c->gx = c->gy = c->gz = 0; c->grid_margin = 0.0; c->grid_entries = 0; c->grid_static_entries = 0;
     if (!(margin > 0.0) || !c->cell.diag) return SITB_OK;
     const double len[3] = {std::fabs(c->cell.c[0]), std::fabs(c->cell.c[4]), std::fabs(c->cell.c[8])};
     if (c->cell.c[0] <= 0.0 || c->cell.c[4] <= 0.0 || c->cell.c[8] <= 0.0) return SITB_OK;
@@ -311,8 +322,28 @@ static int build_grid(sitb_ctx* c, double margin) {
     CK(pool_alloc((void**)&c->d_grid_list, sizeof(uint16_t) * (size_t)(total ? total : 1), c->stream));
     CK(launch_grid_lists(c->cell, c->d_ideal, c->d_va, c->d_q64, c->L, c->Lpad, c->NB, c->S, g[0], g[1], g[2], margin + eps,
                          c->d_grid_ptr, nullptr, c->d_grid_list, c->stream));
+    // the static-lattice sites of each box, same two passes
+    CK(pool_alloc((void**)&d_count, sizeof(unsigned) * cells, c->stream));
+    e = launch_grid_static_lists(c->cell, c->d_ideal, c->d_rmax, c->S, g[0], g[1], g[2], margin + eps, nullptr, d_count, nullptr,
+                                 c->stream);
+    std::vector<unsigned> sptr(cells + 1, 0u);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(sptr.data() + 1, d_count, sizeof(unsigned) * cells, cudaMemcpyDeviceToHost, c->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+    pool_free(d_count, c->stream);
+    if (e != cudaSuccess) return fail(SITB_E_CUDA, "candidate grid (static count): %s", cudaGetErrorString(e));
+    unsigned long long stotal = 0;
+    for (size_t i = 1; i <= cells; ++i) { stotal += sptr[i]; sptr[i] = (unsigned)stotal; }
+    if (stotal >= 0xFFFFFFFFull) {
+        pool_free(c->d_grid_ptr, c->stream); pool_free(c->d_grid_list, c->stream);
+        c->d_grid_ptr = nullptr; c->d_grid_list = nullptr;
+        return SITB_OK;
+    }
+    CK(upload(&c->d_grid_sptr, sptr.data(), cells + 1, c->stream));
+    CK(pool_alloc((void**)&c->d_grid_slist, sizeof(uint16_t) * (size_t)(stotal ? stotal : 1), c->stream));
+    CK(launch_grid_static_lists(c->cell, c->d_ideal, c->d_rmax, c->S, g[0], g[1], g[2], margin + eps, c->d_grid_sptr, nullptr,
+                                c->d_grid_slist, c->stream));
     CK(cudaStreamSynchronize(c->stream));
-    c->gx = g[0]; c->gy = g[1]; c->gz = g[2]; c->grid_margin = margin; c->grid_entries = total;
+    c->gx = g[0]; c->gy = g[1]; c->gz = g[2]; c->grid_margin = margin; c->grid_entries = total; c->grid_static_entries = stotal;
     return SITB_OK;
 }
 
@@ -481,6 +512,7 @@ static int base_params(sitb_ctx* c, int64_t begin, int64_t n, FillParams& p, con
     p.tab.q64 = c->d_q64; p.tab.acoef = c->d_acoef; p.tab.nverts = c->d_nverts; p.tab.orig_of = c->d_orig_of;
     p.tab.chunk_atoms = c->d_chunk_atoms; p.tab.chunk_bound = c->d_chunk_bound;
     p.bcoef = c->bcoef; p.static_thr = c->static_thr; p.dynamic = c->dynamic; p.relaxed = c->relaxed;
+    p.grid_sptr = c->d_grid_sptr; p.grid_slist = c->d_grid_slist;
     p.grid_ptr = c->d_grid_ptr; p.grid_list = c->d_grid_list; p.gx = c->gx; p.gy = c->gy; p.gz = c->gz;
     p.grid_margin_sq = c->grid_margin * c->grid_margin;
     p.errkey = c->d_status; p.counters = c->d_status + 2;

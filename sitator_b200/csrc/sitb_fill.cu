@@ -326,10 +326,28 @@ __global__ void __launch_bounds__(DIAG ? SITB_K1_WARPS * 32 : 512) k_fill(const 
 
             // 3a. screen distances static -> mobile (helpers.pyx:99-103, :174-178)
             float mx = 0.f, my = 0.f, mz = 0.f;
+            int box = 0;
             if (DIAG) {
                 const float* fsb = fs + (size_t)b * 3 * Spad;
                 const float* fmb = fm + (size_t)b * 3 * Mpad;
                 mx = fmb[j]; my = fmb[Mpad + j]; mz = fmb[2 * Mpad + j];
+                if (!full_walk[b]) {
+                    // the grid box of the mobile atom: only the static-lattice sites its candidate landmarks use
+                    int ix = (int)(mx * (float)p.gx), iy = (int)(my * (float)p.gy), iz = (int)(mz * (float)p.gz);
+                    ix = ix < 0 ? 0 : (ix >= p.gx ? p.gx - 1 : ix);
+                    iy = iy < 0 ? 0 : (iy >= p.gy ? p.gy - 1 : iy);
+                    iz = iz < 0 ? 0 : (iz >= p.gz ? p.gz - 1 : iz);
+                    box = (ix * p.gy + iy) * p.gz + iz;
+                    const unsigned sbeg = __ldg(p.grid_sptr + box), send = __ldg(p.grid_sptr + box + 1);
+                    for (unsigned i = sbeg + lane; i < send; i += 32) {
+                        const int s = (int)__ldg(p.grid_slist + i);
+                        const int src = p.dynamic ? (int)lmap[s] : s;
+                        const float cx = centre_frac(fsb[src] - mx) * Lx;
+                        const float cy = centre_frac(fsb[Spad + src] - my) * Ly;
+                        const float cz = centre_frac(fsb[2 * Spad + src] - mz) * Lz;
+                        qfw[s] = fmaf(cz, cz, fmaf(cy, cy, cx * cx));
+                    }
+                } else
                 for (int s = lane; s < S; s += 32) {
                     const int src = p.dynamic ? (int)lmap[s] : s;
                     const float cx = centre_frac(fsb[src] - mx) * Lx;
@@ -360,11 +378,6 @@ __global__ void __launch_bounds__(DIAG ? SITB_K1_WARPS * 32 : 512) k_fill(const 
             if (DIAG && !full_walk[b]) {
                 // 3b'. candidates = the list of the grid box the mobile atom is in (sitb_tables.cu: k_grid_lists);
                 // every vertex of a candidate is screened at once (3c)
-                int ix = (int)(mx * (float)p.gx), iy = (int)(my * (float)p.gy), iz = (int)(mz * (float)p.gz);
-                ix = ix < 0 ? 0 : (ix >= p.gx ? p.gx - 1 : ix);
-                iy = iy < 0 ? 0 : (iy >= p.gy ? p.gy - 1 : iy);
-                iz = iz < 0 ? 0 : (iz >= p.gz ? p.gz - 1 : iz);
-                const int box = (ix * p.gy + iy) * p.gz + iz;
                 const unsigned beg = __ldg(p.grid_ptr + box), end = __ldg(p.grid_ptr + box + 1);
                 for (unsigned i0 = beg; i0 < end; i0 += 32) {
                     const unsigned i = i0 + lane;
@@ -630,7 +643,7 @@ static cudaError_t launch_one(const FillParams& p, int n_sms, cudaStream_t strea
     double best_score = -1.0;
     for (int ctas = 2; ctas >= 1; --ctas) {
         const size_t budget = (size_t)(227 * 1024) / ctas - 1024;
-        for (int w = max_w; w >= 1; w >>= 1) {
+        for (int w = max_w; w >= 1; --w) {
             if (w * ctas > 64) continue;
             int fb_fit = 0;
             size_t bytes_fit = 0;
@@ -643,7 +656,6 @@ static cudaError_t launch_one(const FillParams& p, int n_sms, cudaStream_t strea
             const double fill = (double)(fb_fit * p.M) / (3.0 * w);
             const double score = (double)(ctas * w) * (fill < 1.0 ? fill : 1.0) + 0.01 * ctas;
             if (score > best_score) { best_score = score; best_w = w; best_fb = fb_fit; best_bytes = bytes_fit; }
-            break;   // smaller CTAs of the same count only lose warps
         }
     }
     if (best_w == 0) return cudaErrorInvalidConfiguration;

@@ -50,6 +50,7 @@ struct HostTables {
     std::vector<uint16_t> orig_of;
     std::vector<ushort4> chunk_atoms;
     std::vector<float4> chunk_bound;
+    std::vector<double> rmax;       // [S] largest cut-off radius of any landmark vertex on the site (-1: none)
     std::vector<int> internal_of;   // [L] caller's index -> internal
 };
 
@@ -72,6 +73,8 @@ struct FillParams {
     // list of the box the mobile atom is in; other frames walk all landmarks.
     const unsigned* grid_ptr;    // [gx*gy*gz + 1]
     const uint16_t* grid_list;   // internal landmark ids, ascending within a box
+    const unsigned* grid_sptr;   // [gx*gy*gz + 1] the static-lattice sites those landmarks have as vertices
+    const uint16_t* grid_slist;
     int gx, gy, gz;
     double grid_margin_sq;
     unsigned long long* errkey;  // [2] atomicMin of make_error_key: [0] lattice errors, [1] zero landmark vectors

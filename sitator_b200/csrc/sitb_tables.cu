@@ -122,6 +122,58 @@ __global__ void k_grid_lists(Cell cell, const double* __restrict__ ideal, const 
     if (!ptr && lane == 0) count[id] = n;
 }
 
+// The same grid for the static atoms: a box lists every static-lattice site that is a vertex of one of the
+// box's candidate landmarks, i.e. lies within rmax[s] + margin of the box (rmax[s] = the largest cut-off
+// radius of any landmark vertex on s).  K1 then computes screen distances for those sites only.
+__global__ void k_grid_static_lists(Cell cell, const double* __restrict__ ideal, const double* __restrict__ rmax, int S,
+                                    int gx, int gy, int gz, double margin, const unsigned* __restrict__ ptr,
+                                    unsigned* __restrict__ count, uint16_t* __restrict__ list) {
+    const int lane = threadIdx.x & 31;
+    const long long id = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (id >= (long long)gx * gy * gz) return;
+    const int iz = (int)(id % gz), iy = (int)((id / gz) % gy), ix = (int)(id / ((long long)gz * gy));
+    const double len[3] = {cell.c[0], cell.c[4], cell.c[8]};
+    const double half[3] = {0.5 * len[0] / gx, 0.5 * len[1] / gy, 0.5 * len[2] / gz};
+    const double mid[3] = {(2 * ix + 1) * half[0], (2 * iy + 1) * half[1], (2 * iz + 1) * half[2]};
+    const unsigned base = ptr ? ptr[id] : 0u;
+    unsigned n = 0;
+    for (int s0 = 0; s0 < S; s0 += 32) {
+        const int s = s0 + lane;
+        bool in = s < S;
+        if (in) {
+            const double r = rmax[s];
+            if (!(r >= 0.0)) {
+                in = false;                                       // not a vertex of any landmark
+            } else {
+                double d2 = 0.0;
+                for (int d = 0; d < 3; ++d) {
+                    double f = cell.ci[4 * d] * ideal[3 * s + d];
+                    f -= floor(f);
+                    double x = f * len[d] - mid[d];
+                    x -= len[d] * rint(x / len[d]);
+                    const double a = fmax(fabs(x) - half[d], 0.0);
+                    d2 += a * a;
+                }
+                in = !(d2 > (r + margin) * (r + margin));
+            }
+        }
+        const unsigned m = __ballot_sync(0xffffffffu, in);
+        if (ptr && in) list[base + n + __popc(m & lanemask_lt())] = (uint16_t)s;
+        n += __popc(m);
+    }
+    if (!ptr && lane == 0) count[id] = n;
+}
+
+cudaError_t launch_grid_static_lists(const Cell& cell, const double* ideal, const double* rmax, int S, int gx, int gy,
+                                     int gz, double margin, const unsigned* ptr, unsigned* count, uint16_t* list,
+                                     cudaStream_t stream) {
+    const long long cells = (long long)gx * gy * gz;
+    const int wpb = 8;
+    k_grid_static_lists<<<(unsigned)((cells + wpb - 1) / wpb), wpb * 32, 0, stream>>>(cell, ideal, rmax, S, gx, gy, gz, margin,
+                                                                                 ptr, count, list);
+    return cudaGetLastError();
+}
+
 cudaError_t launch_grid_lists(const Cell& cell, const double* ideal, const ushort4* va, const double* q64, int L,
                               int Lpad, int NB, int S, int gx, int gy, int gz, double margin, const unsigned* ptr,
                               unsigned* count, uint16_t* list, cudaStream_t stream) {
@@ -225,6 +277,14 @@ void build_landmark_tables(const Cell& cell, int L, int V, int Lpad, int NB, int
             out.ba[(size_t)blk * Lpad + ki] = make_float4(bs[4 * blk], bs[4 * blk + 1], bs[4 * blk + 2], bs[4 * blk + 3]);
         }
     }
+    // per static-lattice site: the largest cut-off radius of any landmark vertex on it (-1: not a vertex)
+    out.rmax.assign((size_t)S, -1.0);
+    for (int k = 0; k < L; ++k)
+        for (int h = 0; h < nv[k]; ++h) {
+            const int v = verts_in[(size_t)k * V + h];
+            const double Q = q[(size_t)k * V + h];
+            if (Q >= 0.0 && std::sqrt(Q) > out.rmax[v]) out.rmax[v] = std::sqrt(Q);
+        }
     // chunk skip table: per 32 consecutive landmarks, the (up to 4) distinct first-vertex atoms and, per
     // atom, the loosest first-vertex bound among the chunk's landmarks that use it.  A chunk whose atoms
     // all lie beyond their bound holds no candidate.  More than 4 distinct atoms: never skipped.
