@@ -158,6 +158,31 @@ int sitb_pass_assign(sitb_ctx* ctx, int64_t frame_begin, int64_t n, double thres
                      double* dev_confs, uint64_t* dev_counts, uint64_t* dev_best, double* dev_rep,
                      double* dev_rep_w, uint64_t* dev_site_best);
 
+/* ---- the "dotprod" clustering plugin (landmark/cluster/dotprod.py:11-33), over rows cached by
+ * sitb_pass_stats_cached ----
+ * sitb_dotprod_fit: the first (and only long) iteration of DotProdClassifier.fit_centers
+ *   (util/DotProdClassifier.pyx:228-289): the rows, IN ORDER, join the centre of highest cosine similarity when it
+ *   reaches threshold, else found a new centre.  State is returned in sum form: dev_sums [max_centers][L] (zeroed by
+ *   the caller) = sum of the member rows, dev_counts [max_centers] (zeroed) = members (all-zero rows count for
+ *   centre 0, as NumPy's arg-max of NaNs makes them), dev_norm2 [max_centers] = |sum|^2; centre = sum / count.
+ *   Scratch: dev_lists [L][list_cap] uint16, dev_list_len [L] uint16 (zeroed) = the centres non-zero at a landmark.
+ *   dev_out16 = {centres found, status (0 ok, 1 more than max_centers, 2 a landmark list is full: grow and rerun),
+ *   rows consumed, then diagnostics: SM cycles spent loading rows / flagging candidates / enumerating them / in
+ *   the dot products / committing, and the total number of candidates}.  The later iterations of fit_centers (:228 loop) act on the few hundred centres; the
+ *   caller runs them.
+ * sitb_dotprod_predict: DotProdClassifier.predict with predict_normed=True (:129-197) for dense, already
+ *   normalised centres dev_normed_centers [n_centers][L] plus, per landmark, the centres non-zero there (CSR:
+ *   dev_list_ptr [L+1], dev_list_centers ascending); dev_labels / dev_confs [n_rows], dev_counts [n_centers] +=. */
+int sitb_dotprod_limits(int32_t* max_centers, int32_t* max_row_entries);
+int sitb_dotprod_fit(int device, const uint64_t* dev_row_ptr, const uint16_t* dev_pool_k, const double* dev_pool_v,
+                     int64_t n_rows, int32_t n_landmarks, double threshold, int32_t max_centers, int32_t list_cap,
+                     double* dev_sums, int64_t* dev_counts, double* dev_norm2, uint16_t* dev_lists,
+                     uint16_t* dev_list_len, int64_t* dev_out16, void* cuda_stream);
+int sitb_dotprod_predict(int device, const uint64_t* dev_row_ptr, const uint16_t* dev_pool_k, const double* dev_pool_v,
+                         int64_t n_rows, int32_t n_landmarks, int32_t n_centers, const double* dev_normed_centers,
+                         const uint32_t* dev_list_ptr, const uint16_t* dev_list_centers, double threshold,
+                         int64_t* dev_labels, double* dev_confs, uint64_t* dev_counts, void* cuda_stream);
+
 /* cluster/mcl.py:54-59: cov = gram/n_rows, correlation graph clipped at 0 with unit self loops for
  * never-seen landmarks; dev_gram_upper is the [n][n] upper triangle written by sitb_pass_stats
  * (or the SYRK), dev_cov and dev_graph are full [n][n] float64 outputs. */

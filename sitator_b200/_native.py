@@ -65,6 +65,11 @@ SIGNATURES = {
     "sitb_assign_sparse": (C.c_int, [_P, _P, _P, _P, C.c_int64, C.c_int64, C.c_double] + [_P] * 7),
     "sitb_set_centers": (C.c_int, [_P, _P, _P, C.c_int32]),
     "sitb_pass_assign": (C.c_int, [_P, C.c_int64, C.c_int64, C.c_double] + [_P] * 7),
+    "sitb_dotprod_limits": (C.c_int, [C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
+    "sitb_dotprod_fit": (C.c_int, [C.c_int, _P, _P, _P, C.c_int64, C.c_int32, C.c_double, C.c_int32, C.c_int32,
+                                   _P, _P, _P, _P, _P, _P, _P]),
+    "sitb_dotprod_predict": (C.c_int, [C.c_int, _P, _P, _P, C.c_int64, C.c_int32, C.c_int32, _P, _P, _P, C.c_double,
+                                       _P, _P, _P, _P]),
     "sitb_landmark_graph": (C.c_int, [C.c_int, _P, C.c_int32, C.c_double, _P, _P, _P]),
     "sitb_markov_clustering": (C.c_int, [C.c_int, _P, C.c_int32, C.c_int32, C.c_double, C.c_double, C.c_int32, _P,
                                          C.POINTER(C.c_int32), C.POINTER(C.c_int32), _P]),

@@ -264,17 +264,19 @@ class LandmarkEngine(object):
                                                       C.c_void_p(stream)))
         return seen, gram
 
-    def pass_stats_cached(self, seen=None, gram=None, entries_per_row=40, gram_from_rows=None):
+    def pass_stats_cached(self, seen=None, gram=None, entries_per_row=40, gram_from_rows=None, want_gram=True):
         """Pass A that also caches every landmark vector compressed (SparseRows); grows the pool on overflow.
         ``gram_from_rows`` (default: whenever the shared-memory tables fit, L <= 8192): build the Gram from the
         cached rows per (atom, window of frames) instead of with one atomic per pair product inside K1."""
-        if gram_from_rows is None:
+        if not want_gram:                       # rows and seen counts only (the dotprod plugin)
+            gram_from_rows = True
+        elif gram_from_rows is None:
             gram_from_rows = self.L <= 8192
         torch = _torch()
         n_rows = self.n_frames * self.M
         if seen is None:
             seen = self._zeros((self.L,), torch.int64)
-        if gram is None:
+        if gram is None and want_gram:
             gram = self._zeros((self.L, self.L), torch.float64)
         while True:
             cap = int(n_rows * entries_per_row) + 1024
@@ -294,7 +296,9 @@ class LandmarkEngine(object):
             used = int(rows.cursor.item())
             if used <= cap:
                 seen.copy_(seen_try)
-                if gram_from_rows:
+                if not want_gram:
+                    pass
+                elif gram_from_rows:
                     _native.check(self._lib.sitb_gram_from_cached(self._ctx, self._ptr(rows.ptr), self._ptr(rows.k),
                                                                   self._ptr(rows.v), self.n_frames, self._ptr(gram)))
                 else:

@@ -180,10 +180,6 @@ class LandmarkAnalysis(object):
         if self.site_centers_method not in (self.SITE_CENTERS_REAL_WEIGHTED, self.SITE_CENTERS_REAL_UNWEIGHTED,
                                             self.SITE_CENTERS_REPRESENTATIVE_LANDMARK):
             raise ValueError("Invalid site centers method '%s'" % self.site_centers_method)
-        if self._cluster_algo == 'dotprod':
-            raise NotImplementedError(
-                "clustering_algorithm='dotprod' (the online clustering of DotProdClassifier.fit_centers) is not built "
-                "yet (SURVEY.md section 8f-1); use clustering_algorithm='mcl'. There is no CPU fallback.")
 
         n_frames = len(frames)
         logger.info("--- Running Landmark Analysis ---")
@@ -209,6 +205,8 @@ class LandmarkAnalysis(object):
         clustermod = importlib.import_module("sitator_b200.landmark.cluster." + self._cluster_algo)
         if hasattr(clustermod, "landmark_graph"):
             clustermod.landmark_graph(source)          # pass A runs the lattice / zero-vector checks
+        elif hasattr(clustermod, "first_pass"):
+            clustermod.first_pass(source)
         status = engine.status()
         self._raise_first_error(status, comm, engine)
         if status.n_list_overflow:

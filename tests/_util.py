@@ -58,6 +58,19 @@ GOLDEN_DIR = __import__("os").path.join(__import__("os").path.dirname(__import__
 GOLDEN_CASES = ["toy_bcc_300", "llzo_60", "lgps_dynamic_40"]
 
 
+DOTPROD_GOLDEN_CASES = ["toy_bcc_300_dotprod", "llzo_60_dotprod", "lgps_dynamic_40_dotprod"]
+
+
+def load_dotprod_golden(name):
+    """Outputs of the compiled reference with its default clustering_algorithm='dotprod' + the inputs."""
+    import ast
+    import os
+    g = dict(np.load(os.path.join(GOLDEN_DIR, name + ".npz"), allow_pickle=False))
+    system, cfg = syn.make_config(str(g["config"]))
+    frames = system.trajectory(int(g["n_frames"]), **ast.literal_eval(str(g["traj_kw"])))
+    return g, system, cfg, frames
+
+
 def load_golden(name):
     """Fixture written by tests/golden/make_golden.py (outputs of the compiled reference) + its inputs."""
     import ast

@@ -26,6 +26,38 @@ CASES = [
 ]
 
 
+DOTPROD_CASES = [
+    # the constructor-default clustering (landmark/cluster/dotprod.py), same inputs as the cases above
+    ("toy_bcc_300_dotprod", "toy_bcc", 300, {}),
+    ("llzo_60_dotprod", "llzo", 60, {}),
+    ("lgps_dynamic_40_dotprod", "lgps_dynamic", 40, {"swap_statics_at": 13}),
+]
+
+
+def run_dotprod_case(ref, name, config, n_frames, traj_kw):
+    system, cfg = syn.make_config(config)
+    frames = system.trajectory(n_frames, **traj_kw)
+    sn = syn.site_network_for(system, ref.SiteNetwork, ref.Atoms)
+    la = ref.LandmarkAnalysis(verbose=False, force_no_memmap=True,          # clustering_algorithm defaults to 'dotprod'
+                              dynamic_lattice_mapping=cfg["dynamic"],
+                              check_for_zero_landmarks=cfg.get("check_for_zero_landmarks", True),
+                              max_mobile_per_site=cfg.get("max_mobile_per_site", 1))
+    st = la.run(sn, frames)
+    lv = np.asarray(la.landmark_vectors)
+    zero_rows = ~lv.any(axis=1)
+    confs = st.confidences.copy()
+    confs.reshape(-1)[zero_rows] = 0.0
+    out_sn = st.site_network
+    np.savez_compressed(
+        os.path.join(HERE, name + ".npz"),
+        config=config, n_frames=n_frames, traj_kw=repr(traj_kw),
+        labels=st.traj, confs=confs, site_centers=np.asarray(out_sn.centers),
+        n_multiple_assignments=la.n_multiple_assignments, avg_mobile_per_site=la.avg_mobile_per_site,
+        jumps=np.asarray(list(st.jumps()), dtype=np.int64).reshape(-1, 4),
+    )
+    print("%s: %d frames, %d sites, %d unassigned" % (name, n_frames, out_sn.n_sites, int(np.sum(st.traj < 0))))
+
+
 def run_case(ref, name, config, n_frames, traj_kw):
     system, cfg = syn.make_config(config)
     frames = system.trajectory(n_frames, **traj_kw)
@@ -65,5 +97,10 @@ if __name__ == "__main__":
     if not build_ref.build(verbose=False):
         sys.exit("needs /root/reference to build oracle/_ref")
     ref = ref_loader.load()
-    for case in CASES:
-        run_case(ref, *case)
+    which = sys.argv[1:] or ["mcl", "dotprod"]
+    if "mcl" in which:
+        for case in CASES:
+            run_case(ref, *case)
+    if "dotprod" in which:
+        for case in DOTPROD_CASES:
+            run_dotprod_case(ref, *case)

@@ -36,6 +36,25 @@ def test_oracle_reproduces_reference_golden(name):
     assert np.array_equal(np.nan_to_num(ja["p_ij"], nan=-1.0), np.nan_to_num(g["p_ij"], nan=-1.0))
 
 
+@pytest.mark.parametrize("name", U.DOTPROD_GOLDEN_CASES)
+def test_oracle_dotprod_clustering_reproduces_reference_golden(name):
+    """The constructor-default clustering (DotProdClassifier.fit_centers / predict, landmark/cluster/dotprod.py)."""
+    g, system, cfg, frames = U.load_dotprod_golden(name)
+    kw = U.analysis_kwargs(cfg)
+    lv, n_zero, wrapped = orc.fill_landmark_vectors(
+        system.cell, system.static_pos, system.static_idx, system.mobile_idx, system.lm_centers, system.lm_vertices,
+        frames, check_for_zeros=kw["check_for_zero_landmarks"], dynamic_lattice_mapping=kw["dynamic_lattice_mapping"])
+    res = orc.do_landmark_clustering_dotprod(lv, {}, 0.01 / system.n_mobile)
+    labels = res["cluster-labels"].reshape(g["labels"].shape)
+    assert len(res["cluster-size"]) == len(g["site_centers"])
+    assert np.array_equal(labels, g["labels"])
+    assert np.max(np.abs(res["cluster-confs"].reshape(g["confs"].shape) - g["confs"])) < 1e-12
+    sc = orc.site_centers_real(orc.PBC(system.cell), wrapped[:, system.mobile_idx], labels,
+                               res["cluster-confs"].reshape(labels.shape), len(res["cluster-size"]), weighted=True)
+    assert np.max(np.abs(sc - g["site_centers"])) < 1e-11
+    assert np.array_equal(orc.jumps(labels), g["jumps"])
+
+
 def test_oracle_against_live_reference_if_built():
     from oracle import ref_loader
     if not ref_loader.available():
