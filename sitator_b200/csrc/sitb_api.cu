@@ -289,8 +289,9 @@ static int build_grid(sitb_ctx* c, double margin) {
     if (!(margin > 0.0) || !c->cell.diag) return SITB_OK;
     const double len[3] = {std::fabs(c->cell.c[0]), std::fabs(c->cell.c[4]), std::fabs(c->cell.c[8])};
     if (c->cell.c[0] <= 0.0 || c->cell.c[4] <= 0.0 || c->cell.c[8] <= 0.0) return SITB_OK;
-    // boxes of ~0.8 A (about a quarter of a cut-off radius), at most 64 per axis and ~2e8 (box, landmark) tests
-    double side = 0.8;
+    // boxes of ~0.5 A (a seventh of a cut-off radius), at most 64 per axis and ~2e8 (box, landmark) tests
+    double side = 0.5;
+    if (const char* env = getenv("SITB_GRID_BOX")) { const double v = atof(env); if (v > 0.05) side = v; }   // developer knob
     int g[3];
     for (;;) {
         double cells = 1.0;

@@ -638,13 +638,20 @@ static cudaError_t launch_one(const FillParams& p, int n_sms, cudaStream_t strea
     // 227 KB of shared memory (tables are per CTA, lists per warp, frame buffers per batch); mobile
     // atoms are claimed dynamically inside a batch, so want >= 3 tasks per warp and batch
     const int max_w = DIAG ? SITB_K1_WARPS : 16;
+    // resident warps are also bounded by the register file (64 K registers per SM, allocated per warp in units of
+    // 8 registers per thread)
+    cudaFuncAttributes fa;
+    cudaError_t e0 = cudaFuncGetAttributes(&fa, kern);
+    if (e0 != cudaSuccess) return e0;
+    const int regs = ((fa.numRegs > 0 ? fa.numRegs : 64) + 7) & ~7;
+    const int reg_warps = 65536 / (32 * regs);
     int best_w = 0, best_fb = 1;
     size_t best_bytes = 0;
     double best_score = -1.0;
     for (int ctas = 2; ctas >= 1; --ctas) {
         const size_t budget = (size_t)(227 * 1024) / ctas - 1024;
         for (int w = max_w; w >= 1; --w) {
-            if (w * ctas > 64) continue;
+            if (w * ctas > 64 || w * ctas > reg_warps) continue;
             int fb_fit = 0;
             size_t bytes_fit = 0;
             for (int fb = 1; fb <= 8; ++fb) {

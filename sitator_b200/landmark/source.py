@@ -34,7 +34,21 @@ class LandmarkVectorSource(object):
         global_rows = np.asarray(global_rows, dtype=np.int64)
         out = np.zeros((len(global_rows), eng.L), dtype=np.float64)
         local = (global_rows >= self.row0) & (global_rows < self.row0 + self.n_local)
-        if np.any(local):
+        if np.any(local) and self.sparse is not None:
+            # straight from the compressed cache: row_ptr -> (landmark, value) entries
+            lr = torch.as_tensor(global_rows[local] - self.row0, device=eng.device)
+            ptr = self.sparse.ptr.index_select(0, lr)
+            cnt = (ptr & 0xFF).cpu().numpy()
+            off = (ptr >> 8).cpu().numpy()
+            idx = np.concatenate([np.arange(o, o + c, dtype=np.int64) for o, c in zip(off, cnt)]) if len(off) else np.zeros(0, np.int64)
+            if len(idx):
+                idx_d = torch.as_tensor(idx, device=eng.device)
+                kk = self.sparse.k.index_select(0, idx_d).cpu().numpy().view(np.uint16).astype(np.int64)
+                vv = self.sparse.v.index_select(0, idx_d).cpu().numpy()
+                sub = np.zeros((int(local.sum()), eng.L), dtype=np.float64)
+                sub[np.repeat(np.arange(len(cnt)), cnt), kk] = vv
+                out[local] = sub
+        elif np.any(local):
             lr = global_rows[local] - self.row0
             frames = np.unique(lr // eng.M)
             dense = eng.fill_frames(frames, dtype=torch.float64)            # (len(frames) * M, L) on the device

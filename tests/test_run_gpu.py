@@ -157,5 +157,5 @@ def test_site_center_methods_and_errors():
         la.run(syn.site_network_for(system), frames)
     with pytest.raises(ValueError, match="Wrong shape"):
         LandmarkAnalysis(clustering_algorithm='mcl').run(syn.site_network_for(system), frames[:, :-1])
-    with pytest.raises(NotImplementedError):
+    with pytest.raises(ZeroLandmarkError):        # the default algorithm ('dotprod') runs the same checks first
         LandmarkAnalysis().run(syn.site_network_for(system), frames)
