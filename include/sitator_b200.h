@@ -167,8 +167,8 @@ int sitb_pass_assign(sitb_ctx* ctx, int64_t frame_begin, int64_t n, double thres
  *   centre 0, as NumPy's arg-max of NaNs makes them), dev_norm2 [max_centers] = |sum|^2; centre = sum / count.
  *   Scratch: dev_lists [L][list_cap] uint16, dev_list_len [L] uint16 (zeroed) = the centres non-zero at a landmark.
  *   dev_out16 = {centres found, status (0 ok, 1 more than max_centers, 2 a landmark list is full: grow and rerun),
- *   rows consumed, then diagnostics: SM cycles spent loading rows / flagging candidates / enumerating them / in
- *   the dot products / committing, and the total number of candidates}.  The later iterations of fit_centers (:228 loop) act on the few hundred centres; the
+ *   rows consumed, then diagnostics: SM cycles spent finding candidates / in the dot products / committing, and
+ *   the total number of candidates}.  The later iterations of fit_centers (:228 loop) act on the few hundred centres; the
  *   caller runs them.
  * sitb_dotprod_predict: DotProdClassifier.predict with predict_normed=True (:129-197) for dense, already
  *   normalised centres dev_normed_centers [n_centers][L] plus, per landmark, the centres non-zero there (CSR:

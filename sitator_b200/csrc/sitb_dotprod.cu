@@ -35,221 +35,234 @@ __device__ __forceinline__ double warp_sum(double x) {
 }
 
 // out[0] = number of centres, out[1] = status (0 ok, 1 more than max_c centres, 2 a landmark list is full),
-// out[2] = rows consumed
-__global__ void __launch_bounds__(32) k_dotprod_fit(const unsigned long long* __restrict__ row_ptr,
-                                                     const uint16_t* __restrict__ pk, const double* __restrict__ pv,
-                                                     long long n_rows, int L, double thr, int max_c, int cap,
-                                                     double* S, long long* cnt, double* nrm2, uint16_t* lists,
-                                                     uint16_t* llen, long long* out) {
-    __shared__ unsigned emask[DP_MAX_CENTERS];        // per centre: which entries of the current row it is non-zero at
+// out[2] = rows consumed, out[3..6] = SM cycles in the candidate / dot-product / commit phases and the number
+// of candidates (diagnostics).
+//
+// One CTA of DP_FIT_WARPS warps works on ONE row at a time (the rows are sequential by definition); what the
+// warps share out is the work inside the row, so that the row's critical path is a few short dependent steps
+// instead of one warp's long in-order instruction stream:
+//   1. candidates: warp w takes the row's entries w, w+8, ...; its lanes walk that landmark's centre list and
+//      flag the centres (first toucher appends the centre to the candidate array)
+//   2. dot products: warp w takes candidates w, w+8, ...; lane e gathers S_c[k_e] (all of a warp's candidates in
+//      flight before the first reduction), warp sum, one lane per candidate forms the cosine; best per warp
+//   3. warp 0 merges the warp bests (highest cosine, then lowest centre index = np.argmax), decides and commits;
+//      the other warps clear the flags and pull the next row's lists towards L1 meanwhile
+static constexpr int DP_FIT_WARPS = 8;
+static constexpr int DP_FIT_UNROLL = 4;               // candidates per warp and pass
+
+__global__ void __launch_bounds__(32 * DP_FIT_WARPS) k_dotprod_fit(
+    const unsigned long long* __restrict__ row_ptr, const uint16_t* __restrict__ pk, const double* __restrict__ pv,
+    long long n_rows, int L, double thr, int max_c, int cap, double* S, long long* cnt, double* nrm2,
+    uint16_t* lists, uint16_t* llen, long long* out) {
+    __shared__ unsigned flag[DP_MAX_CENTERS];         // centre is a candidate of the current row
     __shared__ double nrm2s[DP_MAX_CENTERS];          // |S_c|^2 (written back to nrm2 at the end)
-    __shared__ uint16_t cands[DP_MAX_CENTERS];        // candidate centres of the current row, ascending
-    __shared__ unsigned cmask[DP_MAX_CENTERS];        // and their entry masks
-    __shared__ uint16_t rk[32 * DP_ROW_CHUNKS];       // the current row, readable by every lane
-    __shared__ double rv[32 * DP_ROW_CHUNKS];
-    const int lane = threadIdx.x;
-    for (int i = lane; i < DP_MAX_CENTERS; i += 32) emask[i] = 0u;
+    __shared__ uint16_t cands[DP_MAX_CENTERS];        // candidate centres of the current row, in order of first touch
+    __shared__ int ncand_s, sh_C, sh_status;
+    __shared__ double wb_cos[DP_FIT_WARPS], wb_dot[DP_FIT_WARPS];
+    __shared__ int wb_c[DP_FIT_WARPS];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    for (int i = tid; i < DP_MAX_CENTERS; i += blockDim.x) flag[i] = 0u;
+    if (tid == 0) { ncand_s = 0; sh_C = 0; sh_status = 0; }
+    __syncthreads();
     int C = 0;
-    int status = 0;
     long long r = 0;
-    long long t_load = 0, t_flag = 0, t_enum = 0, t_dot = 0, t_commit = 0, n_cand = 0;
-    __syncwarp();
-    unsigned long long ptr_next = n_rows > 0 ? row_ptr[0] : 0ull;
-    int k_next = 0;
-    double v_next = 0.0;
-    if (n_rows > 0 && lane < (int)(ptr_next & 0xFF)) { k_next = pk[(ptr_next >> 8) + lane]; v_next = pv[(ptr_next >> 8) + lane]; }
+    long long t_cand = 0, t_dot = 0, t_commit = 0, n_cand = 0;
+    int k_next = 0;                                   // (last warp) first entries of the next row, for the list prefetch
     for (; r < n_rows; ++r) {
         long long tk = clock64();
 #define DP_TICK(acc) { const long long now_ = clock64(); acc += now_ - tk; tk = now_; }
-        const unsigned long long ptr = ptr_next;
+        const unsigned long long ptr = row_ptr[r];
         const int nnz = (int)(ptr & 0xFF);
         const int nch = (nnz + 31) >> 5;
         const unsigned long long off = ptr >> 8;
-        // one warp, in-order issue: a load only overlaps with what is issued before its first use, so everything
-        // the next rows need is requested early -- the pointer two rows ahead, the entries one row ahead
-        int kk[DP_ROW_CHUNKS];
-        double vv[DP_ROW_CHUNKS];
-        kk[0] = k_next; vv[0] = v_next;                         // first 32 entries: loaded while the previous row ran
-        double sq = (lane < nnz) ? vv[0] * vv[0] : 0.0;
-        if (r + 1 < n_rows) {
-            const unsigned long long np = row_ptr[r + 1];        // (its line was touched two rows ago)
-            ptr_next = np;
-            const unsigned long long no = np >> 8;
-            if (lane < (int)(np & 0xFF)) { k_next = pk[no + lane]; v_next = pv[no + lane]; }   // used one row later
+        unsigned long long ptr_n = 0ull;
+        if (warp == DP_FIT_WARPS - 1 && r + 1 < n_rows) {         // start pulling the next row in
+            ptr_n = row_ptr[r + 1];
+            if (lane < (int)(ptr_n & 0xFF)) {
+                k_next = pk[(ptr_n >> 8) + lane];
+                asm volatile("prefetch.global.L1 [%0];" ::"l"(pv + (ptr_n >> 8) + lane));
+            }
             if (r + 2 < n_rows && lane == 0) asm volatile("prefetch.global.L1 [%0];" ::"l"(row_ptr + r + 2));
         }
-#pragma unroll
-        for (int j = 1; j < DP_ROW_CHUNKS; ++j)
-            if (j < nch) {
-                const int e = 32 * j + lane;
-                kk[j] = 0; vv[j] = 0.0;
-                if (e < nnz) { kk[j] = pk[off + e]; vv[j] = pv[off + e]; }
-                sq = fma(vv[j], vv[j], sq);
-            }
-        const double vn2 = warp_sum(sq);
-        DP_TICK(t_load)
+        // every warp holds the row: lane e <-> entries e, e + 32, ...
+        int kk[DP_ROW_CHUNKS];
+        double vv[DP_ROW_CHUNKS];
+        double sq = 0.0;
+        FOR_ROW_CHUNKS(j) {
+            const int e = 32 * j + lane;
+            kk[j] = 0; vv[j] = 0.0;
+            if (e < nnz) { kk[j] = pk[off + e]; vv[j] = pv[off + e]; }
+            sq = fma(vv[j], vv[j], sq);
+        }
+        const double vn2 = warp_sum(sq);                         // the same value in every warp
         if (C == 0) {                                           // the first row is always its own cluster (:231-233)
-            FOR_ROW_CHUNKS(j)
-                if (32 * j + lane < nnz) {
-                    S[kk[j]] = vv[j];
-                    lists[(size_t)kk[j] * cap] = 0;
-                    llen[kk[j]] = 1;
-                }
-            if (lane == 0) { cnt[0] = 1; nrm2s[0] = vn2; }
+            if (warp == 0) {
+                FOR_ROW_CHUNKS(j)
+                    if (32 * j + lane < nnz) {
+                        S[kk[j]] = vv[j];
+                        lists[(size_t)kk[j] * cap] = 0;
+                        llen[kk[j]] = 1;
+                    }
+                if (lane == 0) { cnt[0] = 1; nrm2s[0] = vn2; sh_C = 1; }
+            }
+            __syncthreads();
             C = 1;
-            __syncwarp();
             continue;
         }
         // np.argmax over similarities that are all NaN returns 0 and NaN < threshold is False: an all-zero row, or
         // any row while centre 0 is still the zero vector, joins cluster 0 (:243-248)
-        int a = -1;
-        double dot_a = 0.0;
-        if (nnz == 0 || nrm2s[0] == 0.0) {
-            a = 0;
-            if (nnz > 0) {
-                double part = 0.0;
-                FOR_ROW_CHUNKS(j)
-                    if (32 * j + lane < nnz) part = fma(vv[j], S[kk[j]], part);
-                dot_a = warp_sum(part);
-            }
-        } else {
-            // candidates: the centres listed at the row's landmarks.  emask[c] collects, per centre, the row entries
-            // where it is non-zero (rows of <= 32 entries; longer rows only flag the centre)
-            const bool small = nnz <= 32;
+        const bool forced0 = (nnz == 0) || (nrm2s[0] == 0.0);
+        int ncand = 0;
+        if (!forced0) {
+            // 1. candidates
             FOR_ROW_CHUNKS(j)
-                if (32 * j + lane < nnz) {
-                    rk[32 * j + lane] = (uint16_t)kk[j];
-                    rv[32 * j + lane] = vv[j];
-                    const unsigned bit = small ? (1u << lane) : 1u;
-                    const int n = llen[kk[j]];
-                    const uint4* lst = (const uint4*)(lists + (size_t)kk[j] * cap);    // cap is a multiple of 32
-                    for (int t0 = 0; t0 < n; t0 += 32) {
-                        const uint4 q0 = lst[(t0 >> 3)], q1 = lst[(t0 >> 3) + 1], q2 = lst[(t0 >> 3) + 2], q3 = lst[(t0 >> 3) + 3];
-                        const unsigned w[16] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w,
-                                                q2.x, q2.y, q2.z, q2.w, q3.x, q3.y, q3.z, q3.w};
-#pragma unroll
-                        for (int i = 0; i < 16; ++i) {
-                            if (t0 + 2 * i < n) atomicOr(&emask[w[i] & 0xFFFFu], bit);
-                            if (t0 + 2 * i + 1 < n) atomicOr(&emask[w[i] >> 16], bit);
-                        }
+                for (int el = warp; el < 32; el += DP_FIT_WARPS) {
+                    if (32 * j + el >= nnz) break;
+                    const int k = __shfl_sync(0xffffffffu, kk[j], el);
+                    const int n = llen[k];
+                    const uint16_t* lst = lists + (size_t)k * cap;
+                    for (int t = lane; t < n; t += 32) {
+                        const unsigned c = lst[t];
+                        if (atomicExch(&flag[c], 1u) == 0u) cands[atomicAdd(&ncand_s, 1)] = (uint16_t)c;
                     }
                 }
-            __syncwarp();
-            DP_TICK(t_flag)
-            // -> candidate array, ascending (32 centres per round)
-            int ncand = 0;
-            for (int c0 = 0; c0 < C; c0 += 32) {
-                const unsigned m = (c0 + lane < C) ? emask[c0 + lane] : 0u;
-                const unsigned any = __ballot_sync(0xffffffffu, m != 0u);
-                if (m) {
-                    const int pos = ncand + __popc(any & lanemask_lt());
-                    cands[pos] = (uint16_t)(c0 + lane);
-                    cmask[pos] = m;
-                    emask[c0 + lane] = 0u;
-                }
-                ncand += __popc(any);
-            }
-            __syncwarp();
-            DP_TICK(t_enum)
-            n_cand += ncand;
-            // one candidate per lane: its dot product with the row is a chain of independent gathers from S
-            // (all in flight at once), summed in ascending entry order
+            __syncthreads();
+            if (tid == 0) DP_TICK(t_cand)
+            ncand = ncand_s;
+            // 2. dot products and cosines
             const double vnorm = sqrt(vn2);
-            double best = 0.0;                                    // similarities are >= 0; untouched centres have 0
-            int besta = 0;                                        // np.argmax of all zeros
-            for (int c0 = 0; c0 < ncand; c0 += 32) {
-                const bool has = c0 + lane < ncand;
-                const int c = has ? (int)cands[c0 + lane] : 0;
-                const double* __restrict__ sc = S + (size_t)c * L;
-                double dot = 0.0;
-                if (has && small) {
-                    unsigned m = cmask[c0 + lane];                          // only the entries where S_c is non-zero
-                    while (m) {                                             // 8 gathers in flight, then the sum in order
-                        double sv[8];
-                        int ee[8];
+            double bcos = -1.0, bdot = 0.0;                       // this lane's best (lanes 0 .. DP_FIT_UNROLL-1 form cosines)
+            int bc = 0x7FFFFFFF;
+            for (int ci0 = warp; ci0 < ncand; ci0 += DP_FIT_WARPS * DP_FIT_UNROLL) {
+                int cu[DP_FIT_UNROLL];
+                double part[DP_FIT_UNROLL];
 #pragma unroll
-                        for (int i = 0; i < 8; ++i) {
-                            ee[i] = -1; sv[i] = 0.0;
-                            if (m) { ee[i] = __ffs(m) - 1; m &= m - 1u; sv[i] = sc[rk[ee[i]]]; }
-                        }
-#pragma unroll
-                        for (int i = 0; i < 8; ++i)
-                            if (ee[i] >= 0) dot = fma(rv[ee[i]], sv[i], dot);
-                    }
-                } else if (has) {
-                    for (int e0 = 0; e0 < nnz; e0 += 16) {
-                        double sv[16];
-#pragma unroll
-                        for (int i = 0; i < 16; ++i) sv[i] = (e0 + i < nnz) ? sc[rk[e0 + i]] : 0.0;
-#pragma unroll
-                        for (int i = 0; i < 16; ++i)
-                            if (e0 + i < nnz) dot = fma(rv[e0 + i], sv[i], dot);
-                    }
+                for (int u = 0; u < DP_FIT_UNROLL; ++u) {
+                    const int ci = ci0 + u * DP_FIT_WARPS;
+                    cu[u] = (ci < ncand) ? (int)cands[ci] : -1;
+                    part[u] = 0.0;
                 }
-                double cosang = has ? (dot / sqrt(nrm2s[c])) / vnorm : -1.0;    // :241-243
-                int cbest = c;
-                double dbest = dot;
-                // arg-max over the lanes: highest similarity, then lowest centre index (np.argmax: first maximum)
+                FOR_ROW_CHUNKS(j) {
+                    const bool in = 32 * j + lane < nnz;
+                    double sv[DP_FIT_UNROLL];
+#pragma unroll
+                    for (int u = 0; u < DP_FIT_UNROLL; ++u)
+                        sv[u] = (in && cu[u] >= 0) ? S[(size_t)cu[u] * L + kk[j]] : 0.0;
+#pragma unroll
+                    for (int u = 0; u < DP_FIT_UNROLL; ++u) part[u] = fma(vv[j], sv[u], part[u]);
+                }
+                double mydot = 0.0;
+                int myc = -1;
+#pragma unroll
+                for (int u = 0; u < DP_FIT_UNROLL; ++u) {
+                    const double d = warp_sum(part[u]);
+                    if (lane == u) { mydot = d; myc = cu[u]; }
+                }
+                if (myc >= 0) {
+                    const double cosang = (mydot / sqrt(nrm2s[myc])) / vnorm;       // :241-243
+                    if (cosang > bcos || (cosang == bcos && myc < bc)) { bcos = cosang; bc = myc; bdot = mydot; }
+                }
+            }
+            // best of the warp: highest similarity, then lowest centre index (np.argmax: first maximum)
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                const double oc = __shfl_xor_sync(0xffffffffu, bcos, o);
+                const int ob = __shfl_xor_sync(0xffffffffu, bc, o);
+                const double od = __shfl_xor_sync(0xffffffffu, bdot, o);
+                if (oc > bcos || (oc == bcos && ob < bc)) { bcos = oc; bc = ob; bdot = od; }
+            }
+            if (lane == 0) { wb_cos[warp] = bcos; wb_c[warp] = bc; wb_dot[warp] = bdot; }
+            __syncthreads();
+            if (tid == 0) DP_TICK(t_dot)
+        }
+        // 3. decision and commit (warp 0); the other warps clear the flags / prefetch for the next row
+        if (warp == 0) {
+            int a = -1;
+            double dot_a = 0.0;
+            int status = 0;
+            if (forced0) {
+                a = 0;
+                if (nnz > 0) {
+                    double part = 0.0;
+                    FOR_ROW_CHUNKS(j)
+                        if (32 * j + lane < nnz) part = fma(vv[j], S[kk[j]], part);
+                    dot_a = warp_sum(part);
+                }
+            } else {
+                double bcos = (lane < DP_FIT_WARPS) ? wb_cos[lane] : -1.0;
+                int bc = (lane < DP_FIT_WARPS) ? wb_c[lane] : 0x7FFFFFFF;
+                double bdot = (lane < DP_FIT_WARPS) ? wb_dot[lane] : 0.0;
 #pragma unroll
                 for (int o = 16; o > 0; o >>= 1) {
-                    const double oc = __shfl_xor_sync(0xffffffffu, cosang, o);
-                    const int ob = __shfl_xor_sync(0xffffffffu, cbest, o);
-                    const double od = __shfl_xor_sync(0xffffffffu, dbest, o);
-                    if (oc > cosang || (oc == cosang && ob < cbest)) { cosang = oc; cbest = ob; dbest = od; }
+                    const double oc = __shfl_xor_sync(0xffffffffu, bcos, o);
+                    const int ob = __shfl_xor_sync(0xffffffffu, bc, o);
+                    const double od = __shfl_xor_sync(0xffffffffu, bdot, o);
+                    if (oc > bcos || (oc == bcos && ob < bc)) { bcos = oc; bc = ob; bdot = od; }
                 }
-                if (cosang > best) { best = cosang; besta = cbest; dot_a = dbest; }   // chunks ascend: ties keep the earlier
+                // similarities are >= 0 and centres the row does not touch have 0: np.argmax of all zeros is 0
+                double best = 0.0;
+                int besta = 0;
+                if (bcos > 0.0) { best = bcos; besta = bc; dot_a = bdot; }
+                if (!(best < thr)) a = besta;                       // :248 (cos < threshold -> new cluster)
             }
-            __syncwarp();
-            DP_TICK(t_dot)
-            if (!(best < thr)) a = besta;                           // :248 (cos < threshold -> new cluster)
-            if (a == besta && best == 0.0) dot_a = 0.0;
-        }
-        if (a < 0) {
-            // new cluster (:252-262)
-            if (C >= max_c) { status = 1; break; }
-            a = C;
-            bool full = false;
-            FOR_ROW_CHUNKS(j)
-                if (32 * j + lane < nnz) {
-                    const int n = llen[kk[j]];
-                    if (n >= cap) { full = true; continue; }
-                    S[(size_t)a * L + kk[j]] = vv[j];
-                    lists[(size_t)kk[j] * cap + n] = (uint16_t)a;
-                    llen[kk[j]] = (uint16_t)(n + 1);
+            if (a < 0) {
+                // new cluster (:252-262)
+                if (C >= max_c) {
+                    status = 1;
+                } else {
+                    a = C;
+                    bool full = false;
+                    FOR_ROW_CHUNKS(j)
+                        if (32 * j + lane < nnz) {
+                            const int n = llen[kk[j]];
+                            if (n >= cap) { full = true; continue; }
+                            S[(size_t)a * L + kk[j]] = vv[j];
+                            lists[(size_t)kk[j] * cap + n] = (uint16_t)a;
+                            llen[kk[j]] = (uint16_t)(n + 1);
+                        }
+                    if (__any_sync(0xffffffffu, full)) status = 2;
+                    if (lane == 0) { cnt[a] = 1; nrm2s[a] = vn2; }
+                    ++C;
                 }
-            if (__any_sync(0xffffffffu, full)) { status = 2; break; }
-            if (lane == 0) { cnt[a] = 1; nrm2s[a] = vn2; }
-            ++C;
-        } else {
-            // join cluster a: the running mean of :283-289 in sum form
-            bool full = false;
-            FOR_ROW_CHUNKS(j)
-                if (32 * j + lane < nnz) {
-                    double* s = S + (size_t)a * L + kk[j];
-                    const double old = *s;
-                    if (old == 0.0) {                               // the centre gains a landmark
-                        const int n = llen[kk[j]];
-                        if (n >= cap) { full = true; continue; }
-                        lists[(size_t)kk[j] * cap + n] = (uint16_t)a;
-                        llen[kk[j]] = (uint16_t)(n + 1);
+            } else {
+                // join cluster a: the running mean of :283-289 in sum form
+                bool full = false;
+                FOR_ROW_CHUNKS(j)
+                    if (32 * j + lane < nnz) {
+                        double* s = S + (size_t)a * L + kk[j];
+                        const double old = *s;
+                        if (old == 0.0) {                               // the centre gains a landmark
+                            const int n = llen[kk[j]];
+                            if (n >= cap) { full = true; continue; }
+                            lists[(size_t)kk[j] * cap + n] = (uint16_t)a;
+                            llen[kk[j]] = (uint16_t)(n + 1);
+                        }
+                        *s = old + vv[j];
                     }
-                    *s = old + vv[j];
+                if (__any_sync(0xffffffffu, full)) status = 2;
+                if (lane == 0) {
+                    atomicAdd((unsigned long long*)&cnt[a], 1ull);          // fire and forget: nothing waits for the count
+                    if (nnz > 0) nrm2s[a] = nrm2s[a] + 2.0 * dot_a + vn2;
                 }
-            if (__any_sync(0xffffffffu, full)) { status = 2; break; }
-            if (lane == 0) {
-                atomicAdd((unsigned long long*)&cnt[a], 1ull);          // fire and forget: nothing waits for the count
-                if (nnz > 0) nrm2s[a] = nrm2s[a] + 2.0 * dot_a + vn2;
+            }
+            if (lane == 0) { sh_C = C; sh_status = status; ncand_s = 0; }
+        } else {
+            for (int ci = tid - 32; ci < ncand; ci += blockDim.x - 32) flag[cands[ci]] = 0u;
+            if (warp == DP_FIT_WARPS - 1 && r + 1 < n_rows && lane < (int)(ptr_n & 0xFF)) {
+                asm volatile("prefetch.global.L1 [%0];" ::"l"(llen + k_next));
+                asm volatile("prefetch.global.L1 [%0];" ::"l"(lists + (size_t)k_next * cap));
             }
         }
-        __syncwarp();
-        DP_TICK(t_commit)
+        __syncthreads();
+        if (tid == 0) { DP_TICK(t_commit) n_cand += ncand; }
+        C = sh_C;
+        if (sh_status != 0) break;
     }
-    __syncwarp();
-    for (int i = lane; i < C; i += 32) nrm2[i] = nrm2s[i];
-    if (lane == 0) {
-        out[0] = C; out[1] = status; out[2] = r;
-        // diagnostics: SM cycles per phase (row load, candidate flags, enumeration, dot products, commit), candidates
-        out[3] = t_load; out[4] = t_flag; out[5] = t_enum; out[6] = t_dot; out[7] = t_commit; out[8] = n_cand;
+    __syncthreads();
+    for (int i = tid; i < C; i += blockDim.x) nrm2[i] = nrm2s[i];
+    if (tid == 0) {
+        out[0] = C; out[1] = sh_status; out[2] = r;
+        out[3] = t_cand; out[4] = t_dot; out[5] = t_commit; out[6] = n_cand;
     }
 }
 
@@ -358,7 +371,7 @@ extern "C" int sitb_dotprod_fit(int device, const uint64_t* dev_row_ptr, const u
         return set_error(SITB_E_LIMIT, "sitb_dotprod_fit: max_centers %d outside [1, %d]", max_centers, DP_MAX_CENTERS);
     cudaError_t e = cudaSetDevice(device);
     if (e != cudaSuccess) return set_error(SITB_E_CUDA, "cudaSetDevice: %s", cudaGetErrorString(e));
-    k_dotprod_fit<<<1, 32, 0, (cudaStream_t)stream>>>((const unsigned long long*)dev_row_ptr, dev_pool_k, dev_pool_v, n_rows,
+    k_dotprod_fit<<<1, 32 * DP_FIT_WARPS, 0, (cudaStream_t)stream>>>((const unsigned long long*)dev_row_ptr, dev_pool_k, dev_pool_v, n_rows,
                                                      n_landmarks, threshold, max_centers, list_cap, dev_sums,
                                                      (long long*)dev_counts, dev_norm2, dev_lists, dev_list_len,
                                                      (long long*)dev_out3);

@@ -33,10 +33,19 @@
 
 namespace sitb {
 
+// inner offsets of a warp's scratch block
+static constexpr size_t WARP_EV = 0;                                          // double[ENTRY_CAP]
+static constexpr size_t WARP_CAND = WARP_EV + sizeof(double) * ENTRY_CAP;     // uint16[CAND_CAP]
+static constexpr size_t WARP_EK = WARP_CAND + sizeof(uint16_t) * CAND_CAP;    // uint16[ENTRY_CAP]
+static constexpr size_t WARP_QFW = WARP_EK + sizeof(uint16_t) * ENTRY_CAP;    // float[qstride]
+
 struct SmemLayout {
     int Spad, Mpad, qstride;
-    size_t off_ss, off_sm, off_ba, off_b0, off_fs, off_fm, off_wqf, off_wev, off_hist, off_lmap, off_seen,
-        off_cw, off_va, off_v0, off_cid, off_wcand, off_wek, off_task, off_flag, off_ca, off_cb, total;
+    // per-warp scratch is one block per warp (off_warp + warp * warp_bytes) with compile-time inner offsets, so one
+    // base address serves the four arrays: values, candidate list, survivor / entry list, screen distances
+    size_t off_warp, warp_bytes;
+    size_t off_ss, off_sm, off_ba, off_b0, off_fs, off_fm, off_hist, off_lmap, off_seen,
+        off_cw, off_va, off_v0, off_cid, off_task, off_flag, off_ca, off_cb, total;
 };
 
 __host__ __device__ inline SmemLayout make_layout(int S, int M, int L, int Lpad, int NB, int warps, int fb, int mode,
@@ -47,7 +56,8 @@ __host__ __device__ inline SmemLayout make_layout(int S, int M, int L, int Lpad,
     l.qstride = l.Spad + 4;     // per-warp screen distances + the dummy vertex slot [S]
     size_t o = 0;
     l.off_ss = o;    o += sizeof(double) * 3 * (size_t)S * fb;
-    l.off_wev = o;   o += sizeof(double) * (size_t)warps * ENTRY_CAP;
+    l.warp_bytes = (WARP_QFW + sizeof(float) * (size_t)l.qstride + 15) & ~(size_t)15;
+    l.off_warp = o;  o += l.warp_bytes * (size_t)warps;
     l.off_cw = o;    o += (mode == MODE_ASSIGN) ? sizeof(double) * (size_t)Lpad : 0;
     l.off_sm = o;    o += sizeof(double) * 3 * (size_t)M * fb;
     o = (o + 15) & ~(size_t)15;
@@ -56,7 +66,6 @@ __host__ __device__ inline SmemLayout make_layout(int S, int M, int L, int Lpad,
     l.off_b0 = o;    o += sizeof(float) * (size_t)Lpad;
     l.off_fs = o;    o += sizeof(float) * 3 * (size_t)l.Spad * fb;
     l.off_fm = o;    o += sizeof(float) * 3 * (size_t)l.Mpad * fb;
-    l.off_wqf = o;   o += sizeof(float) * (size_t)warps * l.qstride;
     l.off_hist = o;
     if (mode == MODE_STATS || mode == MODE_STAGE) o += sizeof(unsigned) * (size_t)L;
     if (mode == MODE_ASSIGN) o += sizeof(unsigned) * (size_t)(n_clusters > 0 ? n_clusters : 1);
@@ -67,8 +76,6 @@ __host__ __device__ inline SmemLayout make_layout(int S, int M, int L, int Lpad,
     l.off_ca = o;    o += sizeof(ushort4) * (size_t)(Lpad / 32);
     l.off_v0 = o;    o += sizeof(uint16_t) * (size_t)Lpad;
     l.off_cid = o;   o += (mode == MODE_ASSIGN) ? sizeof(int16_t) * (size_t)Lpad : 0;
-    l.off_wcand = o; o += sizeof(uint16_t) * (size_t)warps * CAND_CAP;
-    l.off_wek = o;   o += sizeof(uint16_t) * (size_t)warps * ENTRY_CAP;
     o = (o + 3) & ~(size_t)3;
     l.off_task = o;  o += sizeof(int);
     l.off_flag = o;  o += sizeof(int) * (size_t)fb;
@@ -171,8 +178,9 @@ __global__ void __launch_bounds__(DIAG ? SITB_K1_WARPS * 32 : 512) k_fill(const 
     float* tb0 = (float*)(smem_raw + lay.off_b0);           // [Lpad] screen bound of vertex 0
     float* fs = (float*)(smem_raw + lay.off_fs);            // [FB][3][Spad] fractional statics (float, SoA)
     float* fm = (float*)(smem_raw + lay.off_fm);            // [FB][3][Mpad]
-    float* qfw = (float*)(smem_raw + lay.off_wqf) + (size_t)warp * lay.qstride;
-    double* ev = (double*)(smem_raw + lay.off_wev) + (size_t)warp * ENTRY_CAP;
+    unsigned char* wscratch = smem_raw + lay.off_warp + (size_t)warp * lay.warp_bytes;
+    float* qfw = (float*)(wscratch + WARP_QFW);
+    double* ev = (double*)(wscratch + WARP_EV);
     unsigned* hist = (unsigned*)(smem_raw + lay.off_hist);
     unsigned* lmap_all = (unsigned*)(smem_raw + lay.off_lmap);
     unsigned* seen_all = (unsigned*)(smem_raw + lay.off_seen);
@@ -180,8 +188,8 @@ __global__ void __launch_bounds__(DIAG ? SITB_K1_WARPS * 32 : 512) k_fill(const 
     ushort4* tva = (ushort4*)(smem_raw + lay.off_va);       // [NB][Lpad] vertex ids, 4 per block
     uint16_t* tv0 = (uint16_t*)(smem_raw + lay.off_v0);     // [Lpad] vertex 0
     int16_t* tcid = (int16_t*)(smem_raw + lay.off_cid);     // [Lpad] cluster of landmark (MODE_ASSIGN)
-    uint16_t* cand = (uint16_t*)(smem_raw + lay.off_wcand) + (size_t)warp * CAND_CAP;
-    uint16_t* ek = (uint16_t*)(smem_raw + lay.off_wek) + (size_t)warp * ENTRY_CAP;
+    uint16_t* cand = (uint16_t*)(wscratch + WARP_CAND);
+    uint16_t* ek = (uint16_t*)(wscratch + WARP_EK);
     int* task_counter = (int*)(smem_raw + lay.off_task);
     int* full_walk = (int*)(smem_raw + lay.off_flag);      // [FB] frame has a static atom beyond the grid margin
     ushort4* tca = (ushort4*)(smem_raw + lay.off_ca);       // [Lpad/32] chunk skip table: atoms

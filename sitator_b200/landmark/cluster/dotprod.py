@@ -115,8 +115,8 @@ def fit_centers(source, threshold):
     centers = (sums[:n_c] / counts[:n_c, None].to(torch.float64)).cpu().numpy()
     logger.debug("dotprod fit: %d centres after the pass over %d landmark vectors (longest landmark list %d of %d)"
                  % (n_c, rows.n_rows, int(llen.max().item()), cap))
-    logger.debug("dotprod fit: cycles/row load %.0f, flags %.0f, enumerate %.0f, dots %.0f, commit %.0f; %.1f candidates/row"
-                 % tuple(float(x) / max(rows.n_rows, 1) for x in diag[3:9]))
+    logger.debug("dotprod fit: SM cycles per row: candidates %.0f, dot products %.0f, commit %.0f; %.1f candidates per row"
+                 % tuple(float(x) / max(rows.n_rows, 1) for x in diag[3:7]))
     return _refine_centers(centers, n_assigned, threshold)
 
 
