@@ -261,7 +261,7 @@ def run_reference_arm(args):
                          "sample": "whole LandmarkAnalysis.run (mcl) on %d frames per step" % per_step},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(line))
+    emit(line)
 
 
 def workload_name(system, n_frames):
@@ -435,13 +435,28 @@ def run_ours(args):
     }
     if not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline(system, cfg, frames, min(args.cpu_frames, F))
-    print(json.dumps(line))
+    emit(line)
     if world > 1:
         dist.destroy_process_group()
 
 
+_RESULT_OUT = None
+
+
+def emit(line):
+    """The one JSON line, on the process's real stdout."""
+    out = _RESULT_OUT or sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
 if __name__ == "__main__":
     a = parse_args()
+    # stdout carries exactly one JSON line: whatever libraries write to file descriptor 1 (e.g. NCCL's version banner
+    # under torchrun) is sent to stderr instead
+    sys.stdout.flush()
+    _RESULT_OUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     if a.impl == "reference":
         run_reference_arm(a)
     else:
