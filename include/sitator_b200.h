@@ -240,6 +240,33 @@ int sitb_jump_analysis(int device, const int64_t* dev_traj, int64_t n_frames, in
                        double* dev_n_ij, uint64_t* dev_total_time, double* dev_lag_sum, uint64_t* dev_lag_n,
                        uint64_t* dev_n_problems, void* cuda_stream);
 
+/* ---- post-processing of the assignment stream ----
+ * sitb_assign_last_known: SiteTrajectory.assign_to_last_known_site (SiteTrajectory.py:235-304), in place on dev_traj:
+ *   an unknown entry takes the atom's last known site while fewer than frame_threshold frames have passed since
+ *   it was last known.  dev_carry_label / dev_carry_time [n_mobile] (may be NULL: -1 / 0) = state before this
+ *   shard; dev_end_label / dev_end_time [n_mobile] (may be NULL) = state after it.  apply = 0 only chains the
+ *   state (dev_traj untouched).  dev_stats4 += {entries reassigned, sum and number of the unknown stretches that
+ *   ended}; [3] = max over ended stretches longer than the threshold of (global frame << 24 | length): the
+ *   reference reports the length seen at the LAST such frame (:271-273).
+ * sitb_windowed_mode: running_windowed_mode (dynamics/SmoothSiteTrajectory.pyx:79-111): dev_out[f][m] = the most
+ *   frequent label of frames [f - wleft, f + wright) if it occurs >= threshold times, else unknown
+ *   (replace_no_winner_unknown) or the input label.  dev_before / dev_after (may be NULL) = the last halo_before /
+ *   first halo_after frames of the neighbouring shards.
+ * sitb_seen_sites / sitb_relabel_sites: RemoveUnoccupiedSites (dynamics/RemoveUnoccupiedSites.py:30-57): dev_seen
+ *   [n_sites] uint32 (zeroed) = 1 where a site occurs; labels mapped through dev_translation [n_sites]. */
+int sitb_assign_last_known(int device, int64_t* dev_traj, int64_t n_frames, int32_t n_mobile, int64_t frame0,
+                           int64_t frame_threshold, const int64_t* dev_carry_label, const int64_t* dev_carry_time,
+                           int64_t* dev_end_label, int64_t* dev_end_time, uint64_t* dev_stats4, int32_t apply,
+                           void* cuda_stream);
+int sitb_windowed_mode(int device, const int64_t* dev_traj, int64_t* dev_out, int64_t n_frames, int32_t n_mobile,
+                       int32_t wleft, int32_t wright, int64_t threshold, int32_t replace_no_winner_unknown,
+                       int64_t halo_before, const int64_t* dev_before, int64_t halo_after, const int64_t* dev_after,
+                       void* cuda_stream);
+int sitb_seen_sites(int device, const int64_t* dev_traj, int64_t n_entries, int32_t n_sites, uint32_t* dev_seen,
+                    void* cuda_stream);
+int sitb_relabel_sites(int device, int64_t* dev_traj, int64_t n_entries, int32_t n_sites, const int64_t* dev_translation,
+                       void* cuda_stream);
+
 /* Tensor-core alternative for the landmark Gram (the covariance input of cluster/mcl.py:53).
  * Staging buffers: two zero-filled fp16 arrays of lpad * ld elements (lpad % 128 == 0, ld % 64 == 0) holding the
  *   transposed landmark vectors as value = hi + lo * 2^-12, stored as contiguous 16 KB tiles: tile (rt, kt) =

@@ -50,6 +50,8 @@ MODULES = [
     # package __init__ of sitator.dynamics pulls in merging/network/ase calculators;
     # ref_loader installs a namespace stub for the package and loads this one module.
     "sitator/dynamics/JumpAnalysis.py",
+    "sitator/dynamics/RemoveUnoccupiedSites.py",
+    "sitator/dynamics/SmoothSiteTrajectory.pyx",
 ]
 
 

@@ -139,6 +139,9 @@ def load():
     from sitator.util import PBCCalculator, DotProdClassifier
     from sitator.util.mcl import markov_clustering
     from sitator.dynamics.JumpAnalysis import JumpAnalysis
+    from sitator.dynamics.RemoveUnoccupiedSites import RemoveUnoccupiedSites
+    sitator.dynamics.RemoveUnoccupiedSites = RemoveUnoccupiedSites      # what the package __init__ would export
+    from sitator.dynamics.SmoothSiteTrajectory import SmoothSiteTrajectory
     from sitator import SiteNetwork, SiteTrajectory
     import sitator.errors as errors
     import sitator.landmark.errors as lerrors
@@ -147,7 +150,8 @@ def load():
         sitator=sitator, LandmarkAnalysis=LandmarkAnalysis, helpers=helpers,
         cluster_mcl=cluster_mcl, PBCCalculator=PBCCalculator,
         DotProdClassifier=DotProdClassifier, markov_clustering=markov_clustering,
-        JumpAnalysis=JumpAnalysis,
+        JumpAnalysis=JumpAnalysis, RemoveUnoccupiedSites=RemoveUnoccupiedSites,
+        SmoothSiteTrajectory=SmoothSiteTrajectory,
         SiteNetwork=SiteNetwork, SiteTrajectory=SiteTrajectory,
         errors=errors, landmark_errors=lerrors, Atoms=StubAtoms,
     )

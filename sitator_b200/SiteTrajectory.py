@@ -112,6 +112,7 @@ class SiteTrajectory(object):
     def copy(self, with_computed=True):
         st = self[:]
         st.site_network = st.site_network.copy(with_computed=with_computed)
+        st.frame0, st._comm = self.frame0, self._comm
         return st
 
     def set_real_traj(self, real_traj):
@@ -192,9 +193,65 @@ class SiteTrajectory(object):
         n_more, n_assigned, n_distinct = (int(x) for x in out.cpu().numpy())
         return n_more, n_assigned / n_distinct
 
+    # ---- SiteTrajectory.assign_to_last_known_site (ref :235-304) ---------------------------------
     def assign_to_last_known_site(self, frame_threshold=1):
-        raise NotImplementedError("assign_to_last_known_site is on the 'next' list (SURVEY.md section 8f-3); "
-                                  "sitator_b200 has no CPU fallback for it yet")
+        """Assign unassigned mobile particles to their last known site (in place).
+
+        Args:
+            frame_threshold (int): the maximum number of frames between the last known site and the present
+                frame up to which the last known site can be used.
+        Returns:
+            dict with ``max_time_unknown``, ``avg_time_unknown``, ``total_reassigned`` (the reference's diagnostics).
+        """
+        import torch
+        lib = _native.load()
+        dev = _device_index()
+        total_unknown = self.n_unassigned
+        logger.info("%i unassigned positions (%i%%); assigning unassigned mobile particles to last known positions "
+                    "within %s frames..." % (total_unknown, 100.0 * self.percent_unassigned, frame_threshold))
+        traj = self._device_traj()
+        M = self._sn.n_mobile
+        stream = torch.cuda.current_stream().cuda_stream
+        stats = torch.zeros(4, dtype=torch.int64, device="cuda")
+        carry_l = carry_t = None
+        if self._comm is not None:
+            # state at the end of every shard taken alone, chained over the earlier shards on the host
+            end_l = torch.empty(M, dtype=torch.int64, device="cuda")
+            end_t = torch.empty(M, dtype=torch.int64, device="cuda")
+            _native.check(lib.sitb_assign_last_known(dev, C.c_void_p(traj.data_ptr()), self.n_frames, M, int(self.frame0),
+                                                     int(frame_threshold), None, None, C.c_void_p(end_l.data_ptr()),
+                                                     C.c_void_p(end_t.data_ptr()), None, 0, C.c_void_p(stream)))
+            all_l = self._comm.allgather_numpy(end_l.cpu().numpy())
+            all_t = self._comm.allgather_numpy(end_t.cpu().numpy())
+            lk = np.full(M, -1, dtype=np.int64)
+            tu = np.zeros(M, dtype=np.int64)
+            for r in range(self._comm.rank):
+                has = all_l[r] != -1
+                lk = np.where(has, all_l[r], lk)
+                tu = np.where(has, all_t[r], tu + all_t[r])
+            carry_l = torch.as_tensor(lk, device="cuda")
+            carry_t = torch.as_tensor(tu, device="cuda")
+        _native.check(lib.sitb_assign_last_known(
+            dev, C.c_void_p(traj.data_ptr()), self.n_frames, M, int(self.frame0), int(frame_threshold),
+            None if carry_l is None else C.c_void_p(carry_l.data_ptr()),
+            None if carry_t is None else C.c_void_p(carry_t.data_ptr()), None, None,
+            C.c_void_p(stats.data_ptr()), 1, C.c_void_p(stream)))
+        if self._comm is not None:
+            self._comm.allreduce_sum_(stats[:3])
+            self._comm.allreduce_max_u64_(stats[3:])
+        self._traj[...] = traj.cpu().numpy()
+        reassigned, sum_times, n_times, key = (int(x) for x in stats.cpu().numpy().view(np.uint64))
+        if n_times > 0:
+            res = {'max_time_unknown': key & 0xFFFFFF, 'avg_time_unknown': float(sum_times) / n_times,
+                   'total_reassigned': reassigned}
+            logger.info("  Maximum # of frames any mobile particle spent unassigned: %i" % res['max_time_unknown'])
+            logger.info("  Avg. # of frames spent unassigned: %f" % res['avg_time_unknown'])
+            logger.info("  Assigned %i/%i unassigned positions, leaving %i (%i%%) unknown"
+                        % (reassigned, total_unknown, self.n_unassigned, self.percent_unassigned))
+        else:
+            logger.info("  None to correct.")
+            res = {'max_time_unknown': 0, 'avg_time_unknown': 0, 'total_reassigned': 0}
+        return res
 
     # ---- jumps (ref :307-373) ------------------------------------------------------------------
     def jump_array(self, unknown_as_jump=False):

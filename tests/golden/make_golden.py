@@ -58,6 +58,43 @@ def run_dotprod_case(ref, name, config, n_frames, traj_kw):
     print("%s: %d frames, %d sites, %d unassigned" % (name, n_frames, out_sn.n_sites, int(np.sum(st.traj < 0))))
 
 
+def run_postprocess(ref):
+    """assign_to_last_known_site / SmoothSiteTrajectory of the compiled reference on assignment streams with
+    plenty of unknowns: the toy golden's labels and a synthetic stream (random walks over 12 sites, 25 % unknown)."""
+    import ast
+    out = {}
+    g = dict(np.load(os.path.join(HERE, "toy_bcc_300.npz"), allow_pickle=False))
+    system, cfg = syn.make_config("toy_bcc")
+    rng = np.random.default_rng(7)
+    F, M, C = 700, 16, 12
+    steps = rng.random((F, M)) < 0.05
+    synth = (np.cumsum(steps, axis=0) + rng.integers(0, C, M)[None, :]) % C
+    flick = rng.random((F, M)) < 0.04                           # one-frame excursions for the smoother to remove
+    synth = np.where(flick, (synth + 1) % C, synth)
+    holes = rng.random((F, M)) < 0.25
+    holes[200:260, 3] = True                                    # a long unknown stretch
+    holes[:5, 7] = True                                         # unknown from the start
+    synth = np.where(holes, -1, synth).astype(np.int64)
+    streams = {"toy": (g["labels"].astype(np.int64), int(g["site_centers"].shape[0])), "synth": (synth, C)}
+    for name, (traj, n_sites) in streams.items():
+        sn = syn.site_network_for(system, ref.SiteNetwork, ref.Atoms)
+        sn.centers = np.zeros((n_sites, 3))
+        out[name + "_traj"] = traj
+        out[name + "_n_sites"] = n_sites
+        for thr in (1, 2, 5):
+            st = ref.SiteTrajectory(sn, traj.copy())
+            info = st.assign_to_last_known_site(frame_threshold=thr)
+            out["%s_lk%d" % (name, thr)] = st.traj.copy()
+            out["%s_lk%d_info" % (name, thr)] = np.array([info['max_time_unknown'], info['avg_time_unknown'], info['total_reassigned']], dtype=np.float64)
+        for thr, flag in ((3, True), (4, False), (10, True)):
+            st = ref.SiteTrajectory(sn, traj.copy())
+            sm = ref.SmoothSiteTrajectory(set_unassigned_under_threshold=flag).run(st, thr)
+            out["%s_smooth%d_%d" % (name, thr, int(flag))] = sm.traj.copy()
+            out["%s_smooth%d_%d_n_sites" % (name, thr, int(flag))] = sm.site_network.n_sites
+    np.savez_compressed(os.path.join(HERE, "postprocess.npz"), **out)
+    print("postprocess: %d arrays" % len(out))
+
+
 def run_case(ref, name, config, n_frames, traj_kw):
     system, cfg = syn.make_config(config)
     frames = system.trajectory(n_frames, **traj_kw)
@@ -97,10 +134,12 @@ if __name__ == "__main__":
     if not build_ref.build(verbose=False):
         sys.exit("needs /root/reference to build oracle/_ref")
     ref = ref_loader.load()
-    which = sys.argv[1:] or ["mcl", "dotprod"]
+    which = sys.argv[1:] or ["mcl", "dotprod", "post"]
     if "mcl" in which:
         for case in CASES:
             run_case(ref, *case)
+    if "post" in which:
+        run_postprocess(ref)
     if "dotprod" in which:
         for case in DOTPROD_CASES:
             run_dotprod_case(ref, *case)

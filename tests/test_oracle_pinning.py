@@ -55,6 +55,25 @@ def test_oracle_dotprod_clustering_reproduces_reference_golden(name):
     assert np.array_equal(orc.jumps(labels), g["jumps"])
 
 
+def test_oracle_postprocessing_reproduces_reference_golden():
+    """assign_to_last_known_site and SmoothSiteTrajectory (+ RemoveUnoccupiedSites) against tests/golden/postprocess.npz."""
+    import os
+    g = dict(np.load(os.path.join(U.GOLDEN_DIR, "postprocess.npz"), allow_pickle=False))
+    for name in ("toy", "synth"):
+        traj, n_sites = g[name + "_traj"], int(g[name + "_n_sites"])
+        assert np.sum(traj == -1) > 0
+        for thr in (1, 2, 5):
+            out, info = orc.assign_to_last_known_site(traj, thr)
+            assert np.array_equal(out, g["%s_lk%d" % (name, thr)])
+            want = g["%s_lk%d_info" % (name, thr)]
+            assert info['max_time_unknown'] == int(want[0]) and info['total_reassigned'] == int(want[2])
+            assert abs(info['avg_time_unknown'] - want[1]) < 1e-12
+        for thr, flag in ((3, True), (4, False), (10, True)):
+            out, kept = orc.smooth_site_trajectory(traj, n_sites, thr, set_unassigned_under_threshold=flag)
+            assert np.array_equal(out, g["%s_smooth%d_%d" % (name, thr, int(flag))])
+            assert int(kept.sum()) == int(g["%s_smooth%d_%d_n_sites" % (name, thr, int(flag))])
+
+
 def test_oracle_against_live_reference_if_built():
     from oracle import ref_loader
     if not ref_loader.available():
