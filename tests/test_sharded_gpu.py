@@ -37,7 +37,14 @@ def _run_shard(rank, world, port, bounds, q):
         mine = np.ascontiguousarray(frames[bounds[rank]:bounds[rank + 1]])
         la = LandmarkAnalysis(clustering_algorithm='mcl', verbose=False, check_for_zero_landmarks=False)
         st = la.run(syn.site_network_for(system), mine)
+        # post-processing across the shard boundary: the last-known-site scan carries its state over, the
+        # smoothing window reads the neighbour's frames
+        from sitator_b200.dynamics import SmoothSiteTrajectory
+        smooth = SmoothSiteTrajectory(remove_unoccupied_sites=False).run(st, 3).traj
+        lk = st.copy()
+        lk_info = lk.assign_to_last_known_site(frame_threshold=2)
         q.put((rank, dict(traj=st.traj, confs=st.confidences, centers=np.asarray(st.site_network.centers),
+                          smooth=smooth, lk=lk.traj, lk_info=lk_info,
                           verts=[sorted(v) for v in st.site_network.vertices], frame0=st.frame0,
                           n_multi=la.n_multiple_assignments, avg=la.avg_mobile_per_site, nzero=la.n_all_zero_lvecs,
                           jumps=st.jump_array(), jumps_u=st.jump_array(unknown_as_jump=True))))
@@ -55,6 +62,10 @@ def test_two_shards_equal_one():
     la = LandmarkAnalysis(clustering_algorithm='mcl', verbose=False, check_for_zero_landmarks=False)
     st = la.run(syn.site_network_for(system), frames)
     want_j, want_ju = st.jump_array(), st.jump_array(unknown_as_jump=True)
+    from sitator_b200.dynamics import SmoothSiteTrajectory
+    want_smooth = SmoothSiteTrajectory(remove_unoccupied_sites=False).run(st, 3).traj
+    want_lk = st.copy()
+    want_lk_info = want_lk.assign_to_last_known_site(frame_threshold=2)
 
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
@@ -77,5 +88,9 @@ def test_two_shards_equal_one():
         assert res[r]["n_multi"] == la.n_multiple_assignments
         assert abs(res[r]["avg"] - la.avg_mobile_per_site) < 1e-12
         assert res[r]["nzero"] == la.n_all_zero_lvecs
+    assert np.array_equal(np.concatenate([res[0]["smooth"], res[1]["smooth"]]), want_smooth)
+    assert np.array_equal(np.concatenate([res[0]["lk"], res[1]["lk"]]), want_lk.traj)
+    for r in range(2):
+        assert res[r]["lk_info"] == want_lk_info
     assert np.array_equal(np.concatenate([res[0]["jumps"], res[1]["jumps"]]), want_j)
     assert np.array_equal(np.concatenate([res[0]["jumps_u"], res[1]["jumps_u"]]), want_ju)
