@@ -254,6 +254,12 @@ int sitb_jump_analysis(int device, const int64_t* dev_traj, int64_t n_frames, in
  *   first halo_after frames of the neighbouring shards.
  * sitb_seen_sites / sitb_relabel_sites: RemoveUnoccupiedSites (dynamics/RemoveUnoccupiedSites.py:30-57): dev_seen
  *   [n_sites] uint32 (zeroed) = 1 where a site occurs; labels mapped through dev_translation [n_sites]. */
+/* RecenterTrajectory (util/RecenterTrajectory.pyx:14-100), in place on dev_array [n_frames][n_atoms][3]: every frame
+ * minus sum_j dev_weights[j] * x_j (dev_weights[j] = (1 / total static mass) * factor_j * mass_j, built by the caller in
+ * the reference's operation order; the sum runs over the atoms in order, so the centre is the reference's bit for
+ * bit), plus host_shift3 (the cell centroid, :56-57; NULL for velocities). */
+int sitb_recenter(int device, double* dev_array, int64_t n_frames, int32_t n_atoms, const double* dev_weights,
+                  const double* host_shift3, void* cuda_stream);
 int sitb_assign_last_known(int device, int64_t* dev_traj, int64_t n_frames, int32_t n_mobile, int64_t frame0,
                            int64_t frame_threshold, const int64_t* dev_carry_label, const int64_t* dev_carry_time,
                            int64_t* dev_end_label, int64_t* dev_end_time, uint64_t* dev_stats4, int32_t apply,

@@ -155,6 +155,28 @@ __global__ void k_relabel(long long* __restrict__ traj, long long n, int n_sites
     }
 }
 
+// RecenterTrajectory (util/RecenterTrajectory.pyx:61-100): per frame, subtract the mass-weighted centre of the
+// atoms with factor != 0 (accumulated over the atoms IN ORDER with the reference's operation order, so the centre
+// is bit-identical), then add `shift` (the cell centroid; zero for velocities).  One warp per frame: lanes 0..2
+// chain the sum of one coordinate each, then all lanes update the frame.
+__global__ void __launch_bounds__(256) k_recenter(double* __restrict__ arr, long long F, int A, const double* __restrict__ w,
+                                                  double shift_x, double shift_y, double shift_z, int add_shift) {
+    const int lane = threadIdx.x & 31;
+    const long long f = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (f >= F) return;
+    double* fr = arr + (size_t)f * A * 3;
+    double com = 0.0;
+    if (lane < 3)
+        for (int j = 0; j < A; ++j) com = __dadd_rn(com, __dmul_rn(w[j], fr[3 * j + lane]));   // :92-94
+    const double cx = __shfl_sync(0xffffffffu, com, 0), cy = __shfl_sync(0xffffffffu, com, 1), cz = __shfl_sync(0xffffffffu, com, 2);
+    for (int i = lane; i < 3 * A; i += 32) {
+        const int d = i % 3;
+        double v = __dsub_rn(fr[i], d == 0 ? cx : (d == 1 ? cy : cz));                          // :97-99
+        if (add_shift) v = __dadd_rn(v, d == 0 ? shift_x : (d == 1 ? shift_y : shift_z));       // :56-57
+        fr[i] = v;
+    }
+}
+
 }  // namespace sitb
 
 using namespace sitb;
@@ -238,5 +260,17 @@ extern "C" int sitb_relabel_sites(int device, int64_t* dev_traj, int64_t n_entri
     k_relabel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>((long long*)dev_traj, n_entries, n_sites,
                                                                 (const long long*)dev_translation);
     CKP(cudaGetLastError(), "k_relabel");
+    return SITB_OK;
+}
+
+extern "C" int sitb_recenter(int device, double* dev_array, int64_t n_frames, int32_t n_atoms, const double* dev_weights,
+                             const double* host_shift3, void* stream) {
+    if (!dev_array || !dev_weights || n_frames < 0 || n_atoms <= 0) return set_error(SITB_E_INVALID, "sitb_recenter: bad argument");
+    if (n_frames == 0) return SITB_OK;
+    CKP(cudaSetDevice(device), "cudaSetDevice");
+    const double sx = host_shift3 ? host_shift3[0] : 0.0, sy = host_shift3 ? host_shift3[1] : 0.0, sz = host_shift3 ? host_shift3[2] : 0.0;
+    k_recenter<<<(unsigned)((n_frames + 7) / 8), 256, 0, (cudaStream_t)stream>>>(dev_array, n_frames, n_atoms, dev_weights, sx, sy, sz,
+                                                                             host_shift3 ? 1 : 0);
+    CKP(cudaGetLastError(), "k_recenter");
     return SITB_OK;
 }

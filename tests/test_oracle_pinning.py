@@ -74,6 +74,18 @@ def test_oracle_postprocessing_reproduces_reference_golden():
             assert int(kept.sum()) == int(g["%s_smooth%d_%d_n_sites" % (name, thr, int(flag))])
 
 
+def test_oracle_recenter_reproduces_reference_golden():
+    """RecenterTrajectory (util/RecenterTrajectory.pyx) bit for bit."""
+    import os
+    from tests.golden.make_golden import recenter_inputs
+    g = dict(np.load(os.path.join(U.GOLDEN_DIR, "recenter.npz"), allow_pickle=False))
+    system, pos, vel, masses = recenter_inputs()
+    factors = system.static_mask.astype(np.float64)
+    centroid = np.sum(0.5 * system.cell, axis=0)
+    assert np.array_equal(orc.recenter_trajectory(pos, masses, factors, centroid), g["positions"])
+    assert np.array_equal(orc.recenter_trajectory(vel, masses, factors, None), g["velocities"])
+
+
 def test_oracle_against_live_reference_if_built():
     from oracle import ref_loader
     if not ref_loader.available():

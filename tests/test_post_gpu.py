@@ -88,3 +88,16 @@ def test_long_stream_against_the_oracle():
     sm = SmoothSiteTrajectory(remove_unoccupied_sites=False).run(st, 6)
     want = orc.running_windowed_mode(traj, 6, 7, 6, 20, True)
     assert np.array_equal(sm.traj, want)
+
+
+def test_recenter_trajectory_matches_reference_bit_for_bit():
+    from tests.golden.make_golden import recenter_inputs
+    from sitator_b200.util.RecenterTrajectory import RecenterTrajectory
+    from sitator_b200.structure import Atoms
+    g = dict(np.load(os.path.join(U.GOLDEN_DIR, "recenter.npz"), allow_pickle=False))
+    system, pos, vel, masses = recenter_inputs()
+    structure = Atoms(system.initial_structure_positions(), system.cell, np.where(system.static_mask, 8, 3))
+    p, v = pos.copy(), vel.copy()
+    assert RecenterTrajectory().run(structure, system.static_mask.copy(), p, velocities=v, masses=masses) is None
+    assert np.array_equal(p, g["positions"])
+    assert np.array_equal(v, g["velocities"])
