@@ -101,6 +101,9 @@ int sitb_get_tables(sitb_ctx* ctx, double* host_site_vert_dists, double* host_q_
 /* Frames: copied once and kept resident for all passes, or borrowed from the caller's device buffer.
  * frame0 = global index of the first frame (frame-sharded runs). */
 int sitb_upload_frames(sitb_ctx* ctx, const double* host_frames, int64_t n_frames, int64_t frame0);
+/* float32 trajectories (not accepted by the reference, whose Cython fill is typed double): copied at half the
+ * PCIe cost and widened to float64 on the device, so results equal a run on frames.astype(float64). */
+int sitb_upload_frames_f32(sitb_ctx* ctx, const float* host_frames, int64_t n_frames, int64_t frame0);
 int sitb_borrow_frames(sitb_ctx* ctx, const double* dev_frames, int64_t n_frames, int64_t frame0);
 /* sitb_upload_frames copies in chunks on its own stream and returns at once when host_frames is page-locked (the
  * caller keeps it alive and unchanged until the passes reading it have run); a pass waits only for the chunks

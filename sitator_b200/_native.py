@@ -54,6 +54,7 @@ SIGNATURES = {
     "sitb_device_info": (C.c_int, [_P, C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
     "sitb_get_tables": (C.c_int, [_P, _P, _P]),
     "sitb_upload_frames": (C.c_int, [_P, _P, C.c_int64, C.c_int64]),
+    "sitb_upload_frames_f32": (C.c_int, [_P, _P, C.c_int64, C.c_int64]),
     "sitb_borrow_frames": (C.c_int, [_P, _P, C.c_int64, C.c_int64]),
     "sitb_reset_status": (C.c_int, [_P]),
     "sitb_get_status": (C.c_int, [_P, C.POINTER(Status)]),

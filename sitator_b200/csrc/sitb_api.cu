@@ -102,6 +102,8 @@ struct sitb_ctx {
     const double* d_frames = nullptr;
     double* d_frames_owned = nullptr;
     size_t frames_capacity = 0;      // bytes
+    float* d_frames_f32 = nullptr;   // staging for float32 sources (converted to float64 chunk by chunk)
+    size_t f32_capacity = 0;
     long long n_frames = 0, frame0 = 0;
     // the upload runs chunk by chunk on its own stream; a pass waits only for the chunks it reads, so the
     // first pass over a fresh trajectory overlaps the host -> device copy
@@ -126,7 +128,7 @@ static void free_ctx(sitb_ctx* c) {
     pool_free(c->d_grid_ptr, c->stream); pool_free(c->d_grid_list, c->stream);
     pool_free(c->d_grid_sptr, c->stream); pool_free(c->d_grid_slist, c->stream); pool_free(c->d_rmax, c->stream);
     pool_free(c->d_verts_in, c->stream); pool_free(c->d_svd, c->stream); pool_free(c->d_qorig, c->stream); pool_free(c->d_orig_of, c->stream); pool_free(c->d_v0, c->stream); pool_free(c->d_b0, c->stream); pool_free(c->d_va, c->stream); pool_free(c->d_ba, c->stream);
-    pool_free(c->d_q64, c->stream); pool_free(c->d_acoef, c->stream); pool_free(c->d_nverts, c->stream); pool_free(c->d_cid, c->stream); pool_free(c->d_cw, c->stream); pool_free(c->d_cid_orig, c->stream); pool_free(c->d_cw_orig, c->stream); pool_free(c->d_frames_owned, c->stream); pool_free(c->d_status, c->stream);
+    pool_free(c->d_q64, c->stream); pool_free(c->d_acoef, c->stream); pool_free(c->d_nverts, c->stream); pool_free(c->d_cid, c->stream); pool_free(c->d_cw, c->stream); pool_free(c->d_cid_orig, c->stream); pool_free(c->d_cw_orig, c->stream); pool_free(c->d_frames_owned, c->stream); pool_free(c->d_frames_f32, c->stream); pool_free(c->d_status, c->stream);
     delete c;
 }
 
@@ -420,6 +422,59 @@ extern "C" int sitb_upload_frames(sitb_ctx* c, const double* host, int64_t n, in
         const long long nf = (n - f0 < c->up_chunk) ? (n - f0) : c->up_chunk;
         CK(cudaMemcpyAsync(c->d_frames_owned + (size_t)f0 * c->A * 3, host + (size_t)f0 * c->A * 3, frame_bytes * (size_t)nf,
                            cudaMemcpyHostToDevice, c->copy_stream));
+        CK(cudaEventRecord(c->up_events[k], c->copy_stream));
+    }
+    c->up_waited = 0;
+    c->d_frames = c->d_frames_owned; c->n_frames = n; c->frame0 = frame0;
+    return SITB_OK;
+}
+
+__global__ void k_widen_frames(const float* __restrict__ in, double* __restrict__ out, size_t n) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) out[i] = (double)in[i];
+}
+
+// float32 trajectories (what most MD codes write): half the PCIe traffic; widened to float64 on the device, chunk by
+// chunk on the copy stream, so every result equals a run on frames.astype(float64).
+extern "C" int sitb_upload_frames_f32(sitb_ctx* c, const float* host, int64_t n, int64_t frame0) {
+    if (!c || !host || n <= 0) return fail(SITB_E_INVALID, "sitb_upload_frames_f32: bad argument");
+    CK(cudaSetDevice(c->device));
+    const size_t frame_elems = (size_t)c->A * 3;
+    const size_t bytes64 = sizeof(double) * frame_elems * (size_t)n, bytes32 = sizeof(float) * frame_elems * (size_t)n;
+    if (bytes64 > c->frames_capacity) {
+        pool_free(c->d_frames_owned, c->stream);
+        c->d_frames_owned = nullptr; c->frames_capacity = 0;
+        CK(pool_alloc((void**)&c->d_frames_owned, bytes64, c->stream));
+        c->frames_capacity = bytes64;
+    }
+    if (bytes32 > c->f32_capacity) {
+        pool_free(c->d_frames_f32, c->stream);
+        c->d_frames_f32 = nullptr; c->f32_capacity = 0;
+        CK(pool_alloc((void**)&c->d_frames_f32, bytes32, c->stream));
+        c->f32_capacity = bytes32;
+    }
+    if (!c->copy_stream) {
+        CK(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+        CK(cudaEventCreateWithFlags(&c->order_event, cudaEventDisableTiming));
+    }
+    CK(cudaEventRecord(c->order_event, c->stream));
+    CK(cudaStreamWaitEvent(c->copy_stream, c->order_event, 0));
+    c->up_chunk = (long long)((32ull << 20) / (sizeof(float) * frame_elems));
+    if (c->up_chunk < 1) c->up_chunk = 1;
+    const size_t n_chunks = (size_t)((n + c->up_chunk - 1) / c->up_chunk);
+    while (c->up_events.size() < n_chunks) {
+        cudaEvent_t ev;
+        CK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+        c->up_events.push_back(ev);
+    }
+    for (size_t k = 0; k < n_chunks; ++k) {
+        const long long f0 = (long long)k * c->up_chunk;
+        const long long nf = (n - f0 < c->up_chunk) ? (n - f0) : c->up_chunk;
+        const size_t o = (size_t)f0 * frame_elems, cnt = (size_t)nf * frame_elems;
+        CK(cudaMemcpyAsync(c->d_frames_f32 + o, host + o, sizeof(float) * cnt, cudaMemcpyHostToDevice, c->copy_stream));
+        size_t blocks = (cnt + 255) / 256;
+        if (blocks > (size_t)c->n_sms * 8) blocks = (size_t)c->n_sms * 8;
+        k_widen_frames<<<(unsigned)blocks, 256, 0, c->copy_stream>>>(c->d_frames_f32 + o, c->d_frames_owned + o, cnt);
+        CK(cudaGetLastError());
         CK(cudaEventRecord(c->up_events[k], c->copy_stream));
     }
     c->up_waited = 0;

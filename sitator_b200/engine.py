@@ -181,16 +181,21 @@ class LandmarkEngine(object):
             self.frames_bytes = 0
         else:
             frames = np.asarray(frames)
-            if frames.dtype != np.float64:
-                raise ValueError("frames must be float64 (the reference rejects other dtypes too)")
+            if frames.dtype not in (np.float64, np.float32):
+                raise ValueError("frames must be float64 (as in the reference) or float32")
             if frames.shape[1:] != (self.n_atoms, 3):
                 raise ValueError("Wrong shape %s for frames." % (frames.shape,))
             frames = np.ascontiguousarray(frames)
             # asynchronous when the host array is page-locked: the passes wait for the chunks they read, and the
-            # array is kept alive here until the next set_frames()/close()
-            _native.check(self._lib.sitb_upload_frames(self._ctx, frames.ctypes.data, frames.shape[0], frame0))
+            # array is kept alive here until the next set_frames()/close().  float32 sources (np.memmap'ed MD dumps
+            # included) cross PCIe at half the size and are widened on the device.
+            if frames.dtype == np.float32:
+                _native.check(self._lib.sitb_upload_frames_f32(self._ctx, frames.ctypes.data, frames.shape[0], frame0))
+                self.frames_bytes = max(self.frames_bytes, int(frames.nbytes) * 3)
+            else:
+                _native.check(self._lib.sitb_upload_frames(self._ctx, frames.ctypes.data, frames.shape[0], frame0))
+                self.frames_bytes = max(self.frames_bytes, int(frames.nbytes))
             self._frames_keepalive = frames
-            self.frames_bytes = max(self.frames_bytes, int(frames.nbytes))
         self.n_frames = int(frames.shape[0])
         self.frame0 = int(frame0)
 

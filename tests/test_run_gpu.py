@@ -159,3 +159,25 @@ def test_site_center_methods_and_errors():
         LandmarkAnalysis(clustering_algorithm='mcl').run(syn.site_network_for(system), frames[:, :-1])
     with pytest.raises(ZeroLandmarkError):        # the default algorithm ('dotprod') runs the same checks first
         LandmarkAnalysis().run(syn.site_network_for(system), frames)
+
+
+def test_float32_and_memmap_frame_sources(tmp_path):
+    """float32 trajectories are widened on the device: the result equals a run on frames.astype(float64) (up to the
+    run-to-run rounding of the atomically accumulated Gram, ~1e-16); an np.memmap (float32 MD dump on disk) is a
+    valid source."""
+    system, cfg = syn.make_config("toy_bcc")
+    frames32 = system.trajectory(200).astype(np.float32)
+    la64, st64 = _run(system, cfg, frames32.astype(np.float64))
+    la32, st32 = _run(system, cfg, frames32)
+    assert np.array_equal(st32.traj, st64.traj)
+    assert np.max(np.abs(st32.confidences - st64.confidences)) < 1e-13
+    assert np.max(np.abs(np.asarray(st32.site_network.centers) - np.asarray(st64.site_network.centers))) < 1e-12
+    lv32, lv64 = np.asarray(la32.landmark_vectors), np.asarray(la64.landmark_vectors)
+    assert np.array_equal(lv32, lv64)                              # the landmark vectors themselves are bit-equal
+    path = str(tmp_path / "traj.f32")
+    frames32.tofile(path)
+    mm = np.memmap(path, dtype=np.float32, mode="r", shape=frames32.shape)
+    lam, stm = _run(system, cfg, mm)
+    assert np.array_equal(stm.traj, st64.traj) and np.max(np.abs(stm.confidences - st64.confidences)) < 1e-13
+    with pytest.raises(ValueError, match="float64"):
+        _run(system, cfg, frames32.astype(np.float16))
