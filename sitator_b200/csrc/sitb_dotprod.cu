@@ -47,8 +47,12 @@ __device__ __forceinline__ double warp_sum(double x) {
 //      flight before the first reduction), warp sum, one lane per candidate forms the cosine; best per warp
 //   3. warp 0 merges the warp bests (highest cosine, then lowest centre index = np.argmax), decides and commits;
 //      the other warps clear the flags and pull the next row's lists towards L1 meanwhile
-static constexpr int DP_FIT_WARPS = 8;
-static constexpr int DP_FIT_UNROLL = 4;               // candidates per warp and pass
+#ifndef SITB_DP_FIT_WARPS
+#define SITB_DP_FIT_WARPS 16
+#endif
+static constexpr int DP_FIT_WARPS = SITB_DP_FIT_WARPS;
+static constexpr int DP_FIT_UNROLL = (DP_FIT_WARPS >= 16) ? 2 : 4;   // candidates per warp and pass
+static constexpr int DP_SVAL_CANDS = 64;              // candidates whose gathered S values are kept for the commit
 
 __global__ void __launch_bounds__(32 * DP_FIT_WARPS) k_dotprod_fit(
     const unsigned long long* __restrict__ row_ptr, const uint16_t* __restrict__ pk, const double* __restrict__ pv,
@@ -58,42 +62,58 @@ __global__ void __launch_bounds__(32 * DP_FIT_WARPS) k_dotprod_fit(
     __shared__ double nrm2s[DP_MAX_CENTERS];          // |S_c|^2 (written back to nrm2 at the end)
     __shared__ uint16_t cands[DP_MAX_CENTERS];        // candidate centres of the current row, in order of first touch
     __shared__ int ncand_s, sh_C, sh_status;
+    __shared__ unsigned long long nx_ptr[2];
+    __shared__ uint16_t nx_k[2][32];
+    __shared__ double nx_v[2][32];
     __shared__ double wb_cos[DP_FIT_WARPS], wb_dot[DP_FIT_WARPS];
-    __shared__ int wb_c[DP_FIT_WARPS];
+    __shared__ int wb_c[DP_FIT_WARPS], wb_ci[DP_FIT_WARPS];
+    __shared__ double sval[DP_SVAL_CANDS][32];        // S_c[k_e] of the first 32 entries, per candidate (phase 2 -> commit)
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     for (int i = tid; i < DP_MAX_CENTERS; i += blockDim.x) flag[i] = 0u;
     if (tid == 0) { ncand_s = 0; sh_C = 0; sh_status = 0; }
     __syncthreads();
     int C = 0;
     long long r = 0;
-    long long t_cand = 0, t_dot = 0, t_commit = 0, n_cand = 0;
-    int k_next = 0;                                   // (last warp) first entries of the next row, for the list prefetch
+    long long t_cand = 0, t_dot = 0, t_commit = 0, n_cand = 0, t_arrive = 0;
+    // the last warp fetches the next row (pointer + first 32 entries) while the current one is processed and leaves
+    // it in shared memory (double buffered), so a row starts from shared memory instead of two dependent global loads
+    int k_next = 0;
+    double v_next = 0.0;
+    unsigned long long ptr_n = 0ull;
+    if (warp == DP_FIT_WARPS - 1 && n_rows > 0) {
+        ptr_n = row_ptr[0];
+        if (lane < (int)(ptr_n & 0xFF)) { k_next = pk[(ptr_n >> 8) + lane]; v_next = pv[(ptr_n >> 8) + lane]; }
+        if (lane == 0) nx_ptr[0] = ptr_n;
+        nx_k[0][lane] = (uint16_t)k_next; nx_v[0][lane] = v_next;
+    }
+    __syncthreads();
     for (; r < n_rows; ++r) {
         long long tk = clock64();
 #define DP_TICK(acc) { const long long now_ = clock64(); acc += now_ - tk; tk = now_; }
-        const unsigned long long ptr = row_ptr[r];
+        const int buf = (int)(r & 1);
+        const unsigned long long ptr = nx_ptr[buf];
         const int nnz = (int)(ptr & 0xFF);
         const int nch = (nnz + 31) >> 5;
         const unsigned long long off = ptr >> 8;
-        unsigned long long ptr_n = 0ull;
-        if (warp == DP_FIT_WARPS - 1 && r + 1 < n_rows) {         // start pulling the next row in
+        if (warp == DP_FIT_WARPS - 1 && r + 1 < n_rows) {         // start pulling the next row in (used at the end of this row)
             ptr_n = row_ptr[r + 1];
-            if (lane < (int)(ptr_n & 0xFF)) {
-                k_next = pk[(ptr_n >> 8) + lane];
-                asm volatile("prefetch.global.L1 [%0];" ::"l"(pv + (ptr_n >> 8) + lane));
-            }
+            if (lane < (int)(ptr_n & 0xFF)) { k_next = pk[(ptr_n >> 8) + lane]; v_next = pv[(ptr_n >> 8) + lane]; }
             if (r + 2 < n_rows && lane == 0) asm volatile("prefetch.global.L1 [%0];" ::"l"(row_ptr + r + 2));
         }
         // every warp holds the row: lane e <-> entries e, e + 32, ...
         int kk[DP_ROW_CHUNKS];
         double vv[DP_ROW_CHUNKS];
-        double sq = 0.0;
-        FOR_ROW_CHUNKS(j) {
-            const int e = 32 * j + lane;
-            kk[j] = 0; vv[j] = 0.0;
-            if (e < nnz) { kk[j] = pk[off + e]; vv[j] = pv[off + e]; }
-            sq = fma(vv[j], vv[j], sq);
-        }
+        kk[0] = nx_k[buf][lane]; vv[0] = nx_v[buf][lane];
+        double sq = (lane < nnz) ? vv[0] * vv[0] : 0.0;
+        if (lane >= nnz) { kk[0] = 0; vv[0] = 0.0; }
+#pragma unroll
+        for (int j = 1; j < DP_ROW_CHUNKS; ++j)
+            if (j < nch) {                                       // rows longer than 32 entries: the rest from global memory
+                const int e = 32 * j + lane;
+                kk[j] = 0; vv[j] = 0.0;
+                if (e < nnz) { kk[j] = pk[off + e]; vv[j] = pv[off + e]; }
+                sq = fma(vv[j], vv[j], sq);
+            }
         const double vn2 = warp_sum(sq);                         // the same value in every warp
         if (C == 0) {                                           // the first row is always its own cluster (:231-233)
             if (warp == 0) {
@@ -104,6 +124,10 @@ __global__ void __launch_bounds__(32 * DP_FIT_WARPS) k_dotprod_fit(
                         llen[kk[j]] = 1;
                     }
                 if (lane == 0) { cnt[0] = 1; nrm2s[0] = vn2; sh_C = 1; }
+            }
+            if (warp == DP_FIT_WARPS - 1 && r + 1 < n_rows) {
+                if (lane == 0) nx_ptr[buf ^ 1] = ptr_n;
+                nx_k[buf ^ 1][lane] = (uint16_t)k_next; nx_v[buf ^ 1][lane] = v_next;
             }
             __syncthreads();
             C = 1;
@@ -130,9 +154,8 @@ __global__ void __launch_bounds__(32 * DP_FIT_WARPS) k_dotprod_fit(
             if (tid == 0) DP_TICK(t_cand)
             ncand = ncand_s;
             // 2. dot products and cosines
-            const double vnorm = sqrt(vn2);
             double bcos = -1.0, bdot = 0.0;                       // this lane's best (lanes 0 .. DP_FIT_UNROLL-1 form cosines)
-            int bc = 0x7FFFFFFF;
+            int bc = 0x7FFFFFFF, bci = 0x7FFFFFFF;
             for (int ci0 = warp; ci0 < ncand; ci0 += DP_FIT_WARPS * DP_FIT_UNROLL) {
                 int cu[DP_FIT_UNROLL];
                 double part[DP_FIT_UNROLL];
@@ -150,17 +173,24 @@ __global__ void __launch_bounds__(32 * DP_FIT_WARPS) k_dotprod_fit(
                         sv[u] = (in && cu[u] >= 0) ? S[(size_t)cu[u] * L + kk[j]] : 0.0;
 #pragma unroll
                     for (int u = 0; u < DP_FIT_UNROLL; ++u) part[u] = fma(vv[j], sv[u], part[u]);
+                    if (j == 0) {
+#pragma unroll
+                        for (int u = 0; u < DP_FIT_UNROLL; ++u)
+                            if (cu[u] >= 0 && ci0 + u * DP_FIT_WARPS < DP_SVAL_CANDS) sval[ci0 + u * DP_FIT_WARPS][lane] = sv[u];
+                    }
                 }
                 double mydot = 0.0;
-                int myc = -1;
+                int myc = -1, myci = 0;
 #pragma unroll
                 for (int u = 0; u < DP_FIT_UNROLL; ++u) {
                     const double d = warp_sum(part[u]);
-                    if (lane == u) { mydot = d; myc = cu[u]; }
+                    if (lane == u) { mydot = d; myc = cu[u]; myci = ci0 + u * DP_FIT_WARPS; }
                 }
                 if (myc >= 0) {
-                    const double cosang = (mydot / sqrt(nrm2s[myc])) / vnorm;       // :241-243
-                    if (cosang > bcos || (cosang == bcos && myc < bc)) { bcos = cosang; bc = myc; bdot = mydot; }
+                    // :241-243 (dot / |centre|) / |row|, as one reciprocal square root: equal to ~1 ulp, and only
+                    // the order of the cosines and their side of the threshold are used
+                    const double cosang = mydot * rsqrt(nrm2s[myc] * vn2);
+                    if (cosang > bcos || (cosang == bcos && myc < bc)) { bcos = cosang; bc = myc; bdot = mydot; bci = myci; }
                 }
             }
             // best of the warp: highest similarity, then lowest centre index (np.argmax: first maximum)
@@ -169,15 +199,17 @@ __global__ void __launch_bounds__(32 * DP_FIT_WARPS) k_dotprod_fit(
                 const double oc = __shfl_xor_sync(0xffffffffu, bcos, o);
                 const int ob = __shfl_xor_sync(0xffffffffu, bc, o);
                 const double od = __shfl_xor_sync(0xffffffffu, bdot, o);
-                if (oc > bcos || (oc == bcos && ob < bc)) { bcos = oc; bc = ob; bdot = od; }
+                const int oi = __shfl_xor_sync(0xffffffffu, bci, o);
+                if (oc > bcos || (oc == bcos && ob < bc)) { bcos = oc; bc = ob; bdot = od; bci = oi; }
             }
-            if (lane == 0) { wb_cos[warp] = bcos; wb_c[warp] = bc; wb_dot[warp] = bdot; }
+            if (lane == 0) { wb_cos[warp] = bcos; wb_c[warp] = bc; wb_dot[warp] = bdot; wb_ci[warp] = bci; }
             __syncthreads();
             if (tid == 0) DP_TICK(t_dot)
         }
         // 3. decision and commit (warp 0); the other warps clear the flags / prefetch for the next row
+        const long long t_phase3 = clock64();
         if (warp == 0) {
-            int a = -1;
+            int a = -1, a_ci = 0x7FFFFFFF;                       // a_ci: the winner's place in the candidate array
             double dot_a = 0.0;
             int status = 0;
             if (forced0) {
@@ -192,17 +224,19 @@ __global__ void __launch_bounds__(32 * DP_FIT_WARPS) k_dotprod_fit(
                 double bcos = (lane < DP_FIT_WARPS) ? wb_cos[lane] : -1.0;
                 int bc = (lane < DP_FIT_WARPS) ? wb_c[lane] : 0x7FFFFFFF;
                 double bdot = (lane < DP_FIT_WARPS) ? wb_dot[lane] : 0.0;
+                int bci = (lane < DP_FIT_WARPS) ? wb_ci[lane] : 0x7FFFFFFF;
 #pragma unroll
                 for (int o = 16; o > 0; o >>= 1) {
                     const double oc = __shfl_xor_sync(0xffffffffu, bcos, o);
                     const int ob = __shfl_xor_sync(0xffffffffu, bc, o);
                     const double od = __shfl_xor_sync(0xffffffffu, bdot, o);
-                    if (oc > bcos || (oc == bcos && ob < bc)) { bcos = oc; bc = ob; bdot = od; }
+                    const int oi = __shfl_xor_sync(0xffffffffu, bci, o);
+                    if (oc > bcos || (oc == bcos && ob < bc)) { bcos = oc; bc = ob; bdot = od; bci = oi; }
                 }
                 // similarities are >= 0 and centres the row does not touch have 0: np.argmax of all zeros is 0
                 double best = 0.0;
                 int besta = 0;
-                if (bcos > 0.0) { best = bcos; besta = bc; dot_a = bdot; }
+                if (bcos > 0.0) { best = bcos; besta = bc; dot_a = bdot; a_ci = bci; }
                 if (!(best < thr)) a = besta;                       // :248 (cos < threshold -> new cluster)
             }
             if (a < 0) {
@@ -230,7 +264,8 @@ __global__ void __launch_bounds__(32 * DP_FIT_WARPS) k_dotprod_fit(
                 FOR_ROW_CHUNKS(j)
                     if (32 * j + lane < nnz) {
                         double* s = S + (size_t)a * L + kk[j];
-                        const double old = *s;
+                        // (the winner's components were gathered in phase 2: first 32 entries from shared memory)
+                        const double old = (j == 0 && a_ci < DP_SVAL_CANDS) ? sval[a_ci][lane] : *s;
                         if (old == 0.0) {                               // the centre gains a landmark
                             const int n = llen[kk[j]];
                             if (n >= cap) { full = true; continue; }
@@ -248,11 +283,16 @@ __global__ void __launch_bounds__(32 * DP_FIT_WARPS) k_dotprod_fit(
             if (lane == 0) { sh_C = C; sh_status = status; ncand_s = 0; }
         } else {
             for (int ci = tid - 32; ci < ncand; ci += blockDim.x - 32) flag[cands[ci]] = 0u;
-            if (warp == DP_FIT_WARPS - 1 && r + 1 < n_rows && lane < (int)(ptr_n & 0xFF)) {
-                asm volatile("prefetch.global.L1 [%0];" ::"l"(llen + k_next));
-                asm volatile("prefetch.global.L1 [%0];" ::"l"(lists + (size_t)k_next * cap));
+            if (warp == DP_FIT_WARPS - 1 && r + 1 < n_rows) {
+                if (lane == 0) nx_ptr[buf ^ 1] = ptr_n;
+                nx_k[buf ^ 1][lane] = (uint16_t)k_next; nx_v[buf ^ 1][lane] = v_next;
+                if (lane < (int)(ptr_n & 0xFF)) {
+                    asm volatile("prefetch.global.L1 [%0];" ::"l"(llen + k_next));
+                    asm volatile("prefetch.global.L1 [%0];" ::"l"(lists + (size_t)k_next * cap));
+                }
             }
         }
+        if (lane == 0) t_arrive += clock64() - t_phase3;          // diagnostics: when this warp reaches the row's last barrier
         __syncthreads();
         if (tid == 0) { DP_TICK(t_commit) n_cand += ncand; }
         C = sh_C;
@@ -264,6 +304,7 @@ __global__ void __launch_bounds__(32 * DP_FIT_WARPS) k_dotprod_fit(
         out[0] = C; out[1] = sh_status; out[2] = r;
         out[3] = t_cand; out[4] = t_dot; out[5] = t_commit; out[6] = n_cand;
     }
+    if (lane == 0) out[8 + warp] = t_arrive;
 }
 
 // predict: one warp per row.  Centres are given dense and already normalised (C x L), plus per landmark the

@@ -117,6 +117,8 @@ def fit_centers(source, threshold):
                  % (n_c, rows.n_rows, int(llen.max().item()), cap))
     logger.debug("dotprod fit: SM cycles per row: candidates %.0f, dot products %.0f, commit %.0f; %.1f candidates per row"
                  % tuple(float(x) / max(rows.n_rows, 1) for x in diag[3:7]))
+    logger.debug("dotprod fit: cycles per row from the start of phase 3 to the last barrier, per warp: %s"
+                 % " ".join("%.0f" % (float(x) / max(rows.n_rows, 1)) for x in diag[8:16]))
     return _refine_centers(centers, n_assigned, threshold)
 
 
