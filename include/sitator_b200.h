@@ -77,6 +77,7 @@ typedef struct sitb_status {
     uint64_t nnz;                /* non-zero landmark-vector components produced */
     uint64_t n_screen_rejects;       /* landmarks that passed the float pre-screen but failed the exact double test */
     uint64_t n_full_walk_frames;     /* frames with a static atom beyond the candidate-grid margin (all landmarks walked) */
+    uint64_t n_loose_grid_frames;    /* frames with a static atom beyond half the margin (the looser candidate lists) */
 } sitb_status;
 
 const char* sitb_last_error(void);
@@ -89,8 +90,9 @@ int sitb_set_stream(sitb_ctx* ctx, void* cuda_stream);
 /* Candidate grid of the fill kernel (orthorhombic cells; no reference counterpart -- the reference walks every
  * landmark, helpers.pyx:188).  Frames whose static atoms all lie within static_margin (Angstrom) of their ideal
  * positions test only the landmarks that can be non-zero in the grid box of the mobile atom; other frames walk
- * all landmarks.  Results do not depend on it.  sitb_create builds it with 0.5 A (env SITB_GRID_MARGIN
- * overrides); static_margin <= 0 removes it. */
+ * all landmarks.  Lists are kept for static_margin and for half of it; a frame uses the tightest that covers its
+ * largest static displacement.  Results do not depend on it.  sitb_create builds it with 0.5 A (env
+ * SITB_GRID_MARGIN overrides); static_margin <= 0 removes it. */
 int sitb_set_candidate_grid(sitb_ctx* ctx, double static_margin);
 int sitb_candidate_grid_info(sitb_ctx* ctx, int32_t* dims3, double* static_margin, uint64_t* n_entries);
 int sitb_device_info(sitb_ctx* ctx, int32_t* n_sms, int32_t* cc_major, int32_t* cc_minor);

@@ -37,7 +37,7 @@ class Status(C.Structure):
         ("zero_error", C.c_int32), ("zero_index", C.c_int32), ("zero_frame", C.c_int64),
         ("n_zero_rows", C.c_uint64), ("n_duplicate_nearest", C.c_uint64),
         ("n_list_overflow", C.c_uint64), ("nnz", C.c_uint64), ("n_screen_rejects", C.c_uint64),
-        ("n_full_walk_frames", C.c_uint64),
+        ("n_full_walk_frames", C.c_uint64), ("n_loose_grid_frames", C.c_uint64),
     ]
 
 

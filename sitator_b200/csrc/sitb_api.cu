@@ -54,6 +54,15 @@ int set_error(int code, const char* fmt, ...) {
             return fail(SITB_E_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
     } while (0)
 
+struct GridLevelDev {
+    unsigned* ptr = nullptr;          // [cells + 1] landmark lists
+    uint16_t* list = nullptr;
+    unsigned* sptr = nullptr;         // [cells + 1] static-site lists
+    uint16_t* slist = nullptr;
+    double margin = 0.0;
+    unsigned long long entries = 0, static_entries = 0;
+};
+
 struct sitb_ctx {
     int device = 0;
     int n_sms = 0, cc_major = 0, cc_minor = 0;
@@ -83,15 +92,10 @@ struct sitb_ctx {
     double* d_acoef = nullptr;
     uint8_t* d_nverts = nullptr;
     // candidate grid (orthorhombic cells)
-    unsigned* d_grid_ptr = nullptr;
-    uint16_t* d_grid_list = nullptr;
-    unsigned* d_grid_sptr = nullptr;
-    uint16_t* d_grid_slist = nullptr;
+    GridLevelDev grid[2];             // [0] half the margin, [1] the margin
+    int n_grid_levels = 0;
     double* d_rmax = nullptr;
-    unsigned long long grid_static_entries = 0;
     int gx = 0, gy = 0, gz = 0;
-    double grid_margin = 0.0;
-    unsigned long long grid_entries = 0;
     // centres
     int* d_cid = nullptr;
     double* d_cw = nullptr;
@@ -125,8 +129,11 @@ static void free_ctx(sitb_ctx* c) {
     for (cudaEvent_t ev : c->up_events) cudaEventDestroy(ev);
     pool_free(c->d_static_idx, c->stream); pool_free(c->d_mobile_idx, c->stream); pool_free(c->d_ideal, c->stream); pool_free(c->d_centers, c->stream);
     pool_free(c->d_chunk_atoms, c->stream); pool_free(c->d_chunk_bound, c->stream);
-    pool_free(c->d_grid_ptr, c->stream); pool_free(c->d_grid_list, c->stream);
-    pool_free(c->d_grid_sptr, c->stream); pool_free(c->d_grid_slist, c->stream); pool_free(c->d_rmax, c->stream);
+    for (int l = 0; l < 2; ++l) {
+        pool_free(c->grid[l].ptr, c->stream); pool_free(c->grid[l].list, c->stream);
+        pool_free(c->grid[l].sptr, c->stream); pool_free(c->grid[l].slist, c->stream);
+    }
+    pool_free(c->d_rmax, c->stream);
     pool_free(c->d_verts_in, c->stream); pool_free(c->d_svd, c->stream); pool_free(c->d_qorig, c->stream); pool_free(c->d_orig_of, c->stream); pool_free(c->d_v0, c->stream); pool_free(c->d_b0, c->stream); pool_free(c->d_va, c->stream); pool_free(c->d_ba, c->stream);
     pool_free(c->d_q64, c->stream); pool_free(c->d_acoef, c->stream); pool_free(c->d_nverts, c->stream); pool_free(c->d_cid, c->stream); pool_free(c->d_cw, c->stream); pool_free(c->d_cid_orig, c->stream); pool_free(c->d_cw_orig, c->stream); pool_free(c->d_frames_owned, c->stream); pool_free(c->d_frames_f32, c->stream); pool_free(c->d_status, c->stream);
     delete c;
@@ -281,13 +288,59 @@ extern "C" int sitb_create(const sitb_network_desc* d, int device, sitb_ctx** ou
 }
 
 // (Re)build the candidate grid for a static-atom margin (Angstrom); margin <= 0 or a triclinic cell: no grid.
+// one level of the candidate grid: the landmark lists and the static-site lists of every box for one margin
+static int build_grid_level(sitb_ctx* c, const int g[3], double margin, GridLevelDev& out) {
+    const size_t cells = (size_t)g[0] * g[1] * g[2];
+    for (int pass = 0; pass < 2; ++pass) {                // 0: landmarks, 1: static-lattice sites
+        unsigned* d_count = nullptr;
+        CK(pool_alloc((void**)&d_count, sizeof(unsigned) * cells, c->stream));
+        cudaError_t e = pass == 0
+            ? launch_grid_lists(c->cell, c->d_ideal, c->d_va, c->d_q64, c->L, c->Lpad, c->NB, c->S, g[0], g[1], g[2], margin,
+                                nullptr, d_count, nullptr, c->stream)
+            : launch_grid_static_lists(c->cell, c->d_ideal, c->d_rmax, c->S, g[0], g[1], g[2], margin, nullptr, d_count, nullptr,
+                                       c->stream);
+        std::vector<unsigned> ptr(cells + 1, 0u);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(ptr.data() + 1, d_count, sizeof(unsigned) * cells, cudaMemcpyDeviceToHost, c->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+        pool_free(d_count, c->stream);
+        if (e != cudaSuccess) return fail(SITB_E_CUDA, "candidate grid (count): %s", cudaGetErrorString(e));
+        unsigned long long total = 0;
+        for (size_t i = 1; i <= cells; ++i) { total += ptr[i]; ptr[i] = (unsigned)total; }
+        if (total >= 0xFFFFFFFFull) return fail(SITB_E_LIMIT, "candidate grid: more than 2^32 list entries");
+        unsigned** d_ptr = pass == 0 ? &out.ptr : &out.sptr;
+        uint16_t** d_list = pass == 0 ? &out.list : &out.slist;
+        CK(upload(d_ptr, ptr.data(), cells + 1, c->stream));
+        CK(pool_alloc((void**)d_list, sizeof(uint16_t) * (size_t)(total ? total : 1), c->stream));
+        if (pass == 0) {
+            CK(launch_grid_lists(c->cell, c->d_ideal, c->d_va, c->d_q64, c->L, c->Lpad, c->NB, c->S, g[0], g[1], g[2], margin,
+                                 *d_ptr, nullptr, *d_list, c->stream));
+            out.entries = total;
+        } else {
+            CK(launch_grid_static_lists(c->cell, c->d_ideal, c->d_rmax, c->S, g[0], g[1], g[2], margin, *d_ptr, nullptr, *d_list,
+                                        c->stream));
+            out.static_entries = total;
+        }
+    }
+    return SITB_OK;
+}
+
+static void free_grid(sitb_ctx* c) {
+    for (int l = 0; l < 2; ++l) {
+        pool_free(c->grid[l].ptr, c->stream); pool_free(c->grid[l].list, c->stream);
+        pool_free(c->grid[l].sptr, c->stream); pool_free(c->grid[l].slist, c->stream);
+        c->grid[l] = GridLevelDev();
+    }
+    c->n_grid_levels = 0;
+    c->gx = c->gy = c->gz = 0;
+}
+
+// (Re)build the candidate grid for a static-atom margin (Angstrom); margin <= 0 or a triclinic cell: no grid.
+// Two levels: lists for half the margin (what a quiet lattice needs: fewer candidates) and for the margin itself;
+// K1 picks per frame the tightest level that covers the frame's largest static displacement.
 static int build_grid(sitb_ctx* c, double margin) {
     CK(cudaSetDevice(c->device));
     CK(cudaStreamSynchronize(c->stream));
-    pool_free(c->d_grid_ptr, c->stream); pool_free(c->d_grid_list, c->stream);
-    pool_free(c->d_grid_sptr, c->stream); pool_free(c->d_grid_slist, c->stream);
-    c->d_grid_ptr = nullptr; c->d_grid_list = nullptr; c->d_grid_sptr = nullptr; c->d_grid_slist = nullptr;
-    c->gx = c->gy = c->gz = 0; c->grid_margin = 0.0; c->grid_entries = 0; c->grid_static_entries = 0;
+    free_grid(c);
     if (!(margin > 0.0) || !c->cell.diag) return SITB_OK;
     const double len[3] = {std::fabs(c->cell.c[0]), std::fabs(c->cell.c[4]), std::fabs(c->cell.c[8])};
     if (c->cell.c[0] <= 0.0 || c->cell.c[4] <= 0.0 || c->cell.c[8] <= 0.0) return SITB_OK;
@@ -305,48 +358,18 @@ static int build_grid(sitb_ctx* c, double margin) {
         if (cells * (double)c->L <= 2.0e8 || (g[0] == 1 && g[1] == 1 && g[2] == 1)) break;
         side *= 1.26;
     }
-    const size_t cells = (size_t)g[0] * g[1] * g[2];
-    // margin: the caller's bound on static displacements + the float rounding of the box lookup in K1
+    // list margin = the bound on static displacements + the float rounding of the box lookup in K1
     const double lmax = std::max(len[0], std::max(len[1], len[2]));
     const double eps = 1e-5 * lmax + 1e-9;
-    unsigned* d_count = nullptr;
-    CK(pool_alloc((void**)&d_count, sizeof(unsigned) * cells, c->stream));
-    cudaError_t e = launch_grid_lists(c->cell, c->d_ideal, c->d_va, c->d_q64, c->L, c->Lpad, c->NB, c->S, g[0], g[1], g[2],
-                                      margin + eps, nullptr, d_count, nullptr, c->stream);
-    std::vector<unsigned> ptr(cells + 1, 0u);
-    if (e == cudaSuccess) e = cudaMemcpyAsync(ptr.data() + 1, d_count, sizeof(unsigned) * cells, cudaMemcpyDeviceToHost, c->stream);
-    if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
-    pool_free(d_count, c->stream);
-    if (e != cudaSuccess) return fail(SITB_E_CUDA, "candidate grid (count): %s", cudaGetErrorString(e));
-    unsigned long long total = 0;
-    for (size_t i = 1; i <= cells; ++i) { total += ptr[i]; ptr[i] = (unsigned)total; }
-    if (total >= 0xFFFFFFFFull) return SITB_OK;              // absurdly large: keep the full walk
-    CK(upload(&c->d_grid_ptr, ptr.data(), cells + 1, c->stream));
-    CK(pool_alloc((void**)&c->d_grid_list, sizeof(uint16_t) * (size_t)(total ? total : 1), c->stream));
-    CK(launch_grid_lists(c->cell, c->d_ideal, c->d_va, c->d_q64, c->L, c->Lpad, c->NB, c->S, g[0], g[1], g[2], margin + eps,
-                         c->d_grid_ptr, nullptr, c->d_grid_list, c->stream));
-    // the static-lattice sites of each box, same two passes
-    CK(pool_alloc((void**)&d_count, sizeof(unsigned) * cells, c->stream));
-    e = launch_grid_static_lists(c->cell, c->d_ideal, c->d_rmax, c->S, g[0], g[1], g[2], margin + eps, nullptr, d_count, nullptr,
-                                 c->stream);
-    std::vector<unsigned> sptr(cells + 1, 0u);
-    if (e == cudaSuccess) e = cudaMemcpyAsync(sptr.data() + 1, d_count, sizeof(unsigned) * cells, cudaMemcpyDeviceToHost, c->stream);
-    if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
-    pool_free(d_count, c->stream);
-    if (e != cudaSuccess) return fail(SITB_E_CUDA, "candidate grid (static count): %s", cudaGetErrorString(e));
-    unsigned long long stotal = 0;
-    for (size_t i = 1; i <= cells; ++i) { stotal += sptr[i]; sptr[i] = (unsigned)stotal; }
-    if (stotal >= 0xFFFFFFFFull) {
-        pool_free(c->d_grid_ptr, c->stream); pool_free(c->d_grid_list, c->stream);
-        c->d_grid_ptr = nullptr; c->d_grid_list = nullptr;
-        return SITB_OK;
+    const double margins[2] = {0.5 * margin, margin};
+    for (int l = 0; l < 2; ++l) {
+        const int rc = build_grid_level(c, g, margins[l] + eps, c->grid[l]);
+        if (rc != SITB_OK) { free_grid(c); return rc == SITB_E_LIMIT ? SITB_OK : rc; }   // absurdly large: keep the full walk
+        c->grid[l].margin = margins[l];
     }
-    CK(upload(&c->d_grid_sptr, sptr.data(), cells + 1, c->stream));
-    CK(pool_alloc((void**)&c->d_grid_slist, sizeof(uint16_t) * (size_t)(stotal ? stotal : 1), c->stream));
-    CK(launch_grid_static_lists(c->cell, c->d_ideal, c->d_rmax, c->S, g[0], g[1], g[2], margin + eps, c->d_grid_sptr, nullptr,
-                                c->d_grid_slist, c->stream));
     CK(cudaStreamSynchronize(c->stream));
-    c->gx = g[0]; c->gy = g[1]; c->gz = g[2]; c->grid_margin = margin; c->grid_entries = total; c->grid_static_entries = stotal;
+    c->gx = g[0]; c->gy = g[1]; c->gz = g[2];
+    c->n_grid_levels = 2;
     return SITB_OK;
 }
 
@@ -358,8 +381,8 @@ extern "C" int sitb_set_candidate_grid(sitb_ctx* c, double static_margin) {
 extern "C" int sitb_candidate_grid_info(sitb_ctx* c, int32_t* dims, double* static_margin, uint64_t* n_entries) {
     if (!c) return fail(SITB_E_INVALID, "null context");
     if (dims) { dims[0] = c->gx; dims[1] = c->gy; dims[2] = c->gz; }
-    if (static_margin) *static_margin = c->grid_margin;
-    if (n_entries) *n_entries = c->grid_entries;
+    if (static_margin) *static_margin = c->n_grid_levels ? c->grid[c->n_grid_levels - 1].margin : 0.0;
+    if (n_entries) *n_entries = c->grid[0].entries + c->grid[1].entries;
     return SITB_OK;
 }
 
@@ -541,6 +564,7 @@ extern "C" int sitb_get_status(sitb_ctx* c, sitb_status* out) {
     out->nnz = h[2 + CNT_NNZ];
     out->n_screen_rejects = h[2 + CNT_SCREEN_REJECT];
     out->n_full_walk_frames = h[2 + CNT_FULL_WALK_FRAMES];
+    out->n_loose_grid_frames = h[2 + CNT_LOOSE_GRID_FRAMES];
     return SITB_OK;
 }
 
@@ -568,9 +592,12 @@ static int base_params(sitb_ctx* c, int64_t begin, int64_t n, FillParams& p, con
     p.tab.q64 = c->d_q64; p.tab.acoef = c->d_acoef; p.tab.nverts = c->d_nverts; p.tab.orig_of = c->d_orig_of;
     p.tab.chunk_atoms = c->d_chunk_atoms; p.tab.chunk_bound = c->d_chunk_bound;
     p.bcoef = c->bcoef; p.static_thr = c->static_thr; p.dynamic = c->dynamic; p.relaxed = c->relaxed;
-    p.grid_sptr = c->d_grid_sptr; p.grid_slist = c->d_grid_slist;
-    p.grid_ptr = c->d_grid_ptr; p.grid_list = c->d_grid_list; p.gx = c->gx; p.gy = c->gy; p.gz = c->gz;
-    p.grid_margin_sq = c->grid_margin * c->grid_margin;
+    p.n_grid_levels = c->n_grid_levels; p.gx = c->gx; p.gy = c->gy; p.gz = c->gz;
+    for (int l = 0; l < 2; ++l) {
+        p.grid[l].ptr = c->grid[l].ptr; p.grid[l].list = c->grid[l].list;
+        p.grid[l].sptr = c->grid[l].sptr; p.grid[l].slist = c->grid[l].slist;
+        p.grid[l].margin_sq = c->grid[l].margin * c->grid[l].margin;
+    }
     p.errkey = c->d_status; p.counters = c->d_status + 2;
     p.cid = c->d_cid; p.cw = c->d_cw; p.n_clusters = c->n_clusters;
     return SITB_OK;

@@ -191,7 +191,7 @@ __global__ void __launch_bounds__(DIAG ? SITB_K1_WARPS * 32 : 512) k_fill(const 
     uint16_t* cand = (uint16_t*)(wscratch + WARP_CAND);
     uint16_t* ek = (uint16_t*)(wscratch + WARP_EK);
     int* task_counter = (int*)(smem_raw + lay.off_task);
-    int* full_walk = (int*)(smem_raw + lay.off_flag);      // [FB] frame has a static atom beyond the grid margin
+    int* glevel = (int*)(smem_raw + lay.off_flag);         // [FB] grid level of the frame (n_levels: walk all landmarks)
     ushort4* tca = (ushort4*)(smem_raw + lay.off_ca);       // [Lpad/32] chunk skip table: atoms
     float4* tcb = (float4*)(smem_raw + lay.off_cb);         // [Lpad/32] chunk skip table: bounds
 
@@ -221,7 +221,8 @@ __global__ void __launch_bounds__(DIAG ? SITB_K1_WARPS * 32 : 512) k_fill(const 
     __syncthreads();
 
     unsigned long long loc_zero = 0, loc_nnz = 0, loc_rej = 0, loc_over = 0, loc_dup = 0, loc_full = 0;
-    const bool have_grid = DIAG && p.grid_ptr != nullptr;
+    const int n_levels = DIAG ? p.n_grid_levels : 0;
+    unsigned long long loc_loose = 0;
     const Cell& cell = p.cell;
     const float Lx = (float)cell.c[0], Ly = (float)cell.c[4], Lz = (float)cell.c[8];
     const int W = 4 * NB;
@@ -255,7 +256,7 @@ __global__ void __launch_bounds__(DIAG ? SITB_K1_WARPS * 32 : 512) k_fill(const 
         if (p.dynamic)
             for (int t = threadIdx.x; t < nb * Spad; t += blockDim.x) seen_all[t] = 0u;
         if (threadIdx.x == 0) *task_counter = 0;
-        if (threadIdx.x < FB) full_walk[threadIdx.x] = have_grid ? 0 : 1;
+        if (threadIdx.x < FB) glevel[threadIdx.x] = 0;
         __syncthreads();
 
         // ---- 2. static lattice (helpers.pyx:55-92) ---------------------------------------
@@ -270,7 +271,8 @@ __global__ void __launch_bounds__(DIAG ? SITB_K1_WARPS * 32 : 512) k_fill(const 
                 const double q = shifted_dist2<DIAG, false>(cell, pt[0], pt[1], pt[2], ox, oy, oz);
                 if (__dsqrt_rn(q) > p.static_thr)
                     atomicMin(p.errkey, make_error_key(gframe, PHASE_STATIC_MOVED, (unsigned)s));
-                if (q > p.grid_margin_sq) full_walk[b] = 1;
+                if (n_levels > 0 && q > p.grid[0].margin_sq)
+                    atomicMax(&glevel[b], (n_levels > 1 && !(q > p.grid[1].margin_sq)) ? 1 : n_levels);
             }
         } else {
             for (int t = warp; t < nb * S; t += nwarps) {
@@ -295,7 +297,9 @@ __global__ void __launch_bounds__(DIAG ? SITB_K1_WARPS * 32 : 512) k_fill(const 
                 if (lane == 0) {
                     atomicAdd(&seen_all[(size_t)b * Spad + bj], 1u);
                     lmap_all[(size_t)b * Spad + li] = (unsigned)bj;
-                    if (__dmul_rn(bd, bd) > p.grid_margin_sq) full_walk[b] = 1;
+                    const double bq = __dmul_rn(bd, bd);
+                    if (n_levels > 0 && bq > p.grid[0].margin_sq)
+                        atomicMax(&glevel[b], (n_levels > 1 && !(bq > p.grid[1].margin_sq)) ? 1 : n_levels);
                     if (bd > p.static_thr)
                         atomicMin(p.errkey, make_error_key(gframe, PHASE_STATIC_MOVED, (unsigned)li));
                 }
@@ -313,7 +317,10 @@ __global__ void __launch_bounds__(DIAG ? SITB_K1_WARPS * 32 : 512) k_fill(const 
         }
         __syncthreads();
         if (threadIdx.x == 0)
-            for (int b = 0; b < nb; ++b) loc_full += (unsigned long long)full_walk[b];
+            for (int b = 0; b < nb; ++b) {
+                loc_full += (unsigned long long)(glevel[b] >= n_levels);
+                loc_loose += (unsigned long long)(glevel[b] > 0 && glevel[b] < n_levels);
+            }
 
         // ---- 3. one warp per mobile atom, claimed from a per-batch counter ------------------
         for (;;) {
@@ -335,20 +342,21 @@ __global__ void __launch_bounds__(DIAG ? SITB_K1_WARPS * 32 : 512) k_fill(const 
             // 3a. screen distances static -> mobile (helpers.pyx:99-103, :174-178)
             float mx = 0.f, my = 0.f, mz = 0.f;
             int box = 0;
+            const int lv = glevel[b];
             if (DIAG) {
                 const float* fsb = fs + (size_t)b * 3 * Spad;
                 const float* fmb = fm + (size_t)b * 3 * Mpad;
                 mx = fmb[j]; my = fmb[Mpad + j]; mz = fmb[2 * Mpad + j];
-                if (!full_walk[b]) {
+                if (lv < n_levels) {
                     // the grid box of the mobile atom: only the static-lattice sites its candidate landmarks use
                     int ix = (int)(mx * (float)p.gx), iy = (int)(my * (float)p.gy), iz = (int)(mz * (float)p.gz);
                     ix = ix < 0 ? 0 : (ix >= p.gx ? p.gx - 1 : ix);
                     iy = iy < 0 ? 0 : (iy >= p.gy ? p.gy - 1 : iy);
                     iz = iz < 0 ? 0 : (iz >= p.gz ? p.gz - 1 : iz);
                     box = (ix * p.gy + iy) * p.gz + iz;
-                    const unsigned sbeg = __ldg(p.grid_sptr + box), send = __ldg(p.grid_sptr + box + 1);
+                    const unsigned sbeg = __ldg(p.grid[lv].sptr + box), send = __ldg(p.grid[lv].sptr + box + 1);
                     for (unsigned i = sbeg + lane; i < send; i += 32) {
-                        const int s = (int)__ldg(p.grid_slist + i);
+                        const int s = (int)__ldg(p.grid[lv].slist + i);
                         const int src = p.dynamic ? (int)lmap[s] : s;
                         const float cx = centre_frac(fsb[src] - mx) * Lx;
                         const float cy = centre_frac(fsb[Spad + src] - my) * Ly;
@@ -383,14 +391,14 @@ __global__ void __launch_bounds__(DIAG ? SITB_K1_WARPS * 32 : 512) k_fill(const 
 
             int nsurv = 0, ncand = 0;
             const int n_chunks = Lpad >> 5;
-            if (DIAG && !full_walk[b]) {
+            if (DIAG && lv < n_levels) {
                 // 3b'. candidates = the list of the grid box the mobile atom is in (sitb_tables.cu: k_grid_lists);
                 // every vertex of a candidate is screened at once (3c)
-                const unsigned beg = __ldg(p.grid_ptr + box), end = __ldg(p.grid_ptr + box + 1);
+                const unsigned beg = __ldg(p.grid[lv].ptr + box), end = __ldg(p.grid[lv].ptr + box + 1);
                 for (unsigned i0 = beg; i0 < end; i0 += 32) {
                     const unsigned i = i0 + lane;
                     const bool in = i < end;
-                    const int k = in ? (int)__ldg(p.grid_list + i) : 0;
+                    const int k = in ? (int)__ldg(p.grid[lv].list + i) : 0;
                     const ushort4 vv = tva[k];
                     const float4 bb = tba[k];
                     // (no short-circuit: four independent gathers and compares, no branches)
@@ -632,6 +640,7 @@ __global__ void __launch_bounds__(DIAG ? SITB_K1_WARPS * 32 : 512) k_fill(const 
             if (loc_rej) atomicAdd(&p.counters[CNT_SCREEN_REJECT], loc_rej);
             if (loc_dup) atomicAdd(&p.counters[CNT_DUP_NEAREST], loc_dup);
             if (loc_full) atomicAdd(&p.counters[CNT_FULL_WALK_FRAMES], loc_full);
+            if (loc_loose) atomicAdd(&p.counters[CNT_LOOSE_GRID_FRAMES], loc_loose);
         }
     }
 }

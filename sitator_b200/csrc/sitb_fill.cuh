@@ -20,7 +20,7 @@ static constexpr int MAX_VERTS = 8;
 
 // counters[] slots
 enum : int { CNT_ZERO_ROWS = 0, CNT_DUP_NEAREST = 1, CNT_LIST_OVERFLOW = 2, CNT_NNZ = 3,
-             CNT_SCREEN_REJECT = 4, CNT_ROWS = 5, CNT_FULL_WALK_FRAMES = 6, CNT_SLOTS = 8 };
+             CNT_SCREEN_REJECT = 4, CNT_ROWS = 5, CNT_FULL_WALK_FRAMES = 6, CNT_LOOSE_GRID_FRAMES = 7, CNT_SLOTS = 8 };
 
 // Landmark tables (built by sitb_tables.cu).  Vertex ids index the static lattice; a missing
 // vertex (the reference's -1 padding) is the dummy id S, whose screen distance is 0 and whose
@@ -54,6 +54,14 @@ struct HostTables {
     std::vector<int> internal_of;   // [L] caller's index -> internal
 };
 
+struct GridLevel {
+    const unsigned* ptr;         // [gx*gy*gz + 1] landmark lists
+    const uint16_t* list;        // internal landmark ids, ascending within a box
+    const unsigned* sptr;        // [gx*gy*gz + 1] the static-lattice sites those landmarks have as vertices
+    const uint16_t* slist;
+    double margin_sq;
+};
+
 struct FillParams {
     Cell cell;
     const double* frames;        // [n_frames][A][3] float64, unwrapped allowed
@@ -68,15 +76,12 @@ struct FillParams {
     double bcoef;                // steepness*midpoint
     double static_thr;           // static_movement_threshold
     int dynamic, relaxed;
-    // candidate lists per box of a gx*gy*gz grid over the (orthorhombic) cell (sitb_tables.cu: k_grid_lists); null: none.
-    // A frame whose static atoms all lie within sqrt(grid_margin_sq) of their ideal positions tests only the
-    // list of the box the mobile atom is in; other frames walk all landmarks.
-    const unsigned* grid_ptr;    // [gx*gy*gz + 1]
-    const uint16_t* grid_list;   // internal landmark ids, ascending within a box
-    const unsigned* grid_sptr;   // [gx*gy*gz + 1] the static-lattice sites those landmarks have as vertices
-    const uint16_t* grid_slist;
+    // candidate lists per box of a gx*gy*gz grid over the (orthorhombic) cell (sitb_tables.cu: k_grid_lists), for up to two
+    // margins of static-atom displacement (ascending).  A frame uses the first level whose margin covers its largest
+    // static displacement; a frame beyond the last margin walks all landmarks.  n_grid_levels = 0: no grid.
+    GridLevel grid[2];
+    int n_grid_levels;
     int gx, gy, gz;
-    double grid_margin_sq;
     unsigned long long* errkey;  // [2] atomicMin of make_error_key: [0] lattice errors, [1] zero landmark vectors
     unsigned long long* counters;
     // MODE_DENSE

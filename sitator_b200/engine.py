@@ -34,6 +34,7 @@ class EngineStatus(object):
         self.nnz = int(s.nnz)
         self.n_screen_rejects = int(s.n_screen_rejects)
         self.n_full_walk_frames = int(s.n_full_walk_frames)
+        self.n_loose_grid_frames = int(s.n_loose_grid_frames)
 
     def first_error(self, check_for_zeros):
         """(code, frame, index) of the first error in the reference's iteration order, or None."""

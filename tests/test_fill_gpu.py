@@ -192,7 +192,7 @@ def test_candidate_grid_does_not_change_results(name, n_frames, dynamic):
     system, cfg = syn.make_config(name)
     frames = system.trajectory(n_frames)
     results = []
-    for margin in (0.5, 0.0, 0.08):
+    for margin in (0.5, 0.0, 0.08, 0.22):
         eng = U.engine_for(system, dynamic_lattice_mapping=dynamic, candidate_grid_margin=margin)
         info = eng.candidate_grid_info()
         assert (info["entries"] > 0) == (margin > 0)
@@ -212,6 +212,8 @@ def test_candidate_grid_does_not_change_results(name, n_frames, dynamic):
     assert st_grid.n_full_walk_frames == 0
     assert st_none.n_full_walk_frames == n_frames
     assert 0 < st_tight.n_full_walk_frames <= n_frames        # sigma_static = 0.05 A: most frames exceed 0.08 A
+    # lists are kept for the margin and for half of it: at 0.22 A frames spread over both levels (and the full walk)
+    assert results[3][0].n_loose_grid_frames > 0 or name == "toy_bcc"
     for st, seen, rows in results[1:]:
         assert st.nnz == st_grid.nnz and st.n_zero_rows == st_grid.n_zero_rows
         assert np.array_equal(seen, results[0][1])
