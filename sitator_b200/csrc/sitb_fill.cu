@@ -37,7 +37,11 @@ namespace sitb {
 static constexpr size_t WARP_EV = 0;                                          // double[ENTRY_CAP]
 static constexpr size_t WARP_CAND = WARP_EV + sizeof(double) * ENTRY_CAP;     // uint16[CAND_CAP]
 static constexpr size_t WARP_EK = WARP_CAND + sizeof(uint16_t) * CAND_CAP;    // uint16[ENTRY_CAP]
-static constexpr size_t WARP_QFW = WARP_EK + sizeof(uint16_t) * ENTRY_CAP;    // float[qstride]
+static constexpr size_t WARP_POOL = WARP_EK + sizeof(uint16_t) * ENTRY_CAP;   // u64 offset, u32 entries left: the warp's
+                                                                              // current slice of the compressed-row pool
+static constexpr size_t WARP_QFW = WARP_POOL + 16;                            // float[qstride]
+static constexpr unsigned POOL_SLICE = 256;   // entries a warp reserves at a time (>= ENTRY_CAP): one global atomic per
+                                              // ~11 rows instead of one per row (5.6e6 atomics on one address per pass)
 
 struct SmemLayout {
     int Spad, Mpad, qstride;
@@ -190,6 +194,8 @@ __global__ void __launch_bounds__(DIAG ? SITB_K1_WARPS * 32 : 512) k_fill(const 
     int16_t* tcid = (int16_t*)(smem_raw + lay.off_cid);     // [Lpad] cluster of landmark (MODE_ASSIGN)
     uint16_t* cand = (uint16_t*)(wscratch + WARP_CAND);
     uint16_t* ek = (uint16_t*)(wscratch + WARP_EK);
+    unsigned long long* pool_off = (unsigned long long*)(wscratch + WARP_POOL);
+    unsigned* pool_left = (unsigned*)(wscratch + WARP_POOL + 8);
     int* task_counter = (int*)(smem_raw + lay.off_task);
     int* glevel = (int*)(smem_raw + lay.off_flag);         // [FB] grid level of the frame (n_levels: walk all landmarks)
     ushort4* tca = (ushort4*)(smem_raw + lay.off_ca);       // [Lpad/32] chunk skip table: atoms
@@ -217,7 +223,7 @@ __global__ void __launch_bounds__(DIAG ? SITB_K1_WARPS * 32 : 512) k_fill(const 
     const int hist_n = (MODE == MODE_ASSIGN) ? p.n_clusters : L;
     if (use_hist)
         for (int i = threadIdx.x; i < hist_n; i += blockDim.x) hist[i] = 0u;
-    if (lane == 0) qfw[S] = 0.f;                            // dummy vertex: passes every screen
+    if (lane == 0) { qfw[S] = 0.f; *pool_left = 0u; }       // dummy vertex: passes every screen
     __syncthreads();
 
     unsigned long long loc_zero = 0, loc_nnz = 0, loc_rej = 0, loc_over = 0, loc_dup = 0, loc_full = 0;
@@ -569,7 +575,15 @@ __global__ void __launch_bounds__(DIAG ? SITB_K1_WARPS * 32 : 512) k_fill(const 
                 if ((MODE == MODE_STATS || MODE == MODE_STAGE) && p.sparse_ptr) {
                     // keep the row in compressed form: later passes read ~250 B instead of recomputing it
                     unsigned long long off = 0;
-                    if (lane == 0) off = atomicAdd(p.sparse_cursor, (unsigned long long)nent);
+                    if (lane == 0) {
+                        if (*pool_left < (unsigned)nent) {         // next slice (the rest of the old one stays unused)
+                            *pool_off = atomicAdd(p.sparse_cursor, (unsigned long long)POOL_SLICE);
+                            *pool_left = POOL_SLICE;
+                        }
+                        off = *pool_off;
+                        *pool_off = off + (unsigned long long)nent;
+                        *pool_left -= (unsigned)nent;
+                    }
                     off = __shfl_sync(0xffffffffu, off, 0);
                     if (off + (unsigned long long)nent <= p.sparse_capacity) {
                         for (int e = lane; e < nent; e += 32) { p.sparse_k[off + e] = ek[e]; p.sparse_v[off + e] = ev[e]; }

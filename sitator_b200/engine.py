@@ -285,14 +285,16 @@ class LandmarkEngine(object):
         if gram is None and want_gram:
             gram = self._zeros((self.L, self.L), torch.float64)
         while True:
-            cap = int(n_rows * entries_per_row) + 1024
+            # (warps reserve the pool in slices of 256 entries and leave the tail of a slice unused at the end of a launch)
+            step = self.upload_chunk_frames() or self.n_frames
+            n_launches = (self.n_frames + step - 1) // step
+            cap = int(n_rows * entries_per_row) + 1024 + 256 * 32 * self.n_sms * n_launches
             rows = SparseRows(self._empty((n_rows,), torch.int64), self._empty((cap,), torch.int16),
                               self._empty((cap,), torch.float64), self._zeros((1,), torch.int64), cap, n_rows,
                               self.frame0 * self.M)
             seen_try = seen.clone()
             gram_try = None if gram_from_rows else gram.clone()
             # launched per upload chunk: each launch waits only for its own chunk of the host -> device copy
-            step = self.upload_chunk_frames() or self.n_frames
             for b in range(0, self.n_frames, step):
                 nb = min(step, self.n_frames - b)
                 _native.check(self._lib.sitb_pass_stats_cached(
