@@ -51,7 +51,10 @@ __device__ __forceinline__ double warp_sum(double x) {
 #define SITB_DP_FIT_WARPS 16
 #endif
 static constexpr int DP_FIT_WARPS = SITB_DP_FIT_WARPS;
-static constexpr int DP_FIT_UNROLL = (DP_FIT_WARPS >= 16) ? 2 : 4;   // candidates per warp and pass
+#ifndef SITB_DP_FIT_UNROLL
+#define SITB_DP_FIT_UNROLL ((SITB_DP_FIT_WARPS >= 16) ? 3 : 4)
+#endif
+static constexpr int DP_FIT_UNROLL = SITB_DP_FIT_UNROLL;   // candidates per warp and pass
 static constexpr int DP_SVAL_CANDS = 64;              // candidates whose gathered S values are kept for the commit
 
 __global__ void __launch_bounds__(32 * DP_FIT_WARPS) k_dotprod_fit(
