@@ -587,6 +587,7 @@ static int base_params(sitb_ctx* c, int64_t begin, int64_t n, FillParams& p, con
     p.n_work = n;
     p.frame0 = c->frame0 + begin;
     p.A = c->A; p.S = c->S; p.M = c->M; p.L = c->L; p.V = c->V; p.Lpad = c->Lpad; p.NB = c->NB;
+    p.m_magic = (c->M > 1 && c->M < 16384) ? (unsigned)((0x100000000ull + (unsigned long long)c->M - 1ull) / (unsigned long long)c->M) : 0u;
     p.static_idx = c->d_static_idx; p.mobile_idx = c->d_mobile_idx; p.ideal = c->d_ideal;
     p.tab.v0 = c->d_v0; p.tab.b0 = c->d_b0; p.tab.va = c->d_va; p.tab.ba = c->d_ba;
     p.tab.q64 = c->d_q64; p.tab.acoef = c->d_acoef; p.tab.nverts = c->d_nverts; p.tab.orig_of = c->d_orig_of;

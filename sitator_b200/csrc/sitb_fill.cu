@@ -334,10 +334,13 @@ __global__ void __launch_bounds__(DIAG ? SITB_K1_WARPS * 32 : 512) k_fill(const 
             if (lane == 0) jj = atomicAdd(task_counter, 1);
             jj = __shfl_sync(0xffffffffu, jj, 0);
             if (jj >= nb * M) break;
-            const int b = jj / M, j = jj - b * M;
+            // frame of the batch and mobile atom: jj / M by a multiply with ceil(2^32 / M) (exact for jj < 2^17, M < 2^14;
+            // a signed 32-bit division is ~35 instructions on the uniform datapath)
+            const int b = p.m_magic ? (int)__umulhi((unsigned)jj, p.m_magic) : jj / M;
+            const int j = jj - b * M;
             const long long fl = p.frame_list ? p.frame_list[w0 + b] : (w0 + b);
             const long long gframe = p.frame0 + fl;
-            const long long row_local = (w0 + b) * M + j;            // row in this launch's outputs
+            const long long row_local = w0 * M + jj;                 // = (w0 + b) * M + j: row in this launch's outputs
             const unsigned long long row_global = (unsigned long long)(gframe * M + j);
             const double* sb = ss + (size_t)b * S * 3;
             const unsigned* lmap = lmap_all + (size_t)b * Spad;

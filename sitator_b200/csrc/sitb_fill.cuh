@@ -69,6 +69,7 @@ struct FillParams {
     long long n_work;            // frames (or list entries) in this launch
     long long frame0;            // global index of frames[0]: row ids / error keys are global
     int A, S, M, L, V, Lpad, NB;
+    unsigned m_magic;            // ceil(2^32 / M) when M < 2^14 (task index -> frame of the batch), else 0
     const int* static_idx;       // [S] atom index of static lattice atom s
     const int* mobile_idx;       // [M]
     const double* ideal;         // [S][3] ideal static positions
