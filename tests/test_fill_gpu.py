@@ -221,7 +221,8 @@ def test_candidate_grid_does_not_change_results(name, n_frames, dynamic):
             assert np.array_equal(k0, k1) and np.array_equal(v0, v1)
 
 
-def test_dense_lattice_with_far_reaching_landmarks():
+@pytest.mark.parametrize("max_verts", [4, 7])
+def test_dense_lattice_with_far_reaching_landmarks(max_verts):
     """A dense lattice with far-reaching landmarks: dozens of static atoms inside every cut-off radius, long
     candidate lists per grid box (the opposite regime of the LLZO-shaped cases)."""
     import torch
@@ -237,7 +238,7 @@ def test_dense_lattice_with_far_reaching_landmarks():
     for c in centers:
         d = pbc.distances(c, static)
         order = np.argsort(d, kind="stable")
-        nv = int(rng.integers(2, 5))
+        nv = int(rng.integers(2, max_verts + 1))                   # 7: two blocks of four vertices per landmark
         verts.append(sorted(int(x) for x in order[8:8 + nv]))      # far vertices: cut-off radius ~ 4-5 A
     A = n_static + n_mobile
     static_idx = np.arange(n_static)
@@ -257,5 +258,9 @@ def test_dense_lattice_with_far_reaching_landmarks():
     eng = LandmarkEngine(cell, static_idx, mobile_idx, A, static, centers, verts)
     eng.set_frames(frames)
     got = eng.fill_dense(dtype=torch.float64).cpu().numpy()
-    assert np.count_nonzero(want) > 100
+    assert np.count_nonzero(want) > (100 if max_verts == 4 else 20)
     _compare_lv(got, want)
+    # and without the candidate grid (every landmark walked)
+    eng2 = LandmarkEngine(cell, static_idx, mobile_idx, A, static, centers, verts, candidate_grid_margin=0.0)
+    eng2.set_frames(frames)
+    assert np.array_equal(eng2.fill_dense(dtype=torch.float64).cpu().numpy(), got)
