@@ -200,6 +200,26 @@ class LandmarkEngine(object):
         self.n_frames = int(frames.shape[0])
         self.frame0 = int(frame0)
 
+    def unassigned_lattice_atoms(self, global_frame):
+        """Error reporting only (helpers.pyx:87-92): the static atoms of one frame that no static-lattice position
+        picked as its nearest atom, for ``StaticLatticeError.lattice_atoms``.  One frame, evaluated on the host with
+        the reference's own steps (PBCCalculator.pyx:64-103); None if the frame is not resident on this rank."""
+        local = int(global_frame) - self.frame0
+        fr = self._frames_keepalive
+        if fr is None or not (0 <= local < self.n_frames):
+            return None
+        frame = fr[local].cpu().numpy() if hasattr(fr, "cpu") else np.asarray(fr[local], dtype=np.float64)
+        statics = np.asarray(frame, dtype=np.float64)[self.static_idx]
+        seen = np.zeros(self.S, dtype=bool)
+        for li in range(self.S):
+            buf = statics + (self.cell_centroid - self.ideal_static[li])           # shift the lattice point to the centroid
+            f = buf @ self.cellmat_inv.T
+            f -= np.floor(f)
+            buf = f @ self.cellmat.T
+            d = np.sqrt(np.sum((buf - self.cell_centroid) ** 2, axis=1))
+            seen[int(np.argmin(d))] = True
+        return np.where(~seen)[0]
+
     def upload_chunk_frames(self):
         """Frames per chunk of the last set_frames() upload (0: frames borrowed from a device tensor)."""
         n = C.c_int64()

@@ -264,3 +264,28 @@ def test_dense_lattice_with_far_reaching_landmarks(max_verts):
     eng2 = LandmarkEngine(cell, static_idx, mobile_idx, A, static, centers, verts, candidate_grid_margin=0.0)
     eng2.set_frames(frames)
     assert np.array_equal(eng2.fill_dense(dtype=torch.float64).cpu().numpy(), got)
+
+
+def test_unassigned_static_atoms_are_reported():
+    """Dynamic lattice mapping with a static atom displaced onto another one: no lattice position picks it, and the
+    reference raises StaticLatticeError(lattice_atoms = the atoms no lattice position picked, frame) (helpers.pyx:87-92)."""
+    from oracle import landmark_oracle as orc
+    from sitator_b200.landmark import LandmarkAnalysis, StaticLatticeError
+    system, cfg = syn.make_config("lgps_dynamic")
+    frames = system.trajectory(12)
+    pbc = orc.PBC(system.cell)
+    d = pbc.distances(system.static_pos[4], system.static_pos)
+    second = int(np.argsort(d, kind="stable")[2])                      # [0] is position 4 itself, [1] its nearest neighbour
+    # in frame 7 atom 4 sits on the second-nearest neighbour of its lattice position: position 4 then picks its nearest
+    # neighbour's atom, and nobody picks atom 4
+    frames[7, system.static_idx[4]] = frames[7, system.static_idx[second]] + 0.01
+    with pytest.raises(orc.StaticLatticeFailure) as o:
+        orc.fill_landmark_vectors(system.cell, system.static_pos, system.static_idx, system.mobile_idx, system.lm_centers,
+                                  system.lm_vertices, frames, dynamic_lattice_mapping=True, static_movement_threshold=50.0)
+    assert o.value.frame == 7 and o.value.kind == "unassigned"
+    la = LandmarkAnalysis(clustering_algorithm='mcl', verbose=False, dynamic_lattice_mapping=True, max_mobile_per_site=2,
+                          static_movement_threshold=50.0)
+    with pytest.raises(StaticLatticeError) as e:
+        la.run(syn.site_network_for(system), frames)
+    assert e.value.frame == 7
+    assert list(e.value.lattice_atoms) == list(o.value.lattice_atoms) == [4]
