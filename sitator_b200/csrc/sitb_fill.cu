@@ -682,7 +682,11 @@ static cudaError_t launch_one(const FillParams& p, int n_sms, cudaStream_t strea
     int best_w = 0, best_fb = 1;
     size_t best_bytes = 0;
     double best_score = -1.0;
+#ifdef SITB_K1_FORCE_CTAS
+    for (int ctas = SITB_K1_FORCE_CTAS; ctas >= SITB_K1_FORCE_CTAS; --ctas) {
+#else
     for (int ctas = 2; ctas >= 1; --ctas) {
+#endif
         const size_t budget = (size_t)(227 * 1024) / ctas - 1024;
         for (int w = max_w; w >= 1; --w) {
             if (w * ctas > 64 || w * ctas > reg_warps) continue;
@@ -695,7 +699,7 @@ static cudaError_t launch_one(const FillParams& p, int n_sms, cudaStream_t strea
             }
             if (!fb_fit) continue;
             const double fill = (double)(fb_fit * p.M) / (3.0 * w);
-            const double score = (double)(ctas * w) * (fill < 1.0 ? fill : 1.0) + 0.01 * ctas;
+            const double score = (double)(ctas * w) * (fill < 1.0 ? fill : 1.0) - 0.01 * ctas;   // equal warps: one CTA with longer batches measured faster
             if (score > best_score) { best_score = score; best_w = w; best_fb = fb_fit; best_bytes = bytes_fit; }
         }
     }
