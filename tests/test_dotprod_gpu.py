@@ -64,3 +64,55 @@ def test_fit_centers_matches_oracle_on_a_longer_trajectory():
     assert np.array_equal(got_n, want_n)
     assert np.array_equal(got_c != 0, want_c != 0)
     assert np.max(np.abs(got_c - want_c)) < 1e-12
+
+
+@pytest.mark.parametrize("threshold", [0.9, 0.999])
+def test_fit_centers_many_centres_and_growing_tables(threshold):
+    """A high clustering threshold makes hundreds to thousands of centres: the per-landmark centre lists and the
+    centre table outgrow their first sizes and the fit reruns with larger ones; the result is still the oracle's."""
+    from oracle import landmark_oracle as orc
+    from sitator_b200.landmark.source import LandmarkVectorSource
+    from sitator_b200.landmark.cluster import dotprod
+    system, cfg = syn.make_config("llzo")
+    frames = system.trajectory(40)
+    lv, _, _ = orc.fill_landmark_vectors(system.cell, system.static_pos, system.static_idx, system.mobile_idx,
+                                         system.lm_centers, system.lm_vertices, frames, check_for_zeros=False)
+    want_c, want_n = orc.dotprod_fit_centers(lv, threshold)
+    eng = U.engine_for(system)
+    eng.set_frames(frames)
+    src = LandmarkVectorSource(eng)
+    dotprod.first_pass(src)
+    got_c, got_n = dotprod.fit_centers(src, threshold)
+    assert got_c.shape == want_c.shape, (got_c.shape, want_c.shape)
+    assert np.array_equal(got_n, want_n)
+    assert np.array_equal(got_c != 0, want_c != 0)
+    assert np.max(np.abs(got_c - want_c)) < 1e-12
+
+
+def test_fit_centers_when_the_first_row_is_all_zero():
+    """NumPy's arg-max over NaN similarities sends every row to cluster 0 while centre 0 is the zero vector
+    (DotProdClassifier.pyx:241-248): a trajectory whose very first landmark vector is all zero exercises that."""
+    from oracle import landmark_oracle as orc
+    from sitator_b200.landmark.source import LandmarkVectorSource
+    from sitator_b200.landmark.cluster import dotprod
+    system, cfg = syn.make_config("toy_bcc")
+    full = system.trajectory(300)
+    lv_full, _, _ = orc.fill_landmark_vectors(system.cell, system.static_pos, system.static_idx, system.mobile_idx,
+                                              system.lm_centers, system.lm_vertices, full, check_for_zeros=False)
+    zero_rows = np.where(~lv_full.any(axis=1))[0]
+    f, j = int(zero_rows[0]) // system.n_mobile, int(zero_rows[0]) % system.n_mobile
+    frames = full[:120].copy()
+    frames[0, system.mobile_idx[0]] = full[f, system.mobile_idx[j]]           # mobile 0 of frame 0 <- that stray atom
+    frames[0, system.static_idx] = full[f, system.static_idx]
+    lv, _, _ = orc.fill_landmark_vectors(system.cell, system.static_pos, system.static_idx, system.mobile_idx,
+                                         system.lm_centers, system.lm_vertices, frames, check_for_zeros=False)
+    assert not lv[0].any()
+    want_c, want_n = orc.dotprod_fit_centers(lv, 0.45)
+    eng = U.engine_for(system)
+    eng.set_frames(frames)
+    src = LandmarkVectorSource(eng)
+    dotprod.first_pass(src)
+    got_c, got_n = dotprod.fit_centers(src, 0.45)
+    assert got_c.shape == want_c.shape
+    assert np.array_equal(got_n, want_n)
+    assert np.max(np.abs(got_c - want_c)) < 1e-12
