@@ -59,12 +59,10 @@ __device__ __forceinline__ double rowdot(const double* __restrict__ m, int d, do
                      __dmul_rn(m[3 * d + 2], p2));
 }
 
-// x - floor(x) for x in [-1, 2): floor is -1, 0 or 1, picked with two compares.  Callers use it
-// only for the fractional coordinate of (static + centroid - mobile) with both atoms already
-// wrapped into the cell (step 1 of K1), which lies in [-0.5, 1.5] up to rounding.
+// x - floor(x), as the reference computes it (PBCCalculator.pyx:358-360).  Callers use it for the fractional
+// coordinate of (static + centroid - mobile) with both atoms already wrapped into the cell (step 1 of K1).
 __device__ __forceinline__ double frac_near(double f) {
-    const double fl = (f >= 1.0) ? 1.0 : ((f < 0.0) ? -1.0 : 0.0);
-    return __dsub_rn(f, fl);
+    return __dsub_rn(f, floor(f));      // FRND.F64.FLOOR + DADD: two instructions (two compares and selects were six)
 }
 
 // PBCCalculator.wrap_points for one point (general triclinic cell). NEAR: |frac| is small.
