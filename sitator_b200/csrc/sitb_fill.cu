@@ -104,6 +104,11 @@ __constant__ double c_exp[14] = {
     0.00019841269863053618, 0.0013888888917213717, 0.0083333333333300615, 0.041666666666624129,
     0.16666666666666669, 0.50000000000000011};
 
+// MUFU seeds without the library's denormal handling (the arguments are normal floats here)
+__device__ __forceinline__ float rsqrt_approx(float x) { float y; asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float lg2_approx(float x) { float y; asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float ex2_approx(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+
 // exp(x) for |x| < 700 (no overflow / underflow handling)
 __device__ __forceinline__ double exp_bounded(double x) {
     const double t = fma(x, c_exp[0], c_exp[1]);
@@ -121,7 +126,7 @@ __device__ __forceinline__ double exp_bounded(double x) {
 
 // sqrt(q) for 1e-30 < q < 1e30: float reciprocal-square-root seed, two coupled Newton steps, one correction
 __device__ __forceinline__ double sqrt_bounded(double q) {
-    const double y = (double)rsqrtf((float)q);
+    const double y = (double)rsqrt_approx((float)q);
     double g = q * y, h = 0.5 * y;
     double r = fma(-g, h, 0.5);
     g = fma(g, r, g); h = fma(h, r, h);
@@ -133,7 +138,7 @@ __device__ __forceinline__ double sqrt_bounded(double q) {
 // P^(-1/n) for 1 <= P < 3e38, 1 <= n <= 8: float seed, two Newton steps on y^-n = P (same code for every n)
 __device__ __forceinline__ double inv_root(double P, int n) {
     const float rn = __fdividef(1.0f, (float)n);     // approximate is enough: it only scales the Newton step
-    double y = (double)exp2f(-__log2f((float)P) * rn);
+    double y = (double)ex2_approx(-lg2_approx((float)P) * rn);
     const double rnd = (double)rn;
 #pragma unroll
     for (int it = 0; it < 2; ++it) {
