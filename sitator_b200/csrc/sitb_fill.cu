@@ -295,9 +295,54 @@ __global__ void __launch_bounds__(DIAG ? SITB_K1_WARPS * 32 : 512) k_fill(const 
                 const double oz = __dsub_rn(cell.cen[2], p.ideal[3 * li + 2]);
                 double bd = CUDART_INF;
                 int bj = 0x7FFFFFFF;
-                for (int j = lane; j < S; j += 32) {
-                    const double d = __dsqrt_rn(shifted_dist2<DIAG, false>(cell, sb[3 * j], sb[3 * j + 1], sb[3 * j + 2], ox, oy, oz));
-                    if (d < bd) { bd = d; bj = j; }           // first minimum within the lane
+                if (DIAG) {
+                    // FP32 screen first: only atoms whose float distance is within the float error of the smallest one can
+                    // be the exact arg-min (normally one atom), and only those get the exact double evaluation
+                    const float* fsb = fs + (size_t)b * 3 * Spad;
+                    double i0 = __dmul_rn(cell.ci[0], p.ideal[3 * li + 0]), i1 = __dmul_rn(cell.ci[4], p.ideal[3 * li + 1]),
+                           i2 = __dmul_rn(cell.ci[8], p.ideal[3 * li + 2]);
+                    const float fx = (float)(i0 - floor(i0)), fy = (float)(i1 - floor(i1)), fz = (float)(i2 - floor(i2));
+                    float q32[8];                                   // up to 256 static atoms take the screened route
+                    float qmin = CUDART_INF_F;
+                    const int n_it = (S + 31) >> 5;
+                    if (n_it <= 8) {
+#pragma unroll
+                        for (int it = 0; it < 8; ++it) {
+                            const int j = lane + 32 * it;
+                            q32[it] = CUDART_INF_F;
+                            if (it < n_it && j < S) {
+                                const float cx = centre_frac(fsb[j] - fx) * Lx;
+                                const float cy = centre_frac(fsb[Spad + j] - fy) * Ly;
+                                const float cz = centre_frac(fsb[2 * Spad + j] - fz) * Lz;
+                                q32[it] = fmaf(cz, cz, fmaf(cy, cy, cx * cx));
+                                qmin = fminf(qmin, q32[it]);
+                            }
+                        }
+#pragma unroll
+                        for (int o = 16; o > 0; o >>= 1) qmin = fminf(qmin, __shfl_xor_sync(0xffffffffu, qmin, o));
+                        // float error of a squared distance q (sitb_tables.cu: screen_bound), twice, for both sides
+                        const float lmax = fmaxf(Lx, fmaxf(Ly, Lz));
+                        const float dc = 24.0f * 5.9604644775390625e-08f * lmax;
+                        const float bound = qmin + 2.0f * (2.0f * sqrtf(3.0f * qmin) * dc + 3.0f * dc * dc + 1e-6f * qmin) + 1e-12f;
+#pragma unroll
+                        for (int it = 0; it < 8; ++it) {
+                            const int j = lane + 32 * it;
+                            if (it < n_it && j < S && !(q32[it] > bound)) {
+                                const double d = __dsqrt_rn(shifted_dist2<DIAG, false>(cell, sb[3 * j], sb[3 * j + 1], sb[3 * j + 2], ox, oy, oz));
+                                if (d < bd) { bd = d; bj = j; }   // first minimum within the lane (j ascends)
+                            }
+                        }
+                    } else {
+                        for (int j = lane; j < S; j += 32) {
+                            const double d = __dsqrt_rn(shifted_dist2<DIAG, false>(cell, sb[3 * j], sb[3 * j + 1], sb[3 * j + 2], ox, oy, oz));
+                            if (d < bd) { bd = d; bj = j; }
+                        }
+                    }
+                } else {
+                    for (int j = lane; j < S; j += 32) {
+                        const double d = __dsqrt_rn(shifted_dist2<DIAG, false>(cell, sb[3 * j], sb[3 * j + 1], sb[3 * j + 2], ox, oy, oz));
+                        if (d < bd) { bd = d; bj = j; }           // first minimum within the lane
+                    }
                 }
 #pragma unroll
                 for (int o = 16; o > 0; o >>= 1) {            // argmin, ties -> lower index (np.argmin)
