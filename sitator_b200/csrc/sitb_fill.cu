@@ -228,7 +228,7 @@ __global__ void __launch_bounds__(DIAG ? SITB_K1_WARPS * 32 : 512) k_fill(const 
     const int hist_n = (MODE == MODE_ASSIGN) ? p.n_clusters : L;
     if (use_hist)
         for (int i = threadIdx.x; i < hist_n; i += blockDim.x) hist[i] = 0u;
-    if (lane == 0) { qfw[S] = 0.f; *pool_left = 0u; }       // dummy vertex: passes every screen
+    if (lane == 0) { qfw[S] = 0.f; *pool_left = 0u; *pool_off = 0ull; }   // dummy vertex: passes every screen
     __syncthreads();
 
     unsigned long long loc_zero = 0, loc_nnz = 0, loc_rej = 0, loc_over = 0, loc_dup = 0, loc_full = 0;
@@ -628,7 +628,7 @@ __global__ void __launch_bounds__(DIAG ? SITB_K1_WARPS * 32 : 512) k_fill(const 
                 if ((MODE == MODE_STATS || MODE == MODE_STAGE) && p.sparse_ptr) {
                     // keep the row in compressed form: later passes read ~250 B instead of recomputing it
                     unsigned long long off = 0;
-                    if (lane == 0) {
+                    if (lane == 0 && nent > 0) {                   // (an all-zero row needs no space: offset 0, count 0)
                         if (*pool_left < (unsigned)nent) {         // next slice (the rest of the old one stays unused)
                             *pool_off = atomicAdd(p.sparse_cursor, (unsigned long long)POOL_SLICE);
                             *pool_left = POOL_SLICE;
