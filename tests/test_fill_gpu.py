@@ -80,6 +80,8 @@ def test_tables_and_dense_fill_match_oracle(name, n_frames):
         off, n = int(ptr[r] >> np.uint64(8)), int(ptr[r] & np.uint64(0xFF))
         rebuilt[r, k[off:off + n]] = v[off:off + n]
         assert np.array_equal(rebuilt[r], got64[r])
+    # every row's entry count is its number of non-zero components (all-zero rows: count 0, no pool space)
+    assert np.array_equal((ptr & np.uint64(0xFF)).astype(np.int64), np.count_nonzero(want, axis=1))
     assert np.array_equal(seen.cpu().numpy(), np.count_nonzero(want, axis=0))
     G = gram.cpu().numpy()
     Gw = np.triu(want.T @ want)
