@@ -95,6 +95,8 @@ struct sitb_ctx {
     GridLevelDev grid[2];             // [0] half the margin, [1] the margin
     int n_grid_levels = 0;
     double* d_rmax = nullptr;
+    double* d_ideal_wrapped = nullptr;   // static-lattice positions wrapped into the cell (grid builder)
+    double* d_radius = nullptr;          // [Lpad][4NB] cut-off radii sqrt(Q) (grid builder; < 0: degenerate)
     int gx = 0, gy = 0, gz = 0;
     // centres
     int* d_cid = nullptr;
@@ -133,7 +135,7 @@ static void free_ctx(sitb_ctx* c) {
         pool_free(c->grid[l].ptr, c->stream); pool_free(c->grid[l].list, c->stream);
         pool_free(c->grid[l].sptr, c->stream); pool_free(c->grid[l].slist, c->stream);
     }
-    pool_free(c->d_rmax, c->stream);
+    pool_free(c->d_rmax, c->stream); pool_free(c->d_ideal_wrapped, c->stream); pool_free(c->d_radius, c->stream);
     pool_free(c->d_verts_in, c->stream); pool_free(c->d_svd, c->stream); pool_free(c->d_qorig, c->stream); pool_free(c->d_orig_of, c->stream); pool_free(c->d_v0, c->stream); pool_free(c->d_b0, c->stream); pool_free(c->d_va, c->stream); pool_free(c->d_ba, c->stream);
     pool_free(c->d_q64, c->stream); pool_free(c->d_acoef, c->stream); pool_free(c->d_nverts, c->stream); pool_free(c->d_cid, c->stream); pool_free(c->d_cw, c->stream); pool_free(c->d_cid_orig, c->stream); pool_free(c->d_cw_orig, c->stream); pool_free(c->d_frames_owned, c->stream); pool_free(c->d_frames_f32, c->stream); pool_free(c->d_status, c->stream);
     delete c;
@@ -262,6 +264,20 @@ extern "C" int sitb_create(const sitb_network_desc* d, int device, sitb_ctx** ou
         CKC(upload(&c->d_chunk_atoms, ht.chunk_atoms.data(), ht.chunk_atoms.size(), c->stream));
         CKC(upload(&c->d_chunk_bound, ht.chunk_bound.data(), ht.chunk_bound.size(), c->stream));
         CKC(upload(&c->d_rmax, ht.rmax.data(), ht.rmax.size(), c->stream));
+        {
+            // what the grid builder reads per (box, landmark, vertex): wrapped Cartesian positions and radii, once
+            std::vector<double> iw((size_t)c->S * 3, 0.0), rad(ht.q64.size());
+            if (c->cell.diag)
+                for (int s = 0; s < c->S; ++s)
+                    for (int k = 0; k < 3; ++k) {
+                        double f = c->cell.ci[4 * k] * d->host_ideal_static[3 * s + k];
+                        f -= std::floor(f);
+                        iw[(size_t)s * 3 + k] = f * c->cell.c[4 * k];
+                    }
+            for (size_t i = 0; i < rad.size(); ++i) rad[i] = (ht.q64[i] >= 0.0) ? std::sqrt(ht.q64[i]) : -1.0;
+            CKC(upload(&c->d_ideal_wrapped, iw.data(), iw.size(), c->stream));
+            CKC(upload(&c->d_radius, rad.data(), rad.size(), c->stream));
+        }
         c->internal_of = ht.internal_of;
         CKC(upload(&c->d_v0, ht.v0.data(), ht.v0.size(), c->stream));
         CKC(upload(&c->d_b0, ht.b0.data(), ht.b0.size(), c->stream));
@@ -295,9 +311,9 @@ static int build_grid_level(sitb_ctx* c, const int g[3], double margin, GridLeve
         unsigned* d_count = nullptr;
         CK(pool_alloc((void**)&d_count, sizeof(unsigned) * cells, c->stream));
         cudaError_t e = pass == 0
-            ? launch_grid_lists(c->cell, c->d_ideal, c->d_va, c->d_q64, c->L, c->Lpad, c->NB, c->S, g[0], g[1], g[2], margin,
+            ? launch_grid_lists(c->cell, c->d_ideal_wrapped, c->d_va, c->d_radius, c->L, c->Lpad, c->NB, c->S, g[0], g[1], g[2], margin,
                                 nullptr, d_count, nullptr, c->stream)
-            : launch_grid_static_lists(c->cell, c->d_ideal, c->d_rmax, c->S, g[0], g[1], g[2], margin, nullptr, d_count, nullptr,
+            : launch_grid_static_lists(c->cell, c->d_ideal_wrapped, c->d_rmax, c->S, g[0], g[1], g[2], margin, nullptr, d_count, nullptr,
                                        c->stream);
         std::vector<unsigned> ptr(cells + 1, 0u);
         if (e == cudaSuccess) e = cudaMemcpyAsync(ptr.data() + 1, d_count, sizeof(unsigned) * cells, cudaMemcpyDeviceToHost, c->stream);
@@ -312,11 +328,11 @@ static int build_grid_level(sitb_ctx* c, const int g[3], double margin, GridLeve
         CK(upload(d_ptr, ptr.data(), cells + 1, c->stream));
         CK(pool_alloc((void**)d_list, sizeof(uint16_t) * (size_t)(total ? total : 1), c->stream));
         if (pass == 0) {
-            CK(launch_grid_lists(c->cell, c->d_ideal, c->d_va, c->d_q64, c->L, c->Lpad, c->NB, c->S, g[0], g[1], g[2], margin,
+            CK(launch_grid_lists(c->cell, c->d_ideal_wrapped, c->d_va, c->d_radius, c->L, c->Lpad, c->NB, c->S, g[0], g[1], g[2], margin,
                                  *d_ptr, nullptr, *d_list, c->stream));
             out.entries = total;
         } else {
-            CK(launch_grid_static_lists(c->cell, c->d_ideal, c->d_rmax, c->S, g[0], g[1], g[2], margin, *d_ptr, nullptr, *d_list,
+            CK(launch_grid_static_lists(c->cell, c->d_ideal_wrapped, c->d_rmax, c->S, g[0], g[1], g[2], margin, *d_ptr, nullptr, *d_list,
                                         c->stream));
             out.static_entries = total;
         }

@@ -78,6 +78,7 @@ cudaError_t launch_tables(const Cell& cell, const double* centers, const double*
 // box the mobile atom is in (~6 % of the landmarks at the LLZO shape) instead of walking all of them; a
 // frame with a static atom beyond the margin walks all landmarks as before.  One warp per box; lists
 // are in ascending internal landmark order, the same order the full walk produces.
+// (ideal = the static-lattice positions wrapped into the cell, Cartesian; q64 holds the cut-off RADII sqrt(Q) here)
 __global__ void k_grid_lists(Cell cell, const double* __restrict__ ideal, const ushort4* __restrict__ va,
                              const double* __restrict__ q64, int L, int Lpad, int NB, int S, int gx, int gy, int gz,
                              double margin, const unsigned* __restrict__ ptr, unsigned* __restrict__ count,
@@ -87,6 +88,7 @@ __global__ void k_grid_lists(Cell cell, const double* __restrict__ ideal, const 
     if (id >= (long long)gx * gy * gz) return;
     const int iz = (int)(id % gz), iy = (int)((id / gz) % gy), ix = (int)(id / ((long long)gz * gy));
     const double len[3] = {cell.c[0], cell.c[4], cell.c[8]};
+    const double inv_len[3] = {1.0 / len[0], 1.0 / len[1], 1.0 / len[2]};
     const double half[3] = {0.5 * len[0] / gx, 0.5 * len[1] / gy, 0.5 * len[2] / gz};
     const double mid[3] = {(2 * ix + 1) * half[0], (2 * iy + 1) * half[1], (2 * iz + 1) * half[2]};
     const int W = 4 * NB;
@@ -100,15 +102,14 @@ __global__ void k_grid_lists(Cell cell, const double* __restrict__ ideal, const 
             const unsigned vs[4] = {vv.x, vv.y, vv.z, vv.w};
             for (int h = 0; h < 4 && in; ++h) {
                 if (vs[h] == (unsigned)S) continue;
-                const double Q = q64[(size_t)k * W + 4 * blk + h];
-                if (!(Q >= 0.0)) { in = false; break; }           // degenerate landmark: never non-zero
-                const double r = sqrt(Q) + margin;
+                const double R = q64[(size_t)k * W + 4 * blk + h];
+                if (!(R >= 0.0)) { in = false; break; }           // degenerate landmark: never non-zero
+                const double r = R + margin;
                 double d2 = 0.0;
+#pragma unroll
                 for (int d = 0; d < 3; ++d) {
-                    double f = cell.ci[4 * d] * ideal[3 * vs[h] + d];
-                    f -= floor(f);
-                    double x = f * len[d] - mid[d];
-                    x -= len[d] * rint(x / len[d]);
+                    double x = ideal[3 * vs[h] + d] - mid[d];
+                    x -= len[d] * rint(x * inv_len[d]);           // |x| <= len/2 (+ one rounding: covered by the margin's slack)
                     const double a = fmax(fabs(x) - half[d], 0.0);
                     d2 += a * a;
                 }
@@ -133,6 +134,7 @@ __global__ void k_grid_static_lists(Cell cell, const double* __restrict__ ideal,
     if (id >= (long long)gx * gy * gz) return;
     const int iz = (int)(id % gz), iy = (int)((id / gz) % gy), ix = (int)(id / ((long long)gz * gy));
     const double len[3] = {cell.c[0], cell.c[4], cell.c[8]};
+    const double inv_len[3] = {1.0 / len[0], 1.0 / len[1], 1.0 / len[2]};
     const double half[3] = {0.5 * len[0] / gx, 0.5 * len[1] / gy, 0.5 * len[2] / gz};
     const double mid[3] = {(2 * ix + 1) * half[0], (2 * iy + 1) * half[1], (2 * iz + 1) * half[2]};
     const unsigned base = ptr ? ptr[id] : 0u;
@@ -146,11 +148,10 @@ __global__ void k_grid_static_lists(Cell cell, const double* __restrict__ ideal,
                 in = false;                                       // not a vertex of any landmark
             } else {
                 double d2 = 0.0;
+#pragma unroll
                 for (int d = 0; d < 3; ++d) {
-                    double f = cell.ci[4 * d] * ideal[3 * s + d];
-                    f -= floor(f);
-                    double x = f * len[d] - mid[d];
-                    x -= len[d] * rint(x / len[d]);
+                    double x = ideal[3 * s + d] - mid[d];
+                    x -= len[d] * rint(x * inv_len[d]);
                     const double a = fmax(fabs(x) - half[d], 0.0);
                     d2 += a * a;
                 }
