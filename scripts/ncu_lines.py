@@ -37,10 +37,13 @@ for f in sorted(os.listdir(tmp)):
         break
 csvtxt = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
 rows = list(csv.reader(csvtxt.splitlines()))
-hi = [i for i, r in enumerate(rows) if len(r) > 1 and r[0] == "Address"][0]
+his = [i for i, r in enumerate(rows) if len(r) > 1 and r[0] == "Address"]
+which = int(os.environ.get("NCU_LAUNCH", "0"))          # which captured launch of the report to read
+hi = his[which]
+rows = rows[:his[which + 1]] if which + 1 < len(his) else rows
 hdr = rows[hi]
 ix_i, ix_s, ix_t = hdr.index("Instructions Executed"), hdr.index("# Samples"), hdr.index("Thread Instructions Executed")
-sass = [(r[1], int(r[ix_i]), int(r[ix_s]), int(r[ix_t])) for r in rows[hi + 1:] if len(r) > ix_t]
+sass = [(r[1], int(r[ix_i]), int(r[ix_s]), int(r[ix_t])) for r in rows[hi + 1:] if len(r) > ix_t and r[ix_i].isdigit()]
 print("sass instrs: ncu %d, nvdisasm %d" % (len(sass), len(lines)))
 n = min(len(sass), len(lines))
 agg = {}

@@ -15,20 +15,20 @@
 
 namespace sitb {
 
-// Per-warp private (value bits, row) tables in shared memory: a warp walks its rows in ascending order,
-// so "first row among equal values" is simply "do not replace on equality"; no atomics, no locks.
+// Per-warp private (value bits, row) tables in shared memory, merged per CTA at the end: "first row among equal
+// values" is kept explicitly (larger value, or equal value and lower row).
 struct WarpBest {
     unsigned long long* val;     // [C] of this warp
     unsigned long long* row;
     __device__ __forceinline__ void update(int c, double v, unsigned long long r) {
         const unsigned long long vb = (unsigned long long)__double_as_longlong(v);
-        if (vb > val[c]) { val[c] = vb; row[c] = r; }
+        if (vb > val[c] || (vb == val[c] && vb != 0ull && r < row[c])) { val[c] = vb; row[c] = r; }
     }
 };
 
 template <int NCH>
 __device__ __forceinline__ void assign_row(
-    long long r, int nent, unsigned long long off, int lane, const uint16_t* __restrict__ pk,
+    long long r, int nent, unsigned long long off, int lane, int k0, double v0, const uint16_t* __restrict__ pk,
     const double* __restrict__ pv, long long row0, int L, const int* __restrict__ cid, const double* __restrict__ cw,
     double thr, long long* __restrict__ labels, double* __restrict__ confs, unsigned long long* counts, unsigned* hist,
     unsigned long long* best_scratch, WarpBest& wb, double* __restrict__ rep, double* __restrict__ rep_w,
@@ -41,8 +41,8 @@ __device__ __forceinline__ void assign_row(
             const int e = 32 * c + lane;
             myc[c] = -1; mypr[c] = 0.0; myv[c] = 0.0; myk[c] = 0;
             if (e < nent) {
-                const int k = pk[off + e];
-                const double v = pv[off + e];
+                const int k = c == 0 ? k0 : (int)pk[off + e];          // the first 32 entries were prefetched
+                const double v = c == 0 ? v0 : pv[off + e];
                 myk[c] = k; myv[c] = v;
                 myc[c] = __ldg(cid + k);
                 mypr[c] = v * __ldg(cw + k);
@@ -87,13 +87,52 @@ __device__ __forceinline__ void assign_row(
         }
 }
 
-__global__ void __launch_bounds__(256) k_assign_sparse(
+// ---- lane-per-row assign ------------------------------------------------------------------------------------
+// A warp takes 32 consecutive rows.  Staging: row by row (16 rows' loads in flight), lane j loads entry j
+// (coalesced) into the row's padded line of shared memory.  Then every lane walks ITS row out of shared memory
+// and keeps the row's per-cluster sums in LR_SLOTS register slots.  No shuffles or warp reductions per row:
+// ~110 warp instructions per row instead of ~300 for the warp-per-row peel loop (ncu: that one issues 70 % of
+// its cycles, so instructions are its cost).
+// A row with more than 32 entries or more than LR_SLOTS clusters is "hard" (a property of the row alone, so a
+// row takes the same path -- and sums in the same order -- however the trajectory is sharded); the warp handles
+// those afterwards with assign_row.
+// Measured alternatives (100 000 LLZO frames, passes B / C / D of scripts/profile_run.py, ms): warp-per-row
+// 3.15 / 2.12 / 3.27; this kernel 2.81 / 1.83 / 2.72; the same with the centre-table look-ups moved into the
+// staging step, rows up to 64 entries in the lane path and a row-wise sweep for the representative vectors
+// 2.86 / 1.93 / 3.41.
+static constexpr int LR_SLOTS = 12;
+static constexpr int LR_KSTRIDE = 34;      // uint16 per staged row (17 words: conflict-free lane-per-row reads)
+static constexpr int LR_VSTRIDE = 33;      // doubles per staged row
+static constexpr size_t LR_STAGE_BYTES = 32 * LR_VSTRIDE * sizeof(double) + 32 * LR_KSTRIDE * sizeof(uint16_t) + 16;
+
+// (value, first row) table updates from many lanes at once: raise the value with atomicMax and invalidate the row
+// if this lane raised it; after a __syncwarp every lane that holds the final value atomicMins its row.
+__device__ __forceinline__ void table_raise(WarpBest& t, int c, unsigned long long vb) {
+    const unsigned long long old = atomicMax(&t.val[c], vb);
+    if (old < vb) t.row[c] = ~0ull;
+}
+__device__ __forceinline__ void table_claim(WarpBest& t, int c, unsigned long long vb, unsigned long long r) {
+    if (vb != 0ull && vb == t.val[c]) atomicMin(&t.row[c], r);
+}
+
+// add one entry's product to the lane's slot of its cluster (slots fill in order: the first free one appends)
+__device__ __forceinline__ bool slot_add(int (&sid)[LR_SLOTS], double (&ssum)[LR_SLOTS], int c, double pr) {
+    bool done = false;
+#pragma unroll
+    for (int q = 0; q < LR_SLOTS; ++q) {
+        const bool hit = !done && (sid[q] == c || sid[q] < 0);
+        if (hit) { sid[q] = c; ssum[q] += pr; done = true; }
+    }
+    return done;
+}
+
+__global__ void __launch_bounds__(128) k_assign_sparse(
     const unsigned long long* __restrict__ row_ptr, const uint16_t* __restrict__ pk, const double* __restrict__ pv,
     long long n_rows, long long row0, int L, const int* __restrict__ cid, const double* __restrict__ cw,
     int n_clusters, double thr, long long* __restrict__ labels, double* __restrict__ confs,
     unsigned long long* __restrict__ counts, unsigned long long* __restrict__ best_scratch, double* __restrict__ rep,
     double* __restrict__ rep_w, unsigned long long* __restrict__ site_scratch) {
-    // shared: per warp [C] best val | [C] best row | [C] site val | [C] site row ; then [C] hist
+    // shared: per warp [C] best val | [C] best row | [C] site val | [C] site row ; [C] hist ; per warp staging
     extern __shared__ unsigned long long smem_u64[];
     const int C = n_clusters;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
@@ -101,21 +140,134 @@ __global__ void __launch_bounds__(256) k_assign_sparse(
     WarpBest wb = {wbase, wbase + C};
     WarpBest ws = {wbase + 2 * (size_t)C, wbase + 3 * (size_t)C};
     unsigned* hist = (unsigned*)(smem_u64 + (size_t)nwarps * 4 * C);
+    unsigned char* stage = (unsigned char*)(smem_u64 + (size_t)nwarps * 4 * C + (C + 1) / 2) + (size_t)warp * LR_STAGE_BYTES;
+    double* sv = (double*)stage;
+    uint16_t* sk = (uint16_t*)(stage + 32 * LR_VSTRIDE * sizeof(double));
     const long long warp_global = (long long)blockIdx.x * nwarps + warp;
     const long long n_warps = (long long)gridDim.x * nwarps;
     for (int i = threadIdx.x; i < nwarps * 4 * C; i += blockDim.x) smem_u64[i] = 0ull;
     for (int i = threadIdx.x; i < C; i += blockDim.x) hist[i] = 0u;
     __syncthreads();
-    for (long long r = warp_global; r < n_rows; r += n_warps) {
-        const unsigned long long ptr = row_ptr[r];
+    const long long n_groups = (n_rows + 31) >> 5;
+    for (long long g = warp_global; g < n_groups; g += n_warps) {
+        const long long r = (g << 5) + lane;
+        const bool valid = r < n_rows;
+        const unsigned long long ptr = valid ? row_ptr[r] : 0ull;
         const int nent = (int)(ptr & 0xFF);
-        const unsigned long long off = ptr >> 8;
-        if (nent <= 32)          // the common case: one entry per lane
-            assign_row<1>(r, nent, off, lane, pk, pv, row0, L, cid, cw, thr, labels, confs, counts, hist, best_scratch,
-                          wb, rep, rep_w, site_scratch, ws);
-        else
-            assign_row<ENTRY_CAP / 32>(r, nent, off, lane, pk, pv, row0, L, cid, cw, thr, labels, confs, counts, hist,
-                                       best_scratch, wb, rep, rep_w, site_scratch, ws);
+        bool hard = nent > 32;
+        const int ne = hard ? 0 : nent;
+        // stage the 32 rows.  Loads of 16 rows are issued back to back, unconditionally (idle lanes read entry 0),
+        // and stored afterwards: a conditional load per row would serialise the 32 rows on DRAM latency.
+        __syncwarp();
+#pragma unroll
+        for (int i0 = 0; i0 < 32; i0 += 16) {
+            uint16_t kk[16];
+            double vv[16];
+            unsigned on = 0u;
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+                const unsigned long long p = __shfl_sync(0xffffffffu, ptr, i0 + j);
+                const int n = (int)(p & 0xFF);
+                const bool act = n <= 32 && lane < n;
+                const unsigned long long a = act ? (p >> 8) + lane : 0ull;
+                kk[j] = __ldcs(pk + a);
+                vv[j] = __ldcs(pv + a);
+                on |= (act ? 1u : 0u) << j;
+            }
+#pragma unroll
+            for (int j = 0; j < 16; ++j)
+                if (on & (1u << j)) {
+                    sk[(i0 + j) * LR_KSTRIDE + lane] = kk[j];
+                    sv[(i0 + j) * LR_VSTRIDE + lane] = vv[j];
+                }
+        }
+        __syncwarp();
+        // every lane: its row's per-cluster sums, entries in ascending landmark order
+        int sid[LR_SLOTS];
+        double ssum[LR_SLOTS];
+#pragma unroll
+        for (int q = 0; q < LR_SLOTS; ++q) { sid[q] = -1; ssum[q] = 0.0; }
+        const int maxn = __reduce_max_sync(0xffffffffu, ne);
+        const uint16_t* myk = sk + lane * LR_KSTRIDE;
+        const double* myv = sv + lane * LR_VSTRIDE;
+        for (int e0 = 0; e0 < maxn; e0 += 4) {
+            // four entries' table look-ups in flight, then their slot updates in entry order
+            int cq[4];
+            double pq[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const bool act = e0 + j < ne;
+                const int k = act ? (int)myk[e0 + j] : 0;
+                const double v = act ? myv[e0 + j] : 0.0;
+                const int c = __ldg(cid + k);
+                cq[j] = act ? c : -1;
+                pq[j] = v * __ldg(cw + k);
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+                if (cq[j] >= 0 && !slot_add(sid, ssum, cq[j], pq[j])) hard = true;
+        }
+        const bool easy = valid && !hard;
+        // arg-max in ascending cluster id (np.argmax: first maximum; all zero -> index 0)
+        double bestc = 0.0;
+        int bestid = 0;
+#pragma unroll
+        for (int q = 0; q < LR_SLOTS; ++q) {
+            const double cf = fabs(ssum[q]);
+            if (sid[q] >= 0 && (cf > bestc || (cf == bestc && cf > 0.0 && sid[q] < bestid))) { bestc = cf; bestid = sid[q]; }
+        }
+        long long label = bestid;
+        double conf = bestc;
+        if (ne == 0 || !(conf >= thr)) { label = -1; conf = 0.0; }       // DotProdClassifier.pyx:168-172,184-186
+        if (easy) {
+            if (labels) labels[r] = label;
+            if (confs) confs[r] = conf;
+            if (label >= 0) {
+                if (counts) atomicAdd(&hist[label], 1u);
+                if (rep_w) atomicAdd(&rep_w[label], conf);
+            }
+        }
+        if (best_scratch) {                                               // cluster/mcl.py:81-83: every cluster of the row
+#pragma unroll
+            for (int q = 0; q < LR_SLOTS; ++q)
+                if (easy && sid[q] >= 0) table_raise(wb, sid[q], (unsigned long long)__double_as_longlong(fabs(ssum[q])));
+            __syncwarp();
+#pragma unroll
+            for (int q = 0; q < LR_SLOTS; ++q)
+                if (easy && sid[q] >= 0)
+                    table_claim(wb, sid[q], (unsigned long long)__double_as_longlong(fabs(ssum[q])), (unsigned long long)(row0 + r));
+            __syncwarp();
+        }
+        if (site_scratch) {
+            const unsigned long long vb = (unsigned long long)__double_as_longlong(conf);
+            if (easy && label >= 0) table_raise(ws, (int)label, vb);
+            __syncwarp();
+            if (easy && label >= 0) table_claim(ws, (int)label, vb, (unsigned long long)(row0 + r));
+            __syncwarp();
+        }
+        if (rep) {                                                        // mcl.py:118-122
+            for (int e = 0; e < maxn; ++e)
+                if (easy && label >= 0 && e < ne) atomicAdd(&rep[(size_t)label * L + myk[e]], conf * myv[e]);
+        }
+        // the hard rows of the group, one at a time by the whole warp
+        unsigned hm = __ballot_sync(0xffffffffu, valid && hard);
+        while (hm) {
+            const int i = __ffs(hm) - 1;
+            hm &= hm - 1;
+            const unsigned long long p = __shfl_sync(0xffffffffu, ptr, i);
+            const int n = (int)(p & 0xFF);
+            const unsigned long long off = p >> 8;
+            int k0 = 0;
+            double v0 = 0.0;
+            if (lane < n) { k0 = pk[off + lane]; v0 = pv[off + lane]; }
+            if (n <= 32)
+                assign_row<1>((g << 5) + i, n, off, lane, k0, v0, pk, pv, row0, L, cid, cw, thr, labels, confs, counts, hist,
+                              best_scratch, wb, rep, rep_w, site_scratch, ws);
+            else
+                assign_row<ENTRY_CAP / 32>((g << 5) + i, n, off, lane, k0, v0, pk, pv, row0, L, cid, cw, thr, labels, confs,
+                                           counts, hist, best_scratch, wb, rep, rep_w, site_scratch, ws);
+            __syncwarp();
+        }
     }
     __syncthreads();
     // merge the warps' tables (max value, then lowest row) and hand the CTA's table to the merge kernel
@@ -171,13 +323,21 @@ cudaError_t launch_assign_sparse(const unsigned long long* row_ptr, const uint16
                                  unsigned long long* site_best, int n_sms, cudaStream_t st) {
     if (n_rows <= 0) return cudaSuccess;
     const int C = n_clusters > 0 ? n_clusters : 1;
-    int warps = 8;                                            // per-warp tables: 32 B per cluster and warp
-    while (warps > 1 && (32 * (size_t)warps + 4) * C > 160 * 1024) warps >>= 1;
-    const size_t smem = (32 * (size_t)warps + 4) * C;
+    // per warp: 32 B of tables per cluster + the staging block; per CTA: the histogram
+    auto smem_for = [&](int w) { return (size_t)w * (32 * (size_t)C + LR_STAGE_BYTES) + 8 * (size_t)((C + 1) / 2) + 16; };
+    int warps = 4;
+    while (warps > 1 && smem_for(warps) > 56 * 1024) warps >>= 1;       // small enough for several CTAs per SM
+    const size_t smem = smem_for(warps);
     if (smem > 200 * 1024) return cudaErrorInvalidConfiguration;
     cudaError_t e = cudaFuncSetAttribute(k_assign_sparse, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    const int grid = n_sms * 8;
+    int resident = 1;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, k_assign_sparse, warps * 32, smem);
+    if (e != cudaSuccess) return e;
+    if (resident < 1) resident = 1;
+    const long long groups = (n_rows + 31) / 32;
+    long long want = (groups + warps - 1) / warps;
+    const int grid = (int)(want < (long long)n_sms * resident ? want : (long long)n_sms * resident);
     unsigned long long *sb = nullptr, *ss = nullptr;
     if (best) { e = cudaMallocAsync((void**)&sb, sizeof(unsigned long long) * 2 * (size_t)grid * C, st); if (e != cudaSuccess) return e; }
     if (site_best) { e = cudaMallocAsync((void**)&ss, sizeof(unsigned long long) * 2 * (size_t)grid * C, st); if (e != cudaSuccess) return e; }
