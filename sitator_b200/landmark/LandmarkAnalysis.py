@@ -162,11 +162,14 @@ class LandmarkAnalysis(object):
             sn (SiteNetwork): the landmark basis; each site is a landmark defined by its vertex
                 static atoms (``sn.vertices``).
             frames (ndarray n_frames x n_atoms x 3, float64): a trajectory, may be unwrapped.  It is
-                only read (the reference wraps a copy).
+                only read (the reference wraps a copy).  Also accepted: float32 / ``np.memmap`` arrays, and a
+                :class:`sitator_b200.landmark.ChunkedFrames` for trajectories that should not be held in host
+                memory as a whole.
         """
         import torch
         from ..engine import LandmarkEngine
         from .source import LandmarkVectorSource
+        from .frames import ChunkedFrames
         from . import parallel
 
         if not (isinstance(sn, SiteNetwork) or all(hasattr(sn, a) for a in ("static_mask", "mobile_mask", "centers", "vertices"))):
@@ -196,7 +199,11 @@ class LandmarkAnalysis(object):
             relaxed_lattice_checks=self.relaxed_lattice_checks, device=self._device)
         self._engine = engine
         t_start.record()
-        engine.set_frames(frames, frame0=frame0)
+        if isinstance(frames, ChunkedFrames):
+            # a trajectory that arrives in blocks is assembled in HBM; the engine borrows the device array
+            engine.set_frames(frames.to_device(engine.device), frame0=frame0)
+        else:
+            engine.set_frames(frames, frame0=frame0)
         engine.reset_status()
 
         # -- Steps 2/3: landmark vectors + clustering

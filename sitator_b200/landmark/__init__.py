@@ -1,2 +1,3 @@
 from .errors import StaticLatticeError, ZeroLandmarkError, LandmarkAnalysisError
 from .LandmarkAnalysis import LandmarkAnalysis
+from .frames import ChunkedFrames
