@@ -77,11 +77,42 @@ def _refine_centers(centers, n_assigned, threshold):
     raise ValueError("Clustering did not converge after %i iterations" % MAX_CONVERGE_ITERS)
 
 
-def fit_centers(source, threshold):
+def compact_rows(ptr, k, v):
+    """Cached rows without the pool's gaps: (entries per row, keys, values), rows in order."""
+    import torch
+    cnt = ptr & 0xFF
+    off = ptr >> 8                                  # offsets stay below 2^55: the sign bit is clear
+    new_off = torch.cumsum(cnt, 0) - cnt
+    nnz = int(cnt.sum().item())
+    idx = torch.repeat_interleave(off - new_off, cnt) + torch.arange(nnz, dtype=torch.int64, device=ptr.device)
+    return cnt, k.index_select(0, idx), v.index_select(0, idx)
+
+
+def gather_rows(rows, comm):
+    """All ranks' cached rows on every rank, in global row order (shards are contiguous blocks in rank order).
+
+    fit_centers is sequential over ALL landmark vectors (DotProdClassifier.pyx:236), so a frame-sharded run has no
+    parallel form of it: every rank runs the same fit over the same gathered rows and arrives at the same centres
+    (the fit is deterministic), which also saves the broadcast.  The compressed rows are ~250 B each."""
+    from ...engine import SparseRows
+    import torch
+    cnt, k, v = compact_rows(rows.ptr[:rows.n_rows], rows.k, rows.v)
+    sizes = comm.allgather_numpy(np.array([cnt.numel(), k.numel()], dtype=np.int64))
+    cnt = comm.allgather_varlen(cnt, sizes[:, 0])
+    k = comm.allgather_varlen(k, sizes[:, 1])
+    v = comm.allgather_varlen(v, sizes[:, 1])
+    ptr = ((torch.cumsum(cnt, 0) - cnt) << 8) | cnt
+    if k.numel() == 0:                              # keep the pointers valid for the kernels
+        k = torch.zeros((1,), dtype=k.dtype, device=k.device)
+        v = torch.zeros((1,), dtype=v.dtype, device=v.device)
+    return SparseRows(ptr, k, v, None, int(sizes[:, 1].sum()), int(sizes[:, 0].sum()), 0)
+
+
+def fit_centers(source, threshold, rows=None):
     """DotProdClassifier.fit_centers over the cached rows: (centres (C, L) float64, members (C,) int64)."""
     import torch
     eng = source.engine
-    rows = source.sparse
+    rows = source.sparse if rows is None else rows
     lib = _native.load()
     L = eng.L
     stream = torch.cuda.current_stream(eng.device).cuda_stream
@@ -172,17 +203,20 @@ def _site_best_table(labels, confs, n_sites, row0):
 
 def do_landmark_clustering(landmark_vectors, clustering_params, min_samples, verbose):
     source = landmark_vectors
-    if source.comm is not None:
-        raise NotImplementedError("clustering_algorithm='dotprod' is order dependent over ALL landmark vectors "
-                                  "(DotProdClassifier.pyx:236) and is not built for frame-sharded runs; use 'mcl'")
+    comm = source.comm
     params = DEFAULT_PARAMS.copy()
     params.update(clustering_params)
     first_pass(source)
 
     # DotProdClassifier.fit_predict (DotProdClassifier.pyx:68-127)
-    centers, _ = fit_centers(source, params['clustering_threshold'])                       # :83-84
+    # frame-sharded: the order-dependent fit runs redundantly over the gathered rows, predict over the local ones
+    fit_rows = None if comm is None else gather_rows(source.sparse, comm)
+    centers, _ = fit_centers(source, params['clustering_threshold'], fit_rows)             # :83-84
+    del fit_rows
     predict_threshold = params['assignment_threshold']
     labels, confs, counts = _predict(source, centers, predict_threshold, True)              # :86
+    if comm is not None:
+        comm.allreduce_sum_(counts)
     cluster_counts = counts.cpu().numpy()                                                   # :92
     total_n_assigned = int(cluster_counts.sum())                                            # :88
     if isinstance(min_samples, (int, np.integer)):

@@ -84,6 +84,23 @@ class Comm(object):
         self.dist.all_gather(out, t, group=self.group)
         return np.stack([o.cpu().numpy() for o in out])
 
+    def allgather_varlen(self, t, sizes=None):
+        """Concatenate one 1-D tensor per rank, of different lengths, in rank order (result on ``t``'s device).
+        Travels as bytes, so any dtype works on either backend (gloo has no int16)."""
+        import torch
+        t = t.contiguous()
+        if sizes is None:
+            sizes = self.allgather_numpy(np.array([t.numel()], dtype=np.int64))[:, 0]
+        item = t.element_size()
+        n_max = int(max(int(x) for x in sizes)) * item
+        send = t if (self.backend == "nccl" or not t.is_cuda) else t.cpu()
+        pad = torch.zeros((max(n_max, 1),), dtype=torch.uint8, device=send.device)
+        pad[:t.numel() * item] = send.view(torch.uint8)
+        out = [torch.empty_like(pad) for _ in range(self.world)]
+        self.dist.all_gather(out, pad, group=self.group)
+        parts = [o[:int(n) * item] for o, n in zip(out, sizes)]
+        return torch.cat(parts).view(t.dtype).to(t.device)
+
     def exclusive_scan_int(self, v):
         """Sum of ``v`` over the lower ranks (frame offset of this rank's shard)."""
         allv = self.allgather_numpy(np.array([int(v)], dtype=np.int64))[:, 0]

@@ -62,6 +62,37 @@ def _worker(rank, world, port, q):
                         want[k] = full[f][k]
             assert first == int(rank == 0)
             assert np.array_equal(carry.numpy(), want), (rank, uaj)
+        # variable-length all-gather (any dtype, as bytes) and the gather of cached compressed rows that the
+        # frame-sharded dotprod fit runs over: pool gaps squeezed out, rows in global order
+        from sitator_b200.landmark.cluster.dotprod import gather_rows
+        from sitator_b200.engine import SparseRows
+        t16 = torch.arange(3 + 2 * rank, dtype=torch.int16) + 100 * rank
+        out["varlen"] = comm.allgather_varlen(t16).tolist()
+        r2 = np.random.default_rng(40 + rank)
+        n_rows = 5 + 4 * rank
+        cnt = r2.integers(0, 6, n_rows)
+        cnt[1] = 0                                       # an all-zero row takes no pool entries
+        gaps = r2.integers(0, 4, n_rows)
+        off = np.cumsum(cnt + gaps) - cnt
+        pool_k = np.full(int(off[-1] + cnt[-1] + 3), -7, dtype=np.int16)
+        pool_v = np.full(len(pool_k), np.nan)
+        dense = np.zeros((n_rows, 40))
+        for i in range(n_rows):
+            kk = np.sort(r2.choice(40, cnt[i], replace=False))
+            vv = r2.random(cnt[i]) + 0.1
+            pool_k[off[i]:off[i] + cnt[i]] = kk
+            pool_v[off[i]:off[i] + cnt[i]] = vv
+            dense[i, kk] = vv
+        rows = SparseRows(torch.as_tensor((off << 8) | cnt), torch.as_tensor(pool_k), torch.as_tensor(pool_v),
+                          None, len(pool_k), n_rows, 0)
+        g = gather_rows(rows, comm)
+        gp = g.ptr.numpy()
+        got = np.zeros((g.n_rows, 40))
+        for i in range(g.n_rows):
+            o, c = gp[i] >> 8, gp[i] & 0xFF
+            got[i, g.k.numpy()[o:o + c]] = g.v.numpy()[o:o + c]
+        out["gathered"] = got
+        out["dense"] = dense
         q.put((rank, out))
     finally:
         dist.destroy_process_group()
@@ -89,3 +120,5 @@ def test_comm_world_size_2_gloo():
         assert res[r]["min_u64"] == [-1, 5, 1 << 62]                   # both ranks hold "none" (all ones) in slot 0
         assert res[r]["max_u64"] == [-1, 6, (1 << 62) + 1]          # -1 = all ones = the largest key
         assert res[r]["best"] == ([0.6, 0.9, 0.0], [11, 33, 0])
+        assert res[r]["varlen"] == [0, 1, 2, 100, 101, 102, 103, 104]
+        assert np.array_equal(res[r]["gathered"], np.concatenate([res[0]["dense"], res[1]["dense"]]))
