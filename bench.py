@@ -176,9 +176,31 @@ def reference_run_once(ref, system, cfg, frames):
     sn = syn.site_network_for(system, ref.SiteNetwork, ref.Atoms)
     la = ref.LandmarkAnalysis(clustering_algorithm='mcl', verbose=False, force_no_memmap=True,
                               max_mobile_per_site=cfg.get("max_mobile_per_site", 1))
-    t = time.perf_counter()
-    la.run(sn, frames)
-    return time.perf_counter() - t
+    # time the reference's own fill (helpers.pyx:12, the Cython function this repository replaces) inside its run:
+    # the unmodified function is called through a wrapper that only reads the clock
+    fill = ref.helpers._fill_landmark_vectors
+    spent = [0.0]
+
+    def timed_fill(*a, **k):
+        t0 = time.perf_counter()
+        try:
+            return fill(*a, **k)
+        finally:
+            spent[0] += time.perf_counter() - t0
+    ref.helpers._fill_landmark_vectors = timed_fill
+    try:
+        t = time.perf_counter()
+        la.run(sn, frames)
+        dt = time.perf_counter() - t
+    finally:
+        ref.helpers._fill_landmark_vectors = fill
+    LAST_REFERENCE_SPLIT["fill_seconds"] = spent[0]
+    LAST_REFERENCE_SPLIT["clustering_and_rest_seconds"] = dt - spent[0]
+    LAST_REFERENCE_SPLIT["fill_only_value"] = len(frames) * system.n_total / max(spent[0], 1e-9)   # same unit as value
+    return dt
+
+
+LAST_REFERENCE_SPLIT = {}      # fill / everything else of the last reference_run_once (time them separately)
 
 
 def load_reference():
@@ -227,6 +249,7 @@ def cpu_baseline(system, cfg, frames, n_frames):
     return {
         "value": n_frames * system.n_total / dt, "unit": UNIT, "cores": 1, "kind": kind,
         "blas_threads": blas_threads(), "host_cpus": os.cpu_count(), "seconds": dt,
+        **({k: round(v, 4) for k, v in LAST_REFERENCE_SPLIT.items()} if kind == "reference" else {}),
         "sample": "whole LandmarkAnalysis.run (mcl) on the first %d frames of the same trajectory; fill and assign "
                   "are single-threaded in the reference, only np.dot/matrix_power use BLAS threads" % n_frames,
     }
@@ -258,6 +281,7 @@ def run_reference_arm(args):
         "config": {"workload": workload_name(system, per_step), "frames_per_step": per_step},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": 1, "kind": kind, "blas_threads": blas_threads(),
                          "host_cpus": os.cpu_count(),
+                         **({k: round(v, 4) for k, v in LAST_REFERENCE_SPLIT.items()} if kind == "reference" else {}),
                          "sample": "whole LandmarkAnalysis.run (mcl) on %d frames per step" % per_step},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
