@@ -158,3 +158,25 @@ def test_jump_scan_hand_written_table():
     assert j.tolist() == [[1, 0, -1, 4], [2, 1, 2, 5], [4, 0, 4, 6], [4, 2, 3, 7]]
     ju = orc.jumps(t, unknown_as_jump=True)
     assert [1, 2, 3, -1] in ju.tolist() and [3, 0, 4, -1] in ju.tolist()
+
+
+def test_oracle_general_cell_path_reproduces_reference_golden():
+    """Triclinic cell, ragged vertex lists, frames displaced by whole lattice vectors: the compiled reference's
+    landmark vectors and PBCCalculator outputs (tests/golden/make_triclinic_golden.py).  The run() goldens are all
+    orthorhombic; this pins the oracle's general wrap, which the GPU's triclinic test is checked against."""
+    import os
+    g = np.load(os.path.join(U.GOLDEN_DIR, "triclinic_fill.npz"))
+    t = U.triclinic_system()
+    lv, n_zero, _ = orc.fill_landmark_vectors(t["cell"], t["static"], t["static_idx"], t["mobile_idx"], t["centers"],
+                                              t["verts"], t["frames"], check_for_zeros=False)
+    want = np.zeros(tuple(int(x) for x in g["lv_shape"]))
+    want[g["lv_rows"], g["lv_cols"]] = g["lv_vals"]
+    assert lv.shape == want.shape
+    assert np.array_equal(lv != 0, want != 0)
+    nz = want != 0
+    assert np.max(np.abs(lv[nz] - want[nz]) / want[nz]) < 1e-14
+    assert int(n_zero) == int(g["n_all_zero_lvecs"])
+    pb = orc.PBC(t["cell"])
+    assert np.array_equal(pb.wrap_points(g["points"].copy()), g["wrapped"])
+    assert np.array_equal(pb.distances(g["points"][0], g["points"][1:].copy()), g["distances"])
+    assert np.array_equal(pb.average(g["avg_points"].copy(), weights=g["avg_weights"]), g["average"])
