@@ -104,3 +104,44 @@ def compare_labels(got, want, decision_margin, what="labels"):
     bad = diff & ~(decision_margin.reshape(-1) < TIE_TOL)
     assert not np.any(bad), "%d %s differ outside the tie tolerance (of %d differing)" % (int(bad.sum()), what, int(diff.sum()))
     return int(diff.sum())
+
+
+def error_cases():
+    """Seeded inputs on which the reference raises from inside its fill: name -> (system, frames, LandmarkAnalysis kwargs).
+    Shared by tests/golden/make_error_golden.py (compiled reference) and the oracle / GPU tests."""
+    from oracle import landmark_oracle as orc
+    cases = {}
+    # static atoms pushed beyond static_movement_threshold in two frames: the first frame in iteration order wins,
+    # and within it the first lattice position (helpers.pyx:66-80)
+    system, cfg = syn.make_config("toy_bcc")
+    frames = system.trajectory(60)
+    frames[20, system.static_idx[7]] += 1.5
+    frames[9, system.static_idx[5]] += 1.3
+    frames[9, system.static_idx[2]] -= 1.3
+    cases["static_moved"] = (system, frames, dict(check_for_zero_landmarks=False))
+    # dynamic lattice mapping, a static atom sitting on another one: no lattice position picks it (helpers.pyx:87-92)
+    system, cfg = syn.make_config("lgps_dynamic")
+    frames = system.trajectory(12)
+    d = orc.PBC(system.cell).distances(system.static_pos[4], system.static_pos)
+    second = int(np.argsort(d, kind="stable")[2])
+    frames[7, system.static_idx[4]] = frames[7, system.static_idx[second]] + 0.01
+    cases["dynamic_unassigned"] = (system, frames, dict(dynamic_lattice_mapping=True, static_movement_threshold=50.0,
+                                                        max_mobile_per_site=2))
+    # a mobile atom far from every landmark: all-zero landmark vector with check_for_zero_landmarks=True (helpers.pyx:116-122)
+    system, cfg = syn.make_config("toy_bcc")
+    cases["zero_vector"] = (system, system.trajectory(300), dict(check_for_zero_landmarks=True))
+    return cases
+
+
+def occupancy_error_table():
+    """A random assignment table (F, M) with shared sites and unknowns, and its number of sites."""
+    rng = np.random.default_rng(3)
+    M, n_sites, F = 16, 24, 400
+    traj = rng.integers(0, n_sites, (F, M))
+    for f in range(37):                                  # no shared site before frame 37
+        traj[f] = rng.permutation(n_sites)[:M]
+    hold = rng.random((F, M)) < 0.9
+    for f in range(38, F):
+        traj[f, hold[f]] = traj[f - 1, hold[f]]
+    traj[rng.random((F, M)) < 0.3] = -1
+    return traj.astype(np.int64), n_sites

@@ -180,3 +180,36 @@ def test_oracle_general_cell_path_reproduces_reference_golden():
     assert np.array_equal(pb.wrap_points(g["points"].copy()), g["wrapped"])
     assert np.array_equal(pb.distances(g["points"][0], g["points"][1:].copy()), g["distances"])
     assert np.array_equal(pb.average(g["avg_points"].copy(), weights=g["avg_weights"]), g["average"])
+
+
+def test_oracle_failures_reproduce_reference_golden():
+    """Which error, at which frame, naming which atoms: the oracle's failure classes against what the compiled
+    reference raised on the same seeded inputs (tests/golden/errors.json, make_error_golden.py)."""
+    import json
+    import os
+    with open(os.path.join(U.GOLDEN_DIR, "errors.json")) as f:
+        want = json.load(f)
+    for name, (system, frames, kw) in U.error_cases().items():
+        w = want[name]
+        fill_kw = dict(check_for_zeros=kw.get("check_for_zero_landmarks", True),
+                       dynamic_lattice_mapping=kw.get("dynamic_lattice_mapping", False),
+                       static_movement_threshold=kw.get("static_movement_threshold", 1.0))
+        with pytest.raises((orc.StaticLatticeFailure, orc.ZeroLandmarkFailure)) as e:
+            orc.fill_landmark_vectors(system.cell, system.static_pos, system.static_idx, system.mobile_idx,
+                                      system.lm_centers, system.lm_vertices, frames, **fill_kw)
+        if w["error"] == "StaticLatticeError":
+            assert isinstance(e.value, orc.StaticLatticeFailure), name
+            assert e.value.frame == w["frame"], name
+            assert [int(x) for x in e.value.lattice_atoms] == w["lattice_atoms"], name
+        else:
+            assert w["error"] == "ZeroLandmarkError" and isinstance(e.value, orc.ZeroLandmarkFailure), name
+            assert (e.value.frame, e.value.mobile_index) == (w["frame"], w["mobile_index"]), name
+    traj, n_sites = U.occupancy_error_table()
+    w = want["multiple_occupancy"]
+    with pytest.raises(orc.MultipleOccupancyFailure) as e:
+        orc.check_multiple_occupancy(traj, max_mobile_per_site=1)
+    assert (e.value.frame, e.value.site) == (w["frame"], w["site"])
+    assert [int(x) for x in e.value.mobile] == w["mobile_particles"]
+    n_more, avg = orc.check_multiple_occupancy(traj, max_mobile_per_site=traj.shape[1])
+    assert n_more == want["multiple_occupancy_stats"]["n_more_than_one"]
+    assert avg == want["multiple_occupancy_stats"]["avg_mobile_per_site"]
