@@ -213,3 +213,26 @@ def test_oracle_failures_reproduce_reference_golden():
     n_more, avg = orc.check_multiple_occupancy(traj, max_mobile_per_site=traj.shape[1])
     assert n_more == want["multiple_occupancy_stats"]["n_more_than_one"]
     assert avg == want["multiple_occupancy_stats"]["avg_mobile_per_site"]
+
+
+@pytest.mark.parametrize("name", ["toy_bcc_300", "llzo_60"])
+@pytest.mark.parametrize("method", ["real-unweighted", "representative-landmark"])
+def test_oracle_site_center_methods_reproduce_reference_golden(name, method):
+    """The non-default site_centers_method values (LandmarkAnalysis.py:286-296) against the compiled reference's
+    centres (tests/golden/site_center_methods.npz, make_site_center_golden.py)."""
+    import os
+    want = np.load(os.path.join(U.GOLDEN_DIR, "site_center_methods.npz"))["%s/%s" % (name, method)]
+    g, system, cfg, frames = U.load_golden(name)
+    kw = U.analysis_kwargs(cfg)
+    res = orc.run_landmark_analysis(system.cell, system.static_pos, system.static_idx, system.mobile_idx,
+                                    system.lm_centers, system.lm_vertices, frames, site_centers_method=method,
+                                    dynamic_lattice_mapping=kw["dynamic_lattice_mapping"],
+                                    check_for_zero_landmarks=kw["check_for_zero_landmarks"],
+                                    max_mobile_per_site=kw["max_mobile_per_site"])
+    assert res["site_centers"].shape == want.shape
+    # compared modulo lattice vectors: the toy landmarks lie ON cell faces, where a last-bit difference in the weights
+    # turns the final wrap's 0.0 into 12.0 (the same point; seen once, site 16 of the toy case)
+    diff = (res["site_centers"] - want) @ np.linalg.inv(system.cell)
+    diff -= np.round(diff)
+    assert np.max(np.abs(diff @ system.cell)) < 1e-11
+    assert np.sum(np.abs(res["site_centers"] - want) > 1e-11) <= 1
