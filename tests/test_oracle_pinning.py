@@ -236,3 +236,22 @@ def test_oracle_site_center_methods_reproduce_reference_golden(name, method):
     diff -= np.round(diff)
     assert np.max(np.abs(diff @ system.cell)) < 1e-11
     assert np.sum(np.abs(res["site_centers"] - want) > 1e-11) <= 1
+
+
+def test_oracle_relaxed_lattice_checks_reproduce_reference_golden():
+    """relaxed_lattice_checks=True with dynamic lattice mapping and a static atom that no lattice position picks
+    (helpers.pyx:84-92): the run goes on with the duplicated map; landmark vectors of the compiled reference
+    (tests/golden/relaxed_dynamic_fill.npz, make_relaxed_golden.py)."""
+    import os
+    g = np.load(os.path.join(U.GOLDEN_DIR, "relaxed_dynamic_fill.npz"))
+    system, frames, kw = U.error_cases()["dynamic_unassigned"]
+    lv, n_zero, _ = orc.fill_landmark_vectors(system.cell, system.static_pos, system.static_idx, system.mobile_idx,
+                                              system.lm_centers, system.lm_vertices, frames, check_for_zeros=False,
+                                              dynamic_lattice_mapping=True, relaxed_lattice_checks=True,
+                                              static_movement_threshold=kw["static_movement_threshold"])
+    want = np.zeros(tuple(int(x) for x in g["lv_shape"]))
+    want[g["lv_rows"], g["lv_cols"]] = g["lv_vals"]
+    assert np.array_equal(lv != 0, want != 0)
+    nz = want != 0
+    assert np.max(np.abs(lv[nz] - want[nz]) / want[nz]) < 1e-14
+    assert int(n_zero) == int(g["n_all_zero_lvecs"])
