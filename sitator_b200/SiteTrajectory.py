@@ -145,7 +145,12 @@ class SiteTrajectory(object):
 
     def compute_site_occupancies(self):
         """Adds site attribute ``occupancies`` (ref :187-202)."""
-        occ = np.true_divide(np.bincount(self._traj[self._traj >= 0], minlength=self._sn.n_sites), self.n_frames)
+        counts = np.bincount(self._traj[self._traj >= 0], minlength=self._sn.n_sites)
+        n_frames = self.n_frames
+        if self._comm is not None:                # frame-sharded: occupancies over the whole trajectory
+            counts = self._comm.allreduce_sum_numpy(counts.astype(np.int64))
+            n_frames = self._comm.allreduce_sum_scalar(n_frames)
+        occ = np.true_divide(counts, n_frames)
         if self.site_network.has_attribute('occupancies'):
             self.site_network.remove_attribute('occupancies')
         self.site_network.add_site_attribute('occupancies', occ)

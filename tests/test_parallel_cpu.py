@@ -93,6 +93,18 @@ def _worker(rank, world, port, q):
             got[i, g.k.numpy()[o:o + c]] = g.v.numpy()[o:o + c]
         out["gathered"] = got
         out["dense"] = dense
+        # site occupancies of a frame-sharded SiteTrajectory are those of the whole trajectory (SiteTrajectory.py:187-202)
+        from sitator_b200 import SiteNetwork, SiteTrajectory, Atoms
+        r3 = np.random.default_rng(9)
+        whole = r3.integers(-1, 5, (n_local_total(world), 4))
+        atoms = Atoms(r3.random((6, 3)) * 5, np.eye(3) * 5)
+        mob = np.zeros(6, dtype=bool); mob[:4] = True
+        sn = SiteNetwork(atoms, ~mob, mob)
+        sn.centers = r3.random((5, 3)) * 5
+        st = SiteTrajectory(sn, whole[f0:f0 + n_local])
+        st._comm, st.frame0 = comm, f0
+        out["occ"] = st.compute_site_occupancies()
+        out["occ_want"] = np.bincount(whole[whole >= 0], minlength=5) / float(len(whole))
         q.put((rank, out))
     finally:
         dist.destroy_process_group()
@@ -122,3 +134,4 @@ def test_comm_world_size_2_gloo():
         assert res[r]["best"] == ([0.6, 0.9, 0.0], [11, 33, 0])
         assert res[r]["varlen"] == [0, 1, 2, 100, 101, 102, 103, 104]
         assert np.array_equal(res[r]["gathered"], np.concatenate([res[0]["dense"], res[1]["dense"]]))
+        assert np.array_equal(res[r]["occ"], res[r]["occ_want"])
