@@ -145,3 +145,22 @@ def occupancy_error_table():
         traj[f, hold[f]] = traj[f - 1, hold[f]]
     traj[rng.random((F, M)) < 0.3] = -1
     return traj.astype(np.int64), n_sites
+
+
+def cutoff_cases():
+    """Non-default cut-off parameters: name -> (system, frames, cutoff_midpoint, cutoff_steepness)."""
+    cases = {}
+    system, cfg = syn.make_config("toy_bcc")
+    cases["toy_soft"] = (system, system.trajectory(40), 1.3, 12.0)          # wide, soft cut-off: many more non-zeros
+    system, cfg = syn.make_config("llzo")
+    cases["llzo_sharp"] = (system, system.trajectory(8), 1.7, 45.0)         # sharp cut-off further out, ragged vertex lists
+    cases["llzo_steep"] = (system, system.trajectory(8), 1.2, 120.0)        # nearly a step function
+    return cases
+
+
+def load_cutoff_golden(name):
+    import os
+    g = np.load(os.path.join(GOLDEN_DIR, "cutoff_params_fill.npz"))
+    want = np.zeros(tuple(int(x) for x in g[name + "/shape"]))
+    want[g[name + "/rows"], g[name + "/cols"]] = g[name + "/vals"]
+    return want, int(g[name + "/n_zero"])

@@ -255,3 +255,18 @@ def test_oracle_relaxed_lattice_checks_reproduce_reference_golden():
     nz = want != 0
     assert np.max(np.abs(lv[nz] - want[nz]) / want[nz]) < 1e-14
     assert int(n_zero) == int(g["n_all_zero_lvecs"])
+
+
+@pytest.mark.parametrize("name", ["toy_soft", "llzo_sharp", "llzo_steep"])
+def test_oracle_non_default_cutoff_reproduces_reference_golden(name):
+    """cutoff_midpoint / cutoff_steepness away from 1.5 / 30 (helpers.pyx:41-43,127-131,197-209): the compiled
+    reference's landmark vectors (tests/golden/cutoff_params_fill.npz, make_cutoff_golden.py)."""
+    system, frames, midpoint, steepness = U.cutoff_cases()[name]
+    want, want_zero = U.load_cutoff_golden(name)
+    lv, n_zero, _ = orc.fill_landmark_vectors(system.cell, system.static_pos, system.static_idx, system.mobile_idx,
+                                              system.lm_centers, system.lm_vertices, frames, midpoint, steepness,
+                                              check_for_zeros=False)
+    assert np.array_equal(lv != 0, want != 0)
+    nz = want != 0
+    assert np.max(np.abs(lv[nz] - want[nz]) / want[nz]) < 1e-13
+    assert int(n_zero) == want_zero
