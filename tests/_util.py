@@ -164,3 +164,13 @@ def load_cutoff_golden(name):
     want = np.zeros(tuple(int(x) for x in g[name + "/shape"]))
     want[g[name + "/rows"], g[name + "/cols"]] = g[name + "/vals"]
     return want, int(g[name + "/n_zero"])
+
+
+def clustering_param_cases():
+    """Non-default 'mcl' clustering parameters: case -> (golden input name, clustering_params, minimum_site_occupancy)."""
+    return {
+        "toy_inflation3": ("toy_bcc_300", {"inflation": 3, "assignment_threshold": 0.8}, 0.01),
+        "toy_thresholds": ("toy_bcc_300", {"assignment_threshold": 0.6, "good_site_normed_threshold": 0.9,
+                                           "good_site_projected_threshold": 0.5}, 0.2),
+        "llzo_inflation2": ("llzo_60", {"inflation": 2.5, "assignment_threshold": 0.75}, 0.05),
+    }

@@ -270,3 +270,24 @@ def test_oracle_non_default_cutoff_reproduces_reference_golden(name):
     nz = want != 0
     assert np.max(np.abs(lv[nz] - want[nz]) / want[nz]) < 1e-13
     assert int(n_zero) == want_zero
+
+
+@pytest.mark.parametrize("case", ["toy_inflation3", "toy_thresholds", "llzo_inflation2"])
+def test_oracle_non_default_clustering_params_reproduce_reference_golden(case):
+    """'mcl' clustering parameters and minimum_site_occupancy away from their defaults (cluster/mcl.py:28-31,60-66,
+    87-88,98-109): labels, confidences and site centres of the compiled reference (clustering_params.npz)."""
+    import os
+    name, params, min_occ = U.clustering_param_cases()[case]
+    g = np.load(os.path.join(U.GOLDEN_DIR, "clustering_params.npz"))
+    _, system, cfg, frames = U.load_golden(name)
+    kw = U.analysis_kwargs(cfg)
+    res = orc.run_landmark_analysis(system.cell, system.static_pos, system.static_idx, system.mobile_idx,
+                                    system.lm_centers, system.lm_vertices, frames, clustering_params=dict(params),
+                                    minimum_site_occupancy=min_occ,
+                                    dynamic_lattice_mapping=kw["dynamic_lattice_mapping"],
+                                    check_for_zero_landmarks=kw["check_for_zero_landmarks"],
+                                    max_mobile_per_site=kw["max_mobile_per_site"])
+    assert np.array_equal(res["labels"], g[case + "/labels"])
+    assert np.max(np.abs(res["confs"] - g[case + "/confs"])) < 1e-12
+    assert res["site_centers"].shape == g[case + "/site_centers"].shape
+    assert np.max(np.abs(res["site_centers"] - g[case + "/site_centers"])) < 1e-11

@@ -50,3 +50,22 @@ def test_non_default_cutoff_matches_reference_golden(name):
     nz = want != 0
     assert np.max(np.abs(got[nz] - want[nz]) / want[nz]) < U.LV_RTOL
     assert st.n_zero_rows == want_zero
+
+
+@pytest.mark.parametrize("case", ["toy_inflation3", "toy_thresholds", "llzo_inflation2"])
+def test_non_default_clustering_params_match_reference_golden(case):
+    """'mcl' clustering parameters (inflation, assignment / good-site thresholds) and minimum_site_occupancy away
+    from their defaults, whole run() against the compiled reference (clustering_params.npz)."""
+    from sitator_b200 import synthetic as syn
+    from sitator_b200.landmark import LandmarkAnalysis
+    name, params, min_occ = U.clustering_param_cases()[case]
+    g = np.load(os.path.join(U.GOLDEN_DIR, "clustering_params.npz"))
+    _, system, cfg, frames = U.load_golden(name)
+    la = LandmarkAnalysis(clustering_algorithm='mcl', clustering_params=dict(params), verbose=False,
+                          minimum_site_occupancy=min_occ, **U.analysis_kwargs(cfg))
+    st = la.run(syn.site_network_for(system), frames)
+    want = g[case + "/labels"]
+    assert st.site_network.n_sites == len(g[case + "/site_centers"])
+    assert np.array_equal(st.traj, want)
+    assert np.max(np.abs(st.confidences - g[case + "/confs"])) < U.CONF_ATOL
+    assert np.max(np.abs(np.asarray(st.site_network.centers) - g[case + "/site_centers"])) < U.CENTER_ATOL
