@@ -174,3 +174,12 @@ def clustering_param_cases():
                                            "good_site_projected_threshold": 0.5}, 0.2),
         "llzo_inflation2": ("llzo_60", {"inflation": 2.5, "assignment_threshold": 0.75}, 0.05),
     }
+
+
+def dotprod_param_cases():
+    """Non-default 'dotprod' clustering parameters: case -> (golden input name, clustering_params, minimum_site_occupancy)."""
+    return {
+        "toy_loose": ("toy_bcc_300_dotprod", {"clustering_threshold": 0.3, "assignment_threshold": 0.6}, 0.01),
+        "toy_tight": ("toy_bcc_300_dotprod", {"clustering_threshold": 0.7, "assignment_threshold": 0.9}, 0.1),
+        "llzo_tight": ("llzo_60_dotprod", {"clustering_threshold": 0.6, "assignment_threshold": 0.85}, 0.05),
+    }

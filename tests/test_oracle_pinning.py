@@ -291,3 +291,27 @@ def test_oracle_non_default_clustering_params_reproduce_reference_golden(case):
     assert np.max(np.abs(res["confs"] - g[case + "/confs"])) < 1e-12
     assert res["site_centers"].shape == g[case + "/site_centers"].shape
     assert np.max(np.abs(res["site_centers"] - g[case + "/site_centers"])) < 1e-11
+
+
+@pytest.mark.parametrize("case", ["toy_loose", "toy_tight", "llzo_tight"])
+def test_oracle_non_default_dotprod_params_reproduce_reference_golden(case):
+    """clustering_threshold / assignment_threshold of the default 'dotprod' clustering and minimum_site_occupancy away
+    from their defaults (cluster/dotprod.py:6-9): the compiled reference's labels, confidences, site centres."""
+    import os
+    name, params, min_occ = U.dotprod_param_cases()[case]
+    g = np.load(os.path.join(U.GOLDEN_DIR, "dotprod_params.npz"))
+    _, system, cfg, frames = U.load_dotprod_golden(name)
+    kw = U.analysis_kwargs(cfg)
+    lv, n_zero, wrapped = orc.fill_landmark_vectors(
+        system.cell, system.static_pos, system.static_idx, system.mobile_idx, system.lm_centers, system.lm_vertices,
+        frames, check_for_zeros=kw["check_for_zero_landmarks"], dynamic_lattice_mapping=kw["dynamic_lattice_mapping"])
+    res = orc.do_landmark_clustering_dotprod(lv, dict(params), min_occ / system.n_mobile)
+    want = g[case + "/labels"]
+    labels = res["cluster-labels"].reshape(want.shape)
+    assert len(res["cluster-size"]) == len(g[case + "/site_centers"])
+    assert np.array_equal(labels, want)
+    confs = res["cluster-confs"].reshape(want.shape)
+    assert np.max(np.abs(confs - g[case + "/confs"])) < 1e-12
+    sc = orc.site_centers_real(orc.PBC(system.cell), wrapped[:, system.mobile_idx], labels, confs,
+                               len(res["cluster-size"]), weighted=True)
+    assert np.max(np.abs(sc - g[case + "/site_centers"])) < 1e-11

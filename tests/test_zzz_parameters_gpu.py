@@ -69,3 +69,22 @@ def test_non_default_clustering_params_match_reference_golden(case):
     assert np.array_equal(st.traj, want)
     assert np.max(np.abs(st.confidences - g[case + "/confs"])) < U.CONF_ATOL
     assert np.max(np.abs(np.asarray(st.site_network.centers) - g[case + "/site_centers"])) < U.CENTER_ATOL
+
+
+@pytest.mark.parametrize("case", ["toy_loose", "toy_tight", "llzo_tight"])
+def test_non_default_dotprod_params_match_reference_golden(case):
+    """clustering_threshold / assignment_threshold of the default 'dotprod' clustering and minimum_site_occupancy
+    away from their defaults, whole run() against the compiled reference (dotprod_params.npz)."""
+    from sitator_b200 import synthetic as syn
+    from sitator_b200.landmark import LandmarkAnalysis
+    name, params, min_occ = U.dotprod_param_cases()[case]
+    g = np.load(os.path.join(U.GOLDEN_DIR, "dotprod_params.npz"))
+    _, system, cfg, frames = U.load_dotprod_golden(name)
+    la = LandmarkAnalysis(clustering_params=dict(params), verbose=False, minimum_site_occupancy=min_occ,
+                          **U.analysis_kwargs(cfg))
+    assert la._cluster_algo == 'dotprod'
+    st = la.run(syn.site_network_for(system), frames)
+    assert st.site_network.n_sites == len(g[case + "/site_centers"])
+    assert np.array_equal(st.traj, g[case + "/labels"])
+    assert np.max(np.abs(st.confidences - g[case + "/confs"])) < U.CONF_ATOL
+    assert np.max(np.abs(np.asarray(st.site_network.centers) - g[case + "/site_centers"])) < U.CENTER_ATOL
