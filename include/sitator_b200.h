@@ -163,6 +163,24 @@ int sitb_pass_assign(sitb_ctx* ctx, int64_t frame_begin, int64_t n, double thres
                      double* dev_confs, uint64_t* dev_counts, uint64_t* dev_best, double* dev_rep,
                      double* dev_rep_w, uint64_t* dev_site_best);
 
+/* Two-tier evaluation of sitb_pass_assign (labels / confs / counts outputs only; orthorhombic cells with a candidate
+ * grid; no reference counterpart -- the reference evaluates everything in float64, helpers.pyx:10).
+ * SITB_ASSIGN_TWO_TIER: a first kernel evaluates every landmark-vector component in FP32 with a proven error bound
+ * (tau, relative, per component) and takes a row's decisions -- which components are non-zero (helpers.pyx:199-203),
+ * the arg-max cluster (DotProdClassifier.pyx:181), the threshold test (:184-186) -- only if they hold for every value
+ * inside the bound; all other rows are then redone by the exact float64 kernel.  Labels are therefore identical to
+ * SITB_ASSIGN_EXACT; confidences of first-tier rows differ by at most tau * sum |component * centre weight|.
+ * Shapes the first tier does not cover (triclinic cells, no grid, shared memory) silently use the exact kernel. */
+#define SITB_ASSIGN_EXACT 0
+#define SITB_ASSIGN_TWO_TIER 1
+int sitb_set_assign_mode(sitb_ctx* ctx, int32_t mode);
+/* counts[SITB_TWO_TIER_SLOTS] (accumulated over passes since the last reset): rows left to the exact kernel because
+ * [0] their frame has a static atom beyond the grid margin / an ambiguous lattice map, [1] a component's cut-off test
+ * was inside the FP32 error band, [2] the two largest similarities were closer than the bound, [3] the largest
+ * similarity was within the bound of the assignment threshold, [4] more than 64 non-zero components; [5] all of them. */
+#define SITB_TWO_TIER_SLOTS 6
+int sitb_two_tier_info(sitb_ctx* ctx, int32_t* available, double* tau, double* kappa, uint64_t* counts, int32_t reset);
+
 /* ---- the "dotprod" clustering plugin (landmark/cluster/dotprod.py:11-33), over rows cached by
  * sitb_pass_stats_cached ----
  * sitb_dotprod_fit: the first (and only long) iteration of DotProdClassifier.fit_centers

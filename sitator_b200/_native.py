@@ -66,6 +66,9 @@ SIGNATURES = {
     "sitb_assign_sparse": (C.c_int, [_P, _P, _P, _P, C.c_int64, C.c_int64, C.c_double] + [_P] * 7),
     "sitb_set_centers": (C.c_int, [_P, _P, _P, C.c_int32]),
     "sitb_pass_assign": (C.c_int, [_P, C.c_int64, C.c_int64, C.c_double] + [_P] * 7),
+    "sitb_set_assign_mode": (C.c_int, [_P, C.c_int32]),
+    "sitb_two_tier_info": (C.c_int, [_P, C.POINTER(C.c_int32), C.POINTER(C.c_double), C.POINTER(C.c_double),
+                                     C.POINTER(C.c_uint64), C.c_int32]),
     "sitb_dotprod_limits": (C.c_int, [C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
     "sitb_dotprod_fit": (C.c_int, [C.c_int, _P, _P, _P, C.c_int64, C.c_int32, C.c_double, C.c_int32, C.c_int32,
                                    _P, _P, _P, _P, _P, _P, _P]),

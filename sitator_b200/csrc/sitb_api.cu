@@ -61,6 +61,10 @@ struct GridLevelDev {
     uint16_t* slist = nullptr;
     double margin = 0.0;
     unsigned long long entries = 0, static_entries = 0;
+    // first tier of the two-tier assign pass (sitb_fill_fast.cu)
+    uint2* sbox = nullptr;            // [cells] (offset, count) into slist
+    uint2* cbox = nullptr;            // [cells] (offset, count) into clist
+    unsigned* clist = nullptr;        // landmark | cluster << 16, sorted by cluster (rebuilt when the centres change)
 };
 
 struct sitb_ctx {
@@ -120,6 +124,20 @@ struct sitb_ctx {
     size_t up_waited = 0;                 // chunks the compute stream already waits for
     // status
     unsigned long long* d_status = nullptr;   // [2] error keys + [CNT_SLOTS] counters
+    // two-tier assign pass (sitb_fill_fast.cu): float tables, error model, scratch
+    float4* d_fast_ib = nullptr;
+    float4* d_fast_ac = nullptr;
+    float2* d_fast_cw = nullptr;
+    float* d_ideal_frac = nullptr;
+    std::vector<uint8_t> h_nverts;            // internal numbering
+    double fast_kappa = 0.0, fast_tau = 0.0, fast_dc = 0.0, cw_absmax = 0.0;
+    bool fast_tables_ok = false, fast_lists_dirty = true;
+    uint8_t* d_recheck = nullptr;             // [rows]
+    int* d_frame_flag = nullptr;              // [frames]
+    long long* d_frame_list = nullptr;        // [frames]
+    unsigned long long* d_two_tier = nullptr; // [0] list length, [1 .. RECHECK_SLOTS] reason counters
+    size_t recheck_rows_cap = 0, recheck_frames_cap = 0;
+    int assign_mode = 0;                      // 0 exact, 1 two-tier where the shape allows it
 };
 
 static void free_ctx(sitb_ctx* c) {
@@ -134,7 +152,11 @@ static void free_ctx(sitb_ctx* c) {
     for (int l = 0; l < 2; ++l) {
         pool_free(c->grid[l].ptr, c->stream); pool_free(c->grid[l].list, c->stream);
         pool_free(c->grid[l].sptr, c->stream); pool_free(c->grid[l].slist, c->stream);
+        pool_free(c->grid[l].sbox, c->stream); pool_free(c->grid[l].cbox, c->stream); pool_free(c->grid[l].clist, c->stream);
     }
+    pool_free(c->d_fast_ib, c->stream); pool_free(c->d_fast_ac, c->stream); pool_free(c->d_fast_cw, c->stream);
+    pool_free(c->d_ideal_frac, c->stream); pool_free(c->d_recheck, c->stream); pool_free(c->d_frame_flag, c->stream);
+    pool_free(c->d_frame_list, c->stream); pool_free(c->d_two_tier, c->stream);
     pool_free(c->d_rmax, c->stream); pool_free(c->d_ideal_wrapped, c->stream); pool_free(c->d_radius, c->stream);
     pool_free(c->d_verts_in, c->stream); pool_free(c->d_svd, c->stream); pool_free(c->d_qorig, c->stream); pool_free(c->d_orig_of, c->stream); pool_free(c->d_v0, c->stream); pool_free(c->d_b0, c->stream); pool_free(c->d_va, c->stream); pool_free(c->d_ba, c->stream);
     pool_free(c->d_q64, c->stream); pool_free(c->d_acoef, c->stream); pool_free(c->d_nverts, c->stream); pool_free(c->d_cid, c->stream); pool_free(c->d_cw, c->stream); pool_free(c->d_cid_orig, c->stream); pool_free(c->d_cw_orig, c->stream); pool_free(c->d_frames_owned, c->stream); pool_free(c->d_frames_f32, c->stream); pool_free(c->d_status, c->stream);
@@ -287,6 +309,56 @@ extern "C" int sitb_create(const sitb_network_desc* d, int device, sitb_ctx** ou
         CKC(upload(&c->d_acoef, ht.acoef.data(), ht.acoef.size(), c->stream));
         CKC(upload(&c->d_nverts, ht.nverts.data(), ht.nverts.size(), c->stream));
         CKC(upload(&c->d_orig_of, ht.orig_of.data(), ht.orig_of.size(), c->stream));
+        c->h_nverts = ht.nverts;
+        if (c->cell.diag) {
+            // ---- float tables and error model of the two-tier assign pass (sitb_fill_fast.cu) ----
+            // Squared distances are formed in FP32 from float fractional coordinates as |(u - round(u)) L|^2.  With
+            // u24 = 2^-24: a fractional coordinate carries 2^-25 from its rounding to float, their difference one more
+            // rounding, the product with float(L) two; each Cartesian component is off by at most 2 u24 L (3 allowed).
+            const double u24 = 5.9604644775390625e-08;
+            const double lmax = std::max(std::fabs(c->cell.c[0]), std::max(std::fabs(c->cell.c[4]), std::fabs(c->cell.c[8])));
+            const double dc = 3.0 * u24 * lmax;
+            const double log2e = 1.4426950408889634074, ln2 = 0.69314718055994530942;
+            const double bcl = c->steepness * c->midpoint * log2e;
+            const int W = 4 * c->NB;
+            std::vector<float4> ib((size_t)c->NB * c->Lpad, make_float4(0.f, 0.f, 0.f, 0.f)), ac(ib);
+            double eps_max = 0.0, tau_max = 0.0;
+            for (int ki = 0; ki < c->L; ++ki)
+                for (int h = 0; h < W; ++h) {
+                    const double Q = ht.q64[(size_t)ki * W + h];
+                    const double a = ht.acoef[(size_t)ki * W + h] * log2e;     // steepness * log2(e) / site_vert_dist
+                    if (!(Q > 0.0) || std::isinf(Q) || !(a > 0.0)) continue;    // dummy vertex / degenerate landmark: (0, 0)
+                    const double err = 2.0 * std::sqrt(3.0 * Q) * dc + 3.0 * dc * dc + 4.0 * u24 * Q;
+                    const double eps = 1.5 * err / Q + 8.0 * u24;
+                    eps_max = std::max(eps_max, eps);
+                    const double R = std::sqrt(Q);
+                    const double dd = std::sqrt(3.0) * dc + 6.0 * u24 * R;       // |d_float - d|
+                    tau_max = std::max(tau_max, ln2 * (a * dd + (a * R + bcl) * 3.0 * u24));
+                    float* pi = &ib[(size_t)(h / 4) * c->Lpad + ki].x;
+                    float* pa = &ac[(size_t)(h / 4) * c->Lpad + ki].x;
+                    pi[h & 3] = (float)(1.0 / (Q * (1.0 + eps)));
+                    pa[h & 3] = (float)a;
+                }
+            c->fast_kappa = (1.0 - eps_max) / (1.0 + eps_max) * (1.0 - 4.0 * u24);
+            // + lg2.approx (2^-22 relative on |log2 P| <= 54), ex2.approx, product and summation roundings
+            c->fast_tau = 1.25 * (tau_max + ln2 * 54.0 * 4.0 * u24 + 16.0 * u24) + 16.0 * u24;
+            c->fast_dc = dc;
+            std::vector<float> idf((size_t)3 * ((c->S + 4) & ~3), 0.f);
+            const int Spad = (c->S + 4) & ~3;
+            for (int s2 = 0; s2 < c->S; ++s2)
+                for (int k = 0; k < 3; ++k) {
+                    double f = c->cell.ci[4 * k] * d->host_ideal_static[3 * s2 + k];
+                    f -= std::floor(f);
+                    idf[(size_t)k * Spad + s2] = (float)f;
+                }
+            CKC(upload(&c->d_fast_ib, ib.data(), ib.size(), c->stream));
+            CKC(upload(&c->d_fast_ac, ac.data(), ac.size(), c->stream));
+            CKC(upload(&c->d_ideal_frac, idf.data(), idf.size(), c->stream));
+            CKC(pool_alloc((void**)&c->d_fast_cw, sizeof(float2) * (size_t)c->Lpad, c->stream));
+            CKC(pool_alloc((void**)&c->d_two_tier, sizeof(unsigned long long) * (1 + RECHECK_SLOTS), c->stream));
+            CKC(cudaMemsetAsync(c->d_two_tier, 0, sizeof(unsigned long long) * (1 + RECHECK_SLOTS), c->stream));
+            c->fast_tables_ok = c->fast_kappa > 0.9 && c->fast_tau < 1e-2;
+        }
     }
     CKC(cudaStreamSynchronize(c->stream));
 #undef CKC
@@ -331,10 +403,15 @@ static int build_grid_level(sitb_ctx* c, const int g[3], double margin, GridLeve
             CK(launch_grid_lists(c->cell, c->d_ideal_wrapped, c->d_va, c->d_radius, c->L, c->Lpad, c->NB, c->S, g[0], g[1], g[2], margin,
                                  *d_ptr, nullptr, *d_list, c->stream));
             out.entries = total;
+            CK(pool_alloc((void**)&out.cbox, sizeof(uint2) * cells, c->stream));
+            CK(pool_alloc((void**)&out.clist, sizeof(unsigned) * (size_t)(total ? total : 1), c->stream));
         } else {
             CK(launch_grid_static_lists(c->cell, c->d_ideal_wrapped, c->d_rmax, c->S, g[0], g[1], g[2], margin, *d_ptr, nullptr, *d_list,
                                         c->stream));
             out.static_entries = total;
+            std::vector<uint2> sbox(cells);
+            for (size_t i = 0; i < cells; ++i) sbox[i] = make_uint2(ptr[i], ptr[i + 1] - ptr[i]);
+            CK(upload(&out.sbox, sbox.data(), cells, c->stream));
         }
     }
     return SITB_OK;
@@ -344,8 +421,10 @@ static void free_grid(sitb_ctx* c) {
     for (int l = 0; l < 2; ++l) {
         pool_free(c->grid[l].ptr, c->stream); pool_free(c->grid[l].list, c->stream);
         pool_free(c->grid[l].sptr, c->stream); pool_free(c->grid[l].slist, c->stream);
+        pool_free(c->grid[l].sbox, c->stream); pool_free(c->grid[l].cbox, c->stream); pool_free(c->grid[l].clist, c->stream);
         c->grid[l] = GridLevelDev();
     }
+    c->fast_lists_dirty = true;
     c->n_grid_levels = 0;
     c->gx = c->gy = c->gz = 0;
 }
@@ -672,8 +751,113 @@ extern "C" int sitb_set_centers(sitb_ctx* c, const int32_t* cid, const double* w
     }
     CK(cudaMemcpyAsync(c->d_cid_orig, cid, sizeof(int) * (size_t)c->L, cudaMemcpyHostToDevice, c->stream));
     CK(cudaMemcpyAsync(c->d_cw_orig, w, sizeof(double) * (size_t)c->L, cudaMemcpyHostToDevice, c->stream));
+    std::vector<float2> cwf;
+    if (c->d_fast_cw) {
+        cwf.assign((size_t)c->Lpad, make_float2(0.f, -1.f));
+        c->cw_absmax = 0.0;
+        for (int k = 0; k < c->L; ++k) {
+            const int nv = c->h_nverts[k] ? c->h_nverts[k] : 1;
+            cwf[k] = make_float2((float)w_i[k], -1.0f / (float)nv);
+            if (cid_i[k] >= 0) c->cw_absmax = std::max(c->cw_absmax, std::fabs(w_i[k]));
+        }
+        CK(cudaMemcpyAsync(c->d_fast_cw, cwf.data(), sizeof(float2) * cwf.size(), cudaMemcpyHostToDevice, c->stream));
+        c->fast_lists_dirty = true;
+    }
     CK(cudaStreamSynchronize(c->stream));
     c->n_clusters = n_clusters;
+    return SITB_OK;
+}
+
+extern "C" int sitb_set_assign_mode(sitb_ctx* c, int32_t mode) {
+    if (!c) return fail(SITB_E_INVALID, "null context");
+    if (mode != SITB_ASSIGN_EXACT && mode != SITB_ASSIGN_TWO_TIER) return fail(SITB_E_INVALID, "sitb_set_assign_mode: mode %d", mode);
+    c->assign_mode = mode;
+    return SITB_OK;
+}
+
+extern "C" int sitb_two_tier_info(sitb_ctx* c, int32_t* available, double* tau, double* kappa, uint64_t* counts, int32_t reset) {
+    if (!c) return fail(SITB_E_INVALID, "null context");
+    CK(cudaSetDevice(c->device));
+    if (available) *available = (c->fast_tables_ok && c->n_grid_levels == 2) ? 1 : 0;
+    if (tau) *tau = c->fast_tau;
+    if (kappa) *kappa = c->fast_kappa;
+    if (counts) {
+        for (int i = 0; i < SITB_TWO_TIER_SLOTS; ++i) counts[i] = 0;
+        if (c->d_two_tier) {
+            unsigned long long h[1 + RECHECK_SLOTS];
+            CK(cudaMemcpyAsync(h, c->d_two_tier, sizeof(h), cudaMemcpyDeviceToHost, c->stream));
+            CK(cudaStreamSynchronize(c->stream));
+            for (int i = 0; i < SITB_TWO_TIER_SLOTS && i < RECHECK_SLOTS; ++i) counts[i] = h[1 + i];
+        }
+    }
+    if (reset && c->d_two_tier) CK(cudaMemsetAsync(c->d_two_tier, 0, sizeof(unsigned long long) * (1 + RECHECK_SLOTS), c->stream));
+    return SITB_OK;
+}
+
+// First tier (FP32, sitb_fill_fast.cu) over all frames, then the exact kernel over the rows it left undecided.
+// Returns 1 if the shape does not fit the first tier (the caller runs the exact kernel alone).
+static int two_tier_assign(sitb_ctx* c, const FillParams& base, int64_t n, double thr, int64_t* labels, double* confs,
+                           uint64_t* counts) {
+    if (!c->fast_tables_ok || c->n_grid_levels != 2 || c->n_clusters <= 0 || !(thr == thr) || std::isinf(thr) ||
+        !(c->cw_absmax <= 64.0) || !labels || !confs || n <= 0)
+        return 1;
+    const size_t rows = (size_t)n * c->M;
+    if (rows > c->recheck_rows_cap) {
+        pool_free(c->d_recheck, c->stream); c->d_recheck = nullptr; c->recheck_rows_cap = 0;
+        CK(pool_alloc((void**)&c->d_recheck, rows, c->stream));
+        c->recheck_rows_cap = rows;
+    }
+    if ((size_t)n > c->recheck_frames_cap) {
+        pool_free(c->d_frame_flag, c->stream); pool_free(c->d_frame_list, c->stream);
+        c->d_frame_flag = nullptr; c->d_frame_list = nullptr; c->recheck_frames_cap = 0;
+        CK(pool_alloc((void**)&c->d_frame_flag, sizeof(int) * (size_t)n, c->stream));
+        CK(pool_alloc((void**)&c->d_frame_list, sizeof(long long) * (size_t)n, c->stream));
+        c->recheck_frames_cap = (size_t)n;
+    }
+    if (c->fast_lists_dirty) {
+        const long long cells = (long long)c->gx * c->gy * c->gz;
+        for (int l = 0; l < 2; ++l)
+            CK(launch_sort_box_lists(c->grid[l].ptr, c->grid[l].list, c->d_cid, cells, c->grid[l].cbox, c->grid[l].clist, c->stream));
+        c->fast_lists_dirty = false;
+    }
+    CK(cudaMemsetAsync(c->d_recheck, 0, rows, c->stream));
+    CK(cudaMemsetAsync(c->d_frame_flag, 0, sizeof(int) * (size_t)n, c->stream));
+    CK(cudaMemsetAsync(c->d_two_tier, 0, sizeof(unsigned long long), c->stream));
+    FastParams f;
+    memset(&f, 0, sizeof(f));
+    f.ci0 = c->cell.ci[0]; f.ci1 = c->cell.ci[4]; f.ci2 = c->cell.ci[8];
+    f.Lx = (float)c->cell.c[0]; f.Ly = (float)c->cell.c[4]; f.Lz = (float)c->cell.c[8];
+    f.frames = base.frames; f.n_work = n;
+    f.A = c->A; f.S = c->S; f.M = c->M; f.L = c->L; f.Lpad = c->Lpad; f.NB = c->NB; f.m_magic = base.m_magic;
+    f.static_idx = c->d_static_idx; f.mobile_idx = c->d_mobile_idx; f.ideal_frac = c->d_ideal_frac;
+    f.tab.va = c->d_va; f.tab.ib = c->d_fast_ib; f.tab.ac = c->d_fast_ac; f.tab.cw = c->d_fast_cw;
+    f.bc = (float)(c->steepness * c->midpoint * 1.4426950408889634074);
+    f.kappa = std::nextafter((float)c->fast_kappa, 0.0f);
+    f.tau = std::nextafter((float)c->fast_tau, 1.0f);
+    f.thr = (float)thr;
+    f.dyn_dc = (float)(8.0 * c->fast_dc);
+    f.dynamic = c->dynamic; f.n_levels = 2;
+    const double shrink = 0.999;          // float rounding of the screen distances: stay inside the margins
+    for (int l = 0; l < 2; ++l) {
+        f.grid[l].cbox = c->grid[l].cbox; f.grid[l].clist = c->grid[l].clist;
+        f.grid[l].sbox = c->grid[l].sbox; f.grid[l].slist = c->grid[l].slist;
+        f.grid[l].margin_sq = (float)(c->grid[l].margin * c->grid[l].margin * shrink);
+    }
+    f.static_lim_sq = (float)(std::min(c->grid[1].margin * c->grid[1].margin, c->static_thr * c->static_thr) * shrink);
+    f.gx = c->gx; f.gy = c->gy; f.gz = c->gz;
+    f.labels = (long long*)labels; f.confs = confs; f.counts = (unsigned long long*)counts; f.n_clusters = c->n_clusters;
+    f.recheck = c->d_recheck; f.frame_flag = c->d_frame_flag; f.frame_list = c->d_frame_list;
+    f.n_list = c->d_two_tier; f.counters = c->d_two_tier + 1;
+    cudaError_t e = launch_assign_fast(f, c->n_sms, c->stream);
+    if (e == cudaErrorInvalidConfiguration) { cudaGetLastError(); return 1; }
+    if (e != cudaSuccess) return fail(SITB_E_CUDA, "first tier of the assign pass: %s", cudaGetErrorString(e));
+    // second tier: the exact kernel over the flagged frames, restricted to the flagged rows
+    FillParams p = base;
+    p.assign_thr = thr;
+    p.labels = (long long*)labels; p.confs = confs; p.counts = (unsigned long long*)counts;
+    p.frame_list = c->d_frame_list; p.n_work_dev = c->d_two_tier; p.row_filter = c->d_recheck; p.rows_by_frame = 1;
+    p.counters = nullptr;
+    CK(launch_fill(p, MODE_ASSIGN, c->n_sms, c->stream));
     return SITB_OK;
 }
 
@@ -683,6 +867,10 @@ extern "C" int sitb_pass_assign(sitb_ctx* c, int64_t begin, int64_t n, double th
     int rc = base_params(c, begin, n, p, "sitb_pass_assign");
     if (rc) return rc;
     CK(cudaSetDevice(c->device));
+    if (c->assign_mode == SITB_ASSIGN_TWO_TIER && !best && !rep && !rep_w && !site_best) {
+        rc = two_tier_assign(c, p, n, thr, labels, confs, counts);
+        if (rc <= 0) return rc;            // done (or failed); 1: shape not covered, fall through to the exact kernel
+    }
     p.assign_thr = thr;
     p.labels = (long long*)labels; p.confs = confs; p.counts = (unsigned long long*)counts;
     p.best = (unsigned long long*)best; p.rep = rep; p.rep_w = rep_w; p.site_best = (unsigned long long*)site_best;

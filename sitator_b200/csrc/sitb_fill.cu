@@ -238,8 +238,10 @@ __global__ void __launch_bounds__(DIAG ? SITB_K1_WARPS * 32 : 512) k_fill(const 
     const float Lx = (float)cell.c[0], Ly = (float)cell.c[4], Lz = (float)cell.c[8];
     const int W = 4 * NB;
 
-    for (long long w0 = (long long)blockIdx.x * FB; w0 < p.n_work; w0 += (long long)gridDim.x * FB) {
-        const int nb = (int)((p.n_work - w0 < FB) ? (p.n_work - w0) : FB);
+    // (second tier of the two-tier assign pass: the list length is only known on the device)
+    const long long n_work = p.n_work_dev ? (long long)*p.n_work_dev : p.n_work;
+    for (long long w0 = (long long)blockIdx.x * FB; w0 < n_work; w0 += (long long)gridDim.x * FB) {
+        const int nb = (int)((n_work - w0 < FB) ? (n_work - w0) : FB);
 
         // ---- 1. wrap the batch's static and mobile atoms (LandmarkAnalysis.py:182-189) ----
         for (int t = threadIdx.x; t < nb * (S + M); t += blockDim.x) {
@@ -390,7 +392,9 @@ __global__ void __launch_bounds__(DIAG ? SITB_K1_WARPS * 32 : 512) k_fill(const 
             const int j = jj - b * M;
             const long long fl = p.frame_list ? p.frame_list[w0 + b] : (w0 + b);
             const long long gframe = p.frame0 + fl;
-            const long long row_local = w0 * M + jj;                 // = (w0 + b) * M + j: row in this launch's outputs
+            // row in this launch's outputs: by list position, = (w0 + b) * M + j, or by frame
+            const long long row_local = p.rows_by_frame ? fl * M + j : w0 * M + jj;
+            if (p.row_filter && !p.row_filter[row_local]) continue;
             const unsigned long long row_global = (unsigned long long)(gframe * M + j);
             const double* sb = ss + (size_t)b * S * 3;
             const unsigned* lmap = lmap_all + (size_t)b * Spad;

@@ -113,8 +113,64 @@ struct FillParams {
     double* rep;                 // [C][L] optional sum conf*lvec
     double* rep_w;               // [C]
     unsigned long long* site_best; // [3C] optional max over rows of (conf, first row), same layout
+    // second tier of the two-tier assign pass (sitb_fill_fast.cu): redo only the rows the FP32 kernel could not decide
+    const unsigned long long* n_work_dev; // optional: number of frame_list entries, read on the device (overrides n_work)
+    const uint8_t* row_filter;            // optional [frames][M]: rows with a zero byte are skipped
+    int rows_by_frame;                    // with frame_list: outputs are indexed by frame, not by list position
 };
 
 cudaError_t launch_fill(const FillParams& p, int mode, int n_sms, cudaStream_t stream);
+
+// ---- two-tier assign pass: FP32 first tier (sitb_fill_fast.cu) -----------------------------------------
+// Per landmark (internal numbering): vertices, reciprocal upper cut-off bounds, logistic slopes, centre weight.
+struct FastTables {
+    const ushort4* va;   // [NB][Lpad] vertex ids (S = the always-passing dummy)
+    const float4* ib;    // [NB][Lpad] 1 / (Q * (1 + eps)): q * ib > 1  =>  the exact test d^2 > Q holds too
+    const float4* ac;    // [NB][Lpad] steepness * log2(e) / site_vert_dist
+    const float2* cw;    // [Lpad] (centre weight, -1 / n_vertices)
+};
+struct FastGrid {
+    const uint2* cbox;       // [cells] (offset, count) into clist
+    const unsigned* clist;   // landmark | cluster << 16, sorted by cluster; landmarks of no cluster left out
+    const uint2* sbox;       // [cells] (offset, count) into slist
+    const uint16_t* slist;   // static-lattice sites the box's candidate landmarks use
+    float margin_sq;         // frames whose static displacements^2 stay below use this level
+};
+enum : int { RECHECK_FRAME = 0, RECHECK_SUPPORT = 1, RECHECK_MARGIN = 2, RECHECK_THRESHOLD = 3, RECHECK_LONG = 4, RECHECK_ROWS = 5,
+             RECHECK_SLOTS = 8 };
+struct FastParams {
+    double ci0, ci1, ci2;        // diagonal of cellmat^-1
+    float Lx, Ly, Lz;
+    const double* frames;        // first frame of the launch
+    long long n_work;
+    int A, S, M, L, Lpad, NB;
+    unsigned m_magic;
+    const int* static_idx;
+    const int* mobile_idx;
+    const float* ideal_frac;     // [3][Spad] wrapped fractional static-lattice positions
+    FastTables tab;
+    float bc;                    // steepness * midpoint * log2(e)
+    float kappa;                 // q * ib <= kappa  =>  d^2 <= Q certainly
+    float tau;                   // bound on the relative error of an FP32 component value (and of the sums built on it)
+    float thr;                   // assignment threshold
+    float static_lim_sq;         // frames with a static displacement^2 above this are left to the exact kernel
+    float dyn_dc;                // float error of a Cartesian component (dynamic lattice map screen)
+    int dynamic, n_levels;
+    FastGrid grid[2];
+    int gx, gy, gz;
+    long long* labels;           // [n_work*M]
+    double* confs;
+    unsigned long long* counts;  // [C] optional
+    int n_clusters;
+    uint8_t* recheck;            // [n_work*M] zeroed by the caller; 1 = row left to the exact kernel
+    int* frame_flag;             // [n_work] zeroed by the caller
+    long long* frame_list;       // [n_work] frames with at least one such row
+    unsigned long long* n_list;  // [1] zeroed by the caller
+    unsigned long long* counters;// [RECHECK_SLOTS] reasons (+=)
+};
+// cudaErrorInvalidConfiguration: shape does not fit the first tier (the caller uses the exact kernel alone)
+cudaError_t launch_assign_fast(const FastParams& p, int n_sms, cudaStream_t stream);
+cudaError_t launch_sort_box_lists(const unsigned* ptr, const uint16_t* list, const int* cid, long long cells,
+                                  uint2* cbox, unsigned* clist, cudaStream_t stream);
 
 }  // namespace sitb

@@ -350,6 +350,22 @@ class LandmarkEngine(object):
         _native.check(self._lib.sitb_set_centers(self._ctx, cid.ctypes.data, w.ctypes.data, int(n_clusters)))
         self.n_clusters = int(n_clusters)
 
+    TWO_TIER_REASONS = ("frame", "support", "margin", "threshold", "long", "rows")
+
+    def set_assign_mode(self, mode):
+        """'exact': every component in float64 (default).  'two_tier': FP32 first tier with a proven error bound, the
+        exact kernel only for rows whose decisions lie inside the bound -- identical labels, confidences to ~1e-5."""
+        _native.check(self._lib.sitb_set_assign_mode(self._ctx, {"exact": 0, "two_tier": 1}[mode]))
+        self.assign_mode = mode
+
+    def two_tier_info(self, reset=False):
+        avail, tau, kappa = C.c_int32(), C.c_double(), C.c_double()
+        counts = (C.c_uint64 * 6)()
+        _native.check(self._lib.sitb_two_tier_info(self._ctx, C.byref(avail), C.byref(tau), C.byref(kappa), counts, int(reset)))
+        out = {"available": bool(avail.value), "tau": tau.value, "kappa": kappa.value}
+        out.update({"recheck_" + k: int(v) for k, v in zip(self.TWO_TIER_REASONS, counts)})
+        return out
+
     def pass_assign(self, threshold, begin=0, n=None, labels=None, confs=None, counts=None, best=None,
                     rep=None, rep_w=None, site_best=None):
         n = self.n_frames - begin if n is None else n
