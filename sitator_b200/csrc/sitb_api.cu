@@ -61,10 +61,7 @@ struct GridLevelDev {
     uint16_t* slist = nullptr;
     double margin = 0.0;
     unsigned long long entries = 0, static_entries = 0;
-    // first tier of the two-tier assign pass (sitb_fill_fast.cu)
-    uint2* sbox = nullptr;            // [cells] (offset, count) into slist
-    uint2* cbox = nullptr;            // [cells] (offset, count) into clist
-    unsigned* clist = nullptr;        // landmark | cluster << 16, sorted by cluster (rebuilt when the centres change)
+    std::vector<unsigned> h_sptr;     // host copy of sptr (first tier of the two-tier assign pass)
 };
 
 struct sitb_ctx {
@@ -128,7 +125,11 @@ struct sitb_ctx {
     float4* d_fast_ib = nullptr;
     float4* d_fast_ac = nullptr;
     float2* d_fast_cw = nullptr;
-    float* d_ideal_frac = nullptr;
+    float4* d_ideal_frac = nullptr;
+    uint2* d_fast_sbox = nullptr;             // [2 cells] both grid levels: (offset, count) into d_fast_slist
+    uint16_t* d_fast_slist = nullptr;         // 4 * site
+    uint2* d_fast_cbox = nullptr;             // [2 cells] (offset, count) into d_fast_clist (rebuilt when the centres change)
+    unsigned* d_fast_clist = nullptr;         // landmark | cluster << 16, sorted by cluster
     std::vector<uint8_t> h_nverts;            // internal numbering
     double fast_kappa = 0.0, fast_tau = 0.0, fast_dc = 0.0, cw_absmax = 0.0;
     bool fast_tables_ok = false, fast_lists_dirty = true;
@@ -152,8 +153,9 @@ static void free_ctx(sitb_ctx* c) {
     for (int l = 0; l < 2; ++l) {
         pool_free(c->grid[l].ptr, c->stream); pool_free(c->grid[l].list, c->stream);
         pool_free(c->grid[l].sptr, c->stream); pool_free(c->grid[l].slist, c->stream);
-        pool_free(c->grid[l].sbox, c->stream); pool_free(c->grid[l].cbox, c->stream); pool_free(c->grid[l].clist, c->stream);
     }
+    pool_free(c->d_fast_sbox, c->stream); pool_free(c->d_fast_slist, c->stream);
+    pool_free(c->d_fast_cbox, c->stream); pool_free(c->d_fast_clist, c->stream);
     pool_free(c->d_fast_ib, c->stream); pool_free(c->d_fast_ac, c->stream); pool_free(c->d_fast_cw, c->stream);
     pool_free(c->d_ideal_frac, c->stream); pool_free(c->d_recheck, c->stream); pool_free(c->d_frame_flag, c->stream);
     pool_free(c->d_frame_list, c->stream); pool_free(c->d_two_tier, c->stream);
@@ -343,14 +345,16 @@ extern "C" int sitb_create(const sitb_network_desc* d, int device, sitb_ctx** ou
             // + lg2.approx (2^-22 relative on |log2 P| <= 54), ex2.approx, product and summation roundings
             c->fast_tau = 1.25 * (tau_max + ln2 * 54.0 * 4.0 * u24 + 16.0 * u24) + 16.0 * u24;
             c->fast_dc = dc;
-            std::vector<float> idf((size_t)3 * ((c->S + 4) & ~3), 0.f);
-            const int Spad = (c->S + 4) & ~3;
-            for (int s2 = 0; s2 < c->S; ++s2)
+            std::vector<float4> idf((size_t)c->S);
+            for (int s2 = 0; s2 < c->S; ++s2) {
+                float fr[3];
                 for (int k = 0; k < 3; ++k) {
                     double f = c->cell.ci[4 * k] * d->host_ideal_static[3 * s2 + k];
                     f -= std::floor(f);
-                    idf[(size_t)k * Spad + s2] = (float)f;
+                    fr[k] = (float)f;
                 }
+                idf[s2] = make_float4(fr[0], fr[1], fr[2], 0.f);
+            }
             CKC(upload(&c->d_fast_ib, ib.data(), ib.size(), c->stream));
             CKC(upload(&c->d_fast_ac, ac.data(), ac.size(), c->stream));
             CKC(upload(&c->d_ideal_frac, idf.data(), idf.size(), c->stream));
@@ -403,15 +407,11 @@ static int build_grid_level(sitb_ctx* c, const int g[3], double margin, GridLeve
             CK(launch_grid_lists(c->cell, c->d_ideal_wrapped, c->d_va, c->d_radius, c->L, c->Lpad, c->NB, c->S, g[0], g[1], g[2], margin,
                                  *d_ptr, nullptr, *d_list, c->stream));
             out.entries = total;
-            CK(pool_alloc((void**)&out.cbox, sizeof(uint2) * cells, c->stream));
-            CK(pool_alloc((void**)&out.clist, sizeof(unsigned) * (size_t)(total ? total : 1), c->stream));
         } else {
             CK(launch_grid_static_lists(c->cell, c->d_ideal_wrapped, c->d_rmax, c->S, g[0], g[1], g[2], margin, *d_ptr, nullptr, *d_list,
                                         c->stream));
             out.static_entries = total;
-            std::vector<uint2> sbox(cells);
-            for (size_t i = 0; i < cells; ++i) sbox[i] = make_uint2(ptr[i], ptr[i + 1] - ptr[i]);
-            CK(upload(&out.sbox, sbox.data(), cells, c->stream));
+            out.h_sptr = ptr;
         }
     }
     return SITB_OK;
@@ -421,9 +421,11 @@ static void free_grid(sitb_ctx* c) {
     for (int l = 0; l < 2; ++l) {
         pool_free(c->grid[l].ptr, c->stream); pool_free(c->grid[l].list, c->stream);
         pool_free(c->grid[l].sptr, c->stream); pool_free(c->grid[l].slist, c->stream);
-        pool_free(c->grid[l].sbox, c->stream); pool_free(c->grid[l].cbox, c->stream); pool_free(c->grid[l].clist, c->stream);
         c->grid[l] = GridLevelDev();
     }
+    pool_free(c->d_fast_sbox, c->stream); pool_free(c->d_fast_slist, c->stream);
+    pool_free(c->d_fast_cbox, c->stream); pool_free(c->d_fast_clist, c->stream);
+    c->d_fast_sbox = nullptr; c->d_fast_slist = nullptr; c->d_fast_cbox = nullptr; c->d_fast_clist = nullptr;
     c->fast_lists_dirty = true;
     c->n_grid_levels = 0;
     c->gx = c->gy = c->gz = 0;
@@ -465,6 +467,24 @@ static int build_grid(sitb_ctx* c, double margin) {
     CK(cudaStreamSynchronize(c->stream));
     c->gx = g[0]; c->gy = g[1]; c->gz = g[2];
     c->n_grid_levels = 2;
+    if (c->fast_tables_ok && c->S <= 16000) {
+        // first tier of the two-tier assign pass: both levels' static-site lists in one array (entries = 4 * site)
+        const size_t cells = (size_t)g[0] * g[1] * g[2];
+        const size_t n0 = (size_t)c->grid[0].static_entries, n1 = (size_t)c->grid[1].static_entries;
+        std::vector<uint16_t> sl(n0 + n1 + 1);
+        CK(cudaMemcpy(sl.data(), c->grid[0].slist, sizeof(uint16_t) * n0, cudaMemcpyDeviceToHost));
+        CK(cudaMemcpy(sl.data() + n0, c->grid[1].slist, sizeof(uint16_t) * n1, cudaMemcpyDeviceToHost));
+        for (size_t i = 0; i < n0 + n1; ++i) sl[i] = (uint16_t)(4u * sl[i]);
+        std::vector<uint2> sbox(2 * cells);
+        for (int l = 0; l < 2; ++l)
+            for (size_t i = 0; i < cells; ++i)
+                sbox[l * cells + i] = make_uint2((unsigned)(l ? n0 : 0) + c->grid[l].h_sptr[i], c->grid[l].h_sptr[i + 1] - c->grid[l].h_sptr[i]);
+        CK(upload(&c->d_fast_slist, sl.data(), sl.size(), c->stream));
+        CK(upload(&c->d_fast_sbox, sbox.data(), sbox.size(), c->stream));
+        CK(pool_alloc((void**)&c->d_fast_cbox, sizeof(uint2) * 2 * cells, c->stream));
+        CK(pool_alloc((void**)&c->d_fast_clist, sizeof(unsigned) * (size_t)(c->grid[0].entries + c->grid[1].entries + 1), c->stream));
+        c->fast_lists_dirty = true;
+    }
     return SITB_OK;
 }
 
@@ -778,7 +798,7 @@ extern "C" int sitb_set_assign_mode(sitb_ctx* c, int32_t mode) {
 extern "C" int sitb_two_tier_info(sitb_ctx* c, int32_t* available, double* tau, double* kappa, uint64_t* counts, int32_t reset) {
     if (!c) return fail(SITB_E_INVALID, "null context");
     CK(cudaSetDevice(c->device));
-    if (available) *available = (c->fast_tables_ok && c->n_grid_levels == 2) ? 1 : 0;
+    if (available) *available = (c->fast_tables_ok && c->n_grid_levels == 2 && c->d_fast_cbox) ? 1 : 0;
     if (tau) *tau = c->fast_tau;
     if (kappa) *kappa = c->fast_kappa;
     if (counts) {
@@ -798,7 +818,7 @@ extern "C" int sitb_two_tier_info(sitb_ctx* c, int32_t* available, double* tau, 
 // Returns 1 if the shape does not fit the first tier (the caller runs the exact kernel alone).
 static int two_tier_assign(sitb_ctx* c, const FillParams& base, int64_t n, double thr, int64_t* labels, double* confs,
                            uint64_t* counts) {
-    if (!c->fast_tables_ok || c->n_grid_levels != 2 || c->n_clusters <= 0 || !(thr == thr) || std::isinf(thr) ||
+    if (!c->fast_tables_ok || c->n_grid_levels != 2 || !c->d_fast_cbox || c->n_clusters <= 0 || !(thr == thr) || std::isinf(thr) ||
         !(c->cw_absmax <= 64.0) || !labels || !confs || n <= 0)
         return 1;
     const size_t rows = (size_t)n * c->M;
@@ -817,7 +837,8 @@ static int two_tier_assign(sitb_ctx* c, const FillParams& base, int64_t n, doubl
     if (c->fast_lists_dirty) {
         const long long cells = (long long)c->gx * c->gy * c->gz;
         for (int l = 0; l < 2; ++l)
-            CK(launch_sort_box_lists(c->grid[l].ptr, c->grid[l].list, c->d_cid, cells, c->grid[l].cbox, c->grid[l].clist, c->stream));
+            CK(launch_sort_box_lists(c->grid[l].ptr, c->grid[l].list, c->d_cid, cells, l ? (unsigned)c->grid[0].entries : 0u,
+                                     c->d_fast_cbox + (size_t)l * cells, c->d_fast_clist, c->stream));
         c->fast_lists_dirty = false;
     }
     CK(cudaMemsetAsync(c->d_recheck, 0, rows, c->stream));
@@ -829,6 +850,7 @@ static int two_tier_assign(sitb_ctx* c, const FillParams& base, int64_t n, doubl
     f.Lx = (float)c->cell.c[0]; f.Ly = (float)c->cell.c[4]; f.Lz = (float)c->cell.c[8];
     f.frames = base.frames; f.n_work = n;
     f.A = c->A; f.S = c->S; f.M = c->M; f.L = c->L; f.Lpad = c->Lpad; f.NB = c->NB; f.m_magic = base.m_magic;
+    f.sm_magic = (unsigned)((0x100000000ull + (unsigned long long)(c->S + c->M) - 1ull) / (unsigned long long)(c->S + c->M));
     f.static_idx = c->d_static_idx; f.mobile_idx = c->d_mobile_idx; f.ideal_frac = c->d_ideal_frac;
     f.tab.va = c->d_va; f.tab.ib = c->d_fast_ib; f.tab.ac = c->d_fast_ac; f.tab.cw = c->d_fast_cw;
     f.bc = (float)(c->steepness * c->midpoint * 1.4426950408889634074);
@@ -836,15 +858,14 @@ static int two_tier_assign(sitb_ctx* c, const FillParams& base, int64_t n, doubl
     f.tau = std::nextafter((float)c->fast_tau, 1.0f);
     f.thr = (float)thr;
     f.dyn_dc = (float)(8.0 * c->fast_dc);
-    f.dynamic = c->dynamic; f.n_levels = 2;
+    f.dynamic = c->dynamic;
     const double shrink = 0.999;          // float rounding of the screen distances: stay inside the margins
-    for (int l = 0; l < 2; ++l) {
-        f.grid[l].cbox = c->grid[l].cbox; f.grid[l].clist = c->grid[l].clist;
-        f.grid[l].sbox = c->grid[l].sbox; f.grid[l].slist = c->grid[l].slist;
-        f.grid[l].margin_sq = (float)(c->grid[l].margin * c->grid[l].margin * shrink);
-    }
+    for (int l = 0; l < 2; ++l) f.margin_sq[l] = (float)(c->grid[l].margin * c->grid[l].margin * shrink);
+    f.cells = c->gx * c->gy * c->gz;
+    f.cbox = c->d_fast_cbox; f.clist = c->d_fast_clist; f.sbox = c->d_fast_sbox; f.slist = c->d_fast_slist;
     f.static_lim_sq = (float)(std::min(c->grid[1].margin * c->grid[1].margin, c->static_thr * c->static_thr) * shrink);
     f.gx = c->gx; f.gy = c->gy; f.gz = c->gz;
+    f.gxf = (float)c->gx; f.gyf = (float)c->gy; f.gzf = (float)c->gz;
     f.labels = (long long*)labels; f.confs = confs; f.counts = (unsigned long long*)counts; f.n_clusters = c->n_clusters;
     f.recheck = c->d_recheck; f.frame_flag = c->d_frame_flag; f.frame_list = c->d_frame_list;
     f.n_list = c->d_two_tier; f.counters = c->d_two_tier + 1;

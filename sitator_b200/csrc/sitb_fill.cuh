@@ -129,13 +129,6 @@ struct FastTables {
     const float4* ac;    // [NB][Lpad] steepness * log2(e) / site_vert_dist
     const float2* cw;    // [Lpad] (centre weight, -1 / n_vertices)
 };
-struct FastGrid {
-    const uint2* cbox;       // [cells] (offset, count) into clist
-    const unsigned* clist;   // landmark | cluster << 16, sorted by cluster; landmarks of no cluster left out
-    const uint2* sbox;       // [cells] (offset, count) into slist
-    const uint16_t* slist;   // static-lattice sites the box's candidate landmarks use
-    float margin_sq;         // frames whose static displacements^2 stay below use this level
-};
 enum : int { RECHECK_FRAME = 0, RECHECK_SUPPORT = 1, RECHECK_MARGIN = 2, RECHECK_THRESHOLD = 3, RECHECK_LONG = 4, RECHECK_ROWS = 5,
              RECHECK_SLOTS = 8 };
 struct FastParams {
@@ -144,20 +137,28 @@ struct FastParams {
     const double* frames;        // first frame of the launch
     long long n_work;
     int A, S, M, L, Lpad, NB;
-    unsigned m_magic;
+    unsigned m_magic;            // ceil(2^32 / M)
+    unsigned sm_magic;           // ceil(2^32 / (S + M))
     const int* static_idx;
     const int* mobile_idx;
-    const float* ideal_frac;     // [3][Spad] wrapped fractional static-lattice positions
+    const float4* ideal_frac;    // [S] wrapped fractional static-lattice positions
     FastTables tab;
     float bc;                    // steepness * midpoint * log2(e)
     float kappa;                 // q * ib <= kappa  =>  d^2 <= Q certainly
     float tau;                   // bound on the relative error of an FP32 component value (and of the sums built on it)
     float thr;                   // assignment threshold
     float static_lim_sq;         // frames with a static displacement^2 above this are left to the exact kernel
+    float margin_sq[2];          // frames whose static displacements^2 stay below margin_sq[l] may use grid level l
     float dyn_dc;                // float error of a Cartesian component (dynamic lattice map screen)
-    int dynamic, n_levels;
-    FastGrid grid[2];
+    int dynamic;
+    // candidate grid, both levels in one set of arrays (level l, box b -> entry l * cells + b)
+    int cells;
+    const uint2* cbox;           // [2 cells] (offset, count) into clist
+    const unsigned* clist;       // landmark | cluster << 16, sorted by cluster; landmarks of no cluster left out
+    const uint2* sbox;           // [2 cells] (offset, count) into slist
+    const uint16_t* slist;       // 4 * static-lattice site, for the sites the box's candidate landmarks use
     int gx, gy, gz;
+    float gxf, gyf, gzf;
     long long* labels;           // [n_work*M]
     double* confs;
     unsigned long long* counts;  // [C] optional
@@ -170,7 +171,8 @@ struct FastParams {
 };
 // cudaErrorInvalidConfiguration: shape does not fit the first tier (the caller uses the exact kernel alone)
 cudaError_t launch_assign_fast(const FastParams& p, int n_sms, cudaStream_t stream);
-cudaError_t launch_sort_box_lists(const unsigned* ptr, const uint16_t* list, const int* cid, long long cells,
+// candidate lists of level `level`: the grid's landmark lists sorted by cluster, written at clist + base
+cudaError_t launch_sort_box_lists(const unsigned* ptr, const uint16_t* list, const int* cid, long long cells, unsigned base,
                                   uint2* cbox, unsigned* clist, cudaStream_t stream);
 
 }  // namespace sitb

@@ -8,8 +8,8 @@
 //   DotProdClassifier.pyx:166-189 |centre . x| argmax + threshold       -> FP32 with an error bound
 //
 // Two tiers: every landmark-vector component is evaluated in FP32 with a proven bound on its error
-// (sitb_api.cu: fast_tables).  A row's DECISIONS are taken from the FP32 values only when they hold for every value
-// inside the bound:
+// (sitb_api.cu: sitb_create, "error model").  A row's DECISIONS are taken from the FP32 values only when they hold
+// for every value inside the bound:
 //   support    q * ib > 1       =>  d^2 > Q in exact arithmetic (component is zero, helpers.pyx:199-203)
 //              q * ib <= kappa  =>  d^2 <= Q in exact arithmetic; in between the row is undecided
 //   arg-max    best - second > 2 B,   B = tau * sum |value * weight|   (DotProdClassifier.pyx:181)
@@ -17,47 +17,49 @@
 // Undecided rows (and whole frames with a static atom beyond the candidate-grid margin, an ambiguous dynamic
 // lattice map, or more than 64 non-zero components) are flagged; the caller then runs the exact float64 kernel on
 // exactly those rows (FillParams::row_filter).  Labels therefore equal the exact kernel's by construction;
-// confidences of the rows decided here carry the FP32 error (<= tau * sum |value * weight|, ~1e-5).
+// confidences of the rows decided here carry the FP32 error (<= tau * sum |value * weight|, measured ~1e-6).
 //
 // Work decomposition as in k_fill: a CTA takes a batch of frames, its warps claim (frame, mobile atom) tasks.  Per
 // task: FP32 squared distances to the static sites of the atom's grid box; every candidate landmark of the box
-// (sorted by cluster, landmarks of no cluster left out: sitb_api.cu) is tested against its cut-off with one
+// (sorted by cluster, landmarks of no cluster left out: k_sort_box_lists) is tested against its cut-off with one
 // compare on max_h q_h * ib_h; survivors are compacted, their values evaluated by one lane each, and the per-cluster
 // sums fall out of one segmented warp scan because the list is sorted by cluster.
+//
+// Shared-memory layout is chosen for few address computations: one record per landmark (reciprocal bounds, slopes,
+// vertex byte offsets, centre weight) read with immediate offsets from one base; positions as float4 per atom.
 #include "sitb_fill.cuh"
 #include <math_constants.h>
 
 namespace sitb {
 
-struct FastSmem {
-    int Spad, Mpad;
-    size_t off_va, off_ib, off_ac, off_cw, off_if, off_fs, off_fm, off_lmap, off_seen, off_warp, warp_bytes, off_hist,
-        off_misc, total;
-};
-
 static constexpr int SURV_CAP = 64;
+
+// record of a landmark in shared memory, in 16-byte units: [0, NB) reciprocal bounds, [NB, 2 NB) slopes,
+// then NB x 8 bytes of vertex byte offsets (4 * site, uint16) and (centre weight, -1 / n_vertices)
+__host__ __device__ constexpr int rec_units(int NB) { return 2 * NB + (NB * 8 + 8 + 15) / 16; }
+
+struct FastSmem {
+    int Spad;                  // floats per warp for the squared distances (S + 1 rounded up)
+    unsigned off_rec, off_if, off_fs, off_fm, off_lmap, off_seen, off_warp, warp_bytes, off_hist, off_misc, total;
+};
 
 __host__ __device__ inline FastSmem fast_layout(int S, int M, int Lpad, int NB, int warps, int fb, int n_clusters,
                                                 int dynamic, int with_hist) {
     FastSmem l;
     l.Spad = (S + 4) & ~3;          // room for the dummy site S
-    l.Mpad = (M + 3) & ~3;
     size_t o = 0;
-    l.off_ib = o;   o += sizeof(float4) * (size_t)NB * Lpad;
-    l.off_ac = o;   o += sizeof(float4) * (size_t)NB * Lpad;
-    l.off_va = o;   o += sizeof(ushort4) * (size_t)NB * Lpad;
-    l.off_cw = o;   o += sizeof(float2) * (size_t)Lpad;
-    l.off_if = o;   o += sizeof(float) * 3 * (size_t)l.Spad;
-    l.off_fs = o;   o += sizeof(float) * 3 * (size_t)l.Spad * fb;
-    l.off_fm = o;   o += sizeof(float) * 3 * (size_t)l.Mpad * fb;
-    l.off_lmap = o; o += dynamic ? sizeof(unsigned) * (size_t)l.Spad * fb : 0;
-    l.off_seen = o; o += dynamic ? sizeof(unsigned) * (size_t)l.Spad * fb : 0;
-    l.warp_bytes = (sizeof(float) * (size_t)l.Spad + sizeof(unsigned) * SURV_CAP + 15) & ~(size_t)15;
+    l.off_rec = (unsigned)o;  o += 16 * (size_t)rec_units(NB) * Lpad;
+    l.off_if = (unsigned)o;   o += sizeof(float4) * (size_t)S;
+    l.off_fs = (unsigned)o;   o += sizeof(float4) * (size_t)S * fb;
+    l.off_fm = (unsigned)o;   o += sizeof(float4) * (size_t)M * fb;
+    l.off_lmap = (unsigned)o; o += dynamic ? sizeof(unsigned) * (size_t)l.Spad * fb : 0;
+    l.off_seen = (unsigned)o; o += dynamic ? sizeof(unsigned) * (size_t)l.Spad * fb : 0;
+    l.warp_bytes = (unsigned)((sizeof(float) * (size_t)l.Spad + sizeof(unsigned) * SURV_CAP + 15) & ~(size_t)15);
     o = (o + 15) & ~(size_t)15;
-    l.off_warp = o; o += l.warp_bytes * (size_t)warps;
-    l.off_hist = o; o += with_hist ? sizeof(unsigned) * (size_t)(n_clusters > 0 ? n_clusters : 1) : 0;
-    l.off_misc = o; o += sizeof(int) * (size_t)(fb + 1);
-    l.total = (o + 15) & ~(size_t)15;
+    l.off_warp = (unsigned)o; o += (size_t)l.warp_bytes * warps;
+    l.off_hist = (unsigned)o; o += with_hist ? sizeof(unsigned) * (size_t)(n_clusters > 0 ? n_clusters : 1) : 0;
+    l.off_misc = (unsigned)o; o += sizeof(int) * (size_t)(fb + 1);
+    l.total = (unsigned)((o + 15) & ~(size_t)15);
     return l;
 }
 
@@ -71,13 +73,25 @@ __device__ __forceinline__ float cfrac(float u) {
     return __fsub_rn(u, __fsub_rn(__fadd_rn(u, magic), magic));
 }
 
-__device__ __forceinline__ float dist2f(float ax, float ay, float az, float bx, float by, float bz, float Lx, float Ly,
-                                        float Lz) {
-    const float cx = cfrac(ax - bx) * Lx, cy = cfrac(ay - by) * Ly, cz = cfrac(az - bz) * Lz;
+__device__ __forceinline__ float dist2f(const float4 a, const float4 b, float Lx, float Ly, float Lz) {
+    const float cx = cfrac(a.x - b.x) * Lx, cy = cfrac(a.y - b.y) * Ly, cz = cfrac(a.z - b.z) * Lz;
     return fmaf(cz, cz, fmaf(cy, cy, cx * cx));
 }
 
-__device__ __forceinline__ void flag_row(const FastParams& p, long long row, long long frame, int reason) {
+// shared-memory accesses by byte address (one base register + immediate offsets)
+__device__ __forceinline__ float lds_f(unsigned a) { float v; asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a)); return v; }
+__device__ __forceinline__ float4 lds_f4(unsigned a) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ uint2 lds_u2(unsigned a) { uint2 v; asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(a)); return v; }
+__device__ __forceinline__ float2 lds_f2(unsigned a) { float2 v; asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(a)); return v; }
+__device__ __forceinline__ unsigned lds_u(unsigned a) { unsigned v; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
+__device__ __forceinline__ void sts_f(unsigned a, float v) { asm volatile("st.shared.f32 [%0], %1;" ::"r"(a), "f"(v) : "memory"); }
+__device__ __forceinline__ void sts_u(unsigned a, unsigned v) { asm volatile("st.shared.u32 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
+
+__device__ __noinline__ void flag_row(const FastParams& p, unsigned row, long long frame, int reason) {
     p.recheck[row] = 1;
     if (atomicExch(&p.frame_flag[frame], 1) == 0) {
         const unsigned long long at = atomicAdd(p.n_list, 1ull);
@@ -87,173 +101,190 @@ __device__ __forceinline__ void flag_row(const FastParams& p, long long row, lon
     atomicAdd(&p.counters[RECHECK_ROWS], 1ull);
 }
 
+template <int NB, bool DYN>
 __global__ void __launch_bounds__(1024, 1) k_assign_fast(const __grid_constant__ FastParams p, const int FB,
                                                          const __grid_constant__ FastSmem lay) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
+    constexpr int RU = rec_units(NB);
+    constexpr unsigned REC = 16u * RU;            // bytes per landmark record
+    constexpr unsigned OFF_AC = 16u * NB, OFF_VA = 32u * NB, OFF_CW = 32u * NB + 8u * NB;
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
     const int nwarps = blockDim.x >> 5;
-    const int S = p.S, M = p.M, Lpad = p.Lpad, NB = p.NB;
-    const int Spad = lay.Spad, Mpad = lay.Mpad;
-    float4* tib = (float4*)(smem_raw + lay.off_ib);
-    float4* tac = (float4*)(smem_raw + lay.off_ac);
-    ushort4* tva = (ushort4*)(smem_raw + lay.off_va);
-    float2* tcw = (float2*)(smem_raw + lay.off_cw);
-    float* idf = (float*)(smem_raw + lay.off_if);          // [3][Spad]
-    float* fs = (float*)(smem_raw + lay.off_fs);           // [FB][3][Spad]
-    float* fm = (float*)(smem_raw + lay.off_fm);           // [FB][3][Mpad]
+    const int S = p.S, M = p.M;
+    const int Spad = lay.Spad;
+    const unsigned sbase = (unsigned)__cvta_generic_to_shared(smem_raw);
+    const unsigned a_rec = sbase + lay.off_rec;
+    float4* idf = (float4*)(smem_raw + lay.off_if);          // [S]
+    float4* fs = (float4*)(smem_raw + lay.off_fs);           // [FB][S]
+    float4* fm = (float4*)(smem_raw + lay.off_fm);           // [FB][M]
     unsigned* lmap_all = (unsigned*)(smem_raw + lay.off_lmap);
     unsigned* seen_all = (unsigned*)(smem_raw + lay.off_seen);
-    unsigned char* wscratch = smem_raw + lay.off_warp + (size_t)warp * lay.warp_bytes;
-    float* qfw = (float*)wscratch;                         // [Spad] squared screen distances, by static site
-    unsigned* surv = (unsigned*)(wscratch + sizeof(float) * (size_t)Spad);   // [SURV_CAP]
+    const unsigned a_q = sbase + lay.off_warp + (unsigned)warp * lay.warp_bytes;      // float[Spad], by 4 * static site
+    const unsigned a_surv = a_q + 4u * (unsigned)Spad;                                // unsigned[SURV_CAP]
     unsigned* hist = (unsigned*)(smem_raw + lay.off_hist);
     int* task_counter = (int*)(smem_raw + lay.off_misc);
-    int* glevel = task_counter + 1;                        // [FB]
+    int* glevel = task_counter + 1;                          // [FB]
 
-    for (int i = threadIdx.x; i < NB * Lpad; i += blockDim.x) {
-        tib[i] = p.tab.ib[i];
-        tac[i] = p.tab.ac[i];
-        tva[i] = p.tab.va[i];
+    // ---- stage the landmark records once per CTA ----
+    for (int i = threadIdx.x; i < p.Lpad; i += blockDim.x) {
+        uint4* r = (uint4*)(smem_raw + lay.off_rec) + (size_t)i * RU;
+        unsigned tail[4 * (RU - 2 * NB)];
+#pragma unroll
+        for (int blk = 0; blk < NB; ++blk) {
+            const float4 b = p.tab.ib[(size_t)blk * p.Lpad + i], a = p.tab.ac[(size_t)blk * p.Lpad + i];
+            r[blk] = make_uint4(__float_as_uint(b.x), __float_as_uint(b.y), __float_as_uint(b.z), __float_as_uint(b.w));
+            r[NB + blk] = make_uint4(__float_as_uint(a.x), __float_as_uint(a.y), __float_as_uint(a.z), __float_as_uint(a.w));
+            const ushort4 v = p.tab.va[(size_t)blk * p.Lpad + i];
+            tail[2 * blk] = (4u * v.x) | ((4u * v.y) << 16);
+            tail[2 * blk + 1] = (4u * v.z) | ((4u * v.w) << 16);
+        }
+        const float2 cw = p.tab.cw[i];
+        tail[2 * NB] = __float_as_uint(cw.x);
+        tail[2 * NB + 1] = __float_as_uint(cw.y);
+#pragma unroll
+        for (int t = 2 * NB + 2; t < 4 * (RU - 2 * NB); ++t) tail[t] = 0u;
+#pragma unroll
+        for (int t = 0; t < RU - 2 * NB; ++t) r[2 * NB + t] = make_uint4(tail[4 * t], tail[4 * t + 1], tail[4 * t + 2], tail[4 * t + 3]);
     }
-    for (int i = threadIdx.x; i < Lpad; i += blockDim.x) tcw[i] = p.tab.cw[i];
-    for (int i = threadIdx.x; i < 3 * Spad; i += blockDim.x) idf[i] = p.ideal_frac[i];
+    for (int i = threadIdx.x; i < S; i += blockDim.x) idf[i] = p.ideal_frac[i];
     if (p.counts)
         for (int i = threadIdx.x; i < p.n_clusters; i += blockDim.x) hist[i] = 0u;
-    if (lane == 0) qfw[S] = 0.f;                           // dummy vertex: distance 0
+    if (lane == 0) sts_f(a_q + 4u * (unsigned)S, 0.f);       // dummy vertex: distance 0
     __syncthreads();
 
     const float Lx = p.Lx, Ly = p.Ly, Lz = p.Lz;
-    const int n_levels = p.n_levels;
-    const float m0 = p.grid[0].margin_sq, m1 = p.grid[1].margin_sq, lim = p.static_lim_sq;
+    const float m0 = p.margin_sq[0], m1 = p.margin_sq[1], lim = p.static_lim_sq;
     const float bc = p.bc, kappa = p.kappa;
+    const int SM = S + M;
 
     for (long long w0 = (long long)blockIdx.x * FB; w0 < p.n_work; w0 += (long long)gridDim.x * FB) {
         const int nb = (int)((p.n_work - w0 < FB) ? (p.n_work - w0) : FB);
 
         // ---- 1. fractional coordinates of the batch's atoms (LandmarkAnalysis.py:182-189; float64, then rounded) ----
-        for (int t = threadIdx.x; t < nb * (S + M); t += blockDim.x) {
-            const int b = t / (S + M), r = t - b * (S + M);
+        for (int t = threadIdx.x; t < nb * SM; t += blockDim.x) {
+            const int b = (int)__umulhi((unsigned)t, p.sm_magic), r = t - b * SM;
             const double* __restrict__ fr = p.frames + (size_t)(w0 + b) * (size_t)p.A * 3;
             const int a = (r < S) ? p.static_idx[r] : p.mobile_idx[r - S];
             double f0 = fr[3 * a + 0] * p.ci0, f1 = fr[3 * a + 1] * p.ci1, f2 = fr[3 * a + 2] * p.ci2;
             f0 -= floor(f0); f1 -= floor(f1); f2 -= floor(f2);
-            if (r < S) {
-                float* d = fs + (size_t)b * 3 * Spad;
-                d[r] = (float)f0; d[Spad + r] = (float)f1; d[2 * Spad + r] = (float)f2;
-            } else {
-                float* d = fm + (size_t)b * 3 * Mpad;
-                d[r - S] = (float)f0; d[Mpad + r - S] = (float)f1; d[2 * Mpad + r - S] = (float)f2;
-            }
+            const float4 v = make_float4((float)f0, (float)f1, (float)f2, 0.f);
+            if (r < S) fs[b * S + r] = v;
+            else fm[b * M + (r - S)] = v;
         }
-        if (p.dynamic)
+        if (DYN)
             for (int t = threadIdx.x; t < nb * Spad; t += blockDim.x) seen_all[t] = 0u;
         if (threadIdx.x == 0) *task_counter = 0;
         if (threadIdx.x < FB) glevel[threadIdx.x] = 0;
         __syncthreads();
 
         // ---- 2. static lattice (helpers.pyx:55-92): FP32 screen; frames it cannot clear go to the exact kernel ----
-        if (!p.dynamic) {
-            for (int t = threadIdx.x; t < nb * S; t += blockDim.x) {
-                const int b = t / S, s = t - b * S;
-                const float* fsb = fs + (size_t)b * 3 * Spad;
-                const float q = dist2f(fsb[s], fsb[Spad + s], fsb[2 * Spad + s], idf[s], idf[Spad + s], idf[2 * Spad + s], Lx, Ly, Lz);
-                const int lvl = (q > lim) ? n_levels : ((q > m0) ? ((q > m1) ? n_levels : 1) : 0);
-                if (lvl) atomicMax(&glevel[b], lvl);
-            }
+        if (!DYN) {
+            for (int b = 0; b < nb; ++b)
+                for (int s = threadIdx.x; s < S; s += blockDim.x) {
+                    const float q = dist2f(fs[b * S + s], idf[s], Lx, Ly, Lz);
+                    const int lvl = (q > lim) ? 2 : ((q > m0) ? ((q > m1) ? 2 : 1) : 0);
+                    if (lvl) atomicMax(&glevel[b], lvl);
+                }
         } else {
             for (int t = warp; t < nb * S; t += nwarps) {
                 const int b = t / S, li = t - b * S;
-                const float* fsb = fs + (size_t)b * 3 * Spad;
-                const float ix = idf[li], iy = idf[Spad + li], iz = idf[2 * Spad + li];
+                const float4* fsb = fs + b * S;
+                const float4 id = idf[li];
                 float qmin = CUDART_INF_F;
-                for (int j = lane; j < S; j += 32)
-                    qmin = fminf(qmin, dist2f(fsb[j], fsb[Spad + j], fsb[2 * Spad + j], ix, iy, iz, Lx, Ly, Lz));
+                for (int j = lane; j < S; j += 32) qmin = fminf(qmin, dist2f(fsb[j], id, Lx, Ly, Lz));
 #pragma unroll
                 for (int o = 16; o > 0; o >>= 1) qmin = fminf(qmin, __shfl_xor_sync(0xffffffffu, qmin, o));
                 // an atom whose float distance is within the float error of the smallest could be the exact arg-min
                 const float dc = p.dyn_dc;
                 const float bound = qmin + 2.0f * (2.0f * sqrtf(3.0f * qmin) * dc + 3.0f * dc * dc + 1e-6f * qmin) + 1e-12f;
                 int cnt = 0, bj = 0;
-                for (int j = lane; j < S; j += 32) {
-                    const float q = dist2f(fsb[j], fsb[Spad + j], fsb[2 * Spad + j], ix, iy, iz, Lx, Ly, Lz);
-                    if (!(q > bound)) { ++cnt; bj = j; }
-                }
+                for (int j = lane; j < S; j += 32)
+                    if (!(dist2f(fsb[j], id, Lx, Ly, Lz) > bound)) { ++cnt; bj = j; }
                 cnt = __reduce_add_sync(0xffffffffu, cnt);
                 bj = __reduce_max_sync(0xffffffffu, bj);
                 if (lane == 0) {
-                    lmap_all[(size_t)b * Spad + li] = (unsigned)bj;
-                    atomicAdd(&seen_all[(size_t)b * Spad + bj], 1u);
-                    int lvl = (qmin > lim) ? n_levels : ((qmin > m0) ? ((qmin > m1) ? n_levels : 1) : 0);
-                    if (cnt != 1) lvl = n_levels;                 // ambiguous nearest atom
+                    lmap_all[b * Spad + li] = (unsigned)bj;
+                    atomicAdd(&seen_all[b * Spad + bj], 1u);
+                    int lvl = (qmin > lim) ? 2 : ((qmin > m0) ? ((qmin > m1) ? 2 : 1) : 0);
+                    if (cnt != 1) lvl = 2;                        // ambiguous nearest atom
                     if (lvl) atomicMax(&glevel[b], lvl);
                 }
             }
             __syncthreads();
-            for (int t = threadIdx.x; t < nb * S; t += blockDim.x) {
-                const int b = t / S, s = t - b * S;
-                if (seen_all[(size_t)b * Spad + s] != 1u) atomicMax(&glevel[b], n_levels);   // unassigned / doubly assigned
-            }
+            for (int b = 0; b < nb; ++b)
+                for (int s = threadIdx.x; s < S; s += blockDim.x)
+                    if (seen_all[b * Spad + s] != 1u) atomicMax(&glevel[b], 2);      // unassigned / doubly assigned
         }
         __syncthreads();
 
         // ---- 3. one warp per (frame, mobile atom) ------------------------------------------------------------
+        const int ntask = nb * M;
+        const unsigned row0 = (unsigned)(w0 * M);
         for (;;) {
             int jj = 0;
             if (lane == 0) jj = atomicAdd(task_counter, 1);
             jj = __shfl_sync(0xffffffffu, jj, 0);
-            if (jj >= nb * M) break;
-            const int b = p.m_magic ? (int)__umulhi((unsigned)jj, p.m_magic) : jj / M;
-            const int j = jj - b * M;
-            const long long row = w0 * M + jj;
+            if (jj >= ntask) break;
+            const int b = (int)__umulhi((unsigned)jj, p.m_magic);
+            const unsigned row = row0 + (unsigned)jj;          // < 2^32 landmark vectors per launch (sitb_api.cu: base_params)
             const int lv = glevel[b];
-            if (lv >= n_levels) {
+            if (lv >= 2) {
                 if (lane == 0) flag_row(p, row, w0 + b, RECHECK_FRAME);
                 continue;
             }
-            const float* fsb = fs + (size_t)b * 3 * Spad;
-            const float* fmb = fm + (size_t)b * 3 * Mpad;
-            const unsigned* lmap = lmap_all + (size_t)b * Spad;
-            const float mx = fmb[j], my = fmb[Mpad + j], mz = fmb[2 * Mpad + j];
-            int ix = (int)(mx * (float)p.gx), iy = (int)(my * (float)p.gy), iz = (int)(mz * (float)p.gz);
-            ix = ix < 0 ? 0 : (ix >= p.gx ? p.gx - 1 : ix);
-            iy = iy < 0 ? 0 : (iy >= p.gy ? p.gy - 1 : iy);
-            iz = iz < 0 ? 0 : (iz >= p.gz ? p.gz - 1 : iz);
-            const int box = (ix * p.gy + iy) * p.gz + iz;
-            const FastGrid& g = p.grid[lv];
-            const uint2 sp = __ldg(g.sbox + box);
-            const uint2 cp = __ldg(g.cbox + box);
+            const unsigned a_fs = sbase + lay.off_fs + 16u * (unsigned)(b * S);
+            const float4 mp = fm[jj];                          // fm is [b][M]: index b * M + j = jj
+            const int ix = min((int)(mp.x * p.gxf), p.gx - 1), iy = min((int)(mp.y * p.gyf), p.gy - 1),
+                      iz = min((int)(mp.z * p.gzf), p.gz - 1);
+            const int box = lv * p.cells + (ix * p.gy + iy) * p.gz + iz;
+            const uint2 sp = __ldg(p.sbox + box);
+            const uint2 cp = __ldg(p.cbox + box);
 
             // 3a. squared distances to the box's static sites (helpers.pyx:99-103, :174-178)
-            for (unsigned i = lane; i < sp.y; i += 32) {
-                const int s = (int)__ldg(g.slist + sp.x + i);
-                const int src = p.dynamic ? (int)lmap[s] : s;
-                qfw[s] = dist2f(fsb[src], fsb[Spad + src], fsb[2 * Spad + src], mx, my, mz, Lx, Ly, Lz);
+            {
+                const uint16_t* sl = p.slist + sp.x;
+#pragma unroll 1
+                for (unsigned i0 = 0; i0 < sp.y; i0 += 32) {
+                    const unsigned i = i0 + lane;
+                    if (i < sp.y) {
+                        const unsigned s4 = __ldg(sl + i);         // 4 * site
+                        unsigned src4 = s4;
+                        if (DYN) src4 = 4u * lmap_all[b * Spad + (s4 >> 2)];
+                        sts_f(a_q + s4, dist2f(lds_f4(a_fs + 4u * src4), mp, Lx, Ly, Lz));
+                    }
+                }
             }
             __syncwarp();
 
             // 3b. cut-off test of every candidate (helpers.pyx:197-203) on max_h q_h / Q_h; survivors compacted
             int nsurv = 0;
             unsigned amb_any = 0u;
-            for (unsigned i0 = 0; i0 < cp.y; i0 += 32) {
-                const unsigned i = i0 + lane;
-                const bool in = i < cp.y;
-                const unsigned rec = in ? __ldg(g.clist + cp.x + i) : 0u;
-                const int k = (int)(rec & 0xFFFFu);
-                float m = 0.f;
-                for (int blk = 0; blk < NB; ++blk) {
-                    const ushort4 vv = tva[(size_t)blk * Lpad + k];
-                    const float4 bb = tib[(size_t)blk * Lpad + k];
-                    m = fmaxf(fmaxf(fmaxf(m, qfw[vv.x] * bb.x), fmaxf(qfw[vv.y] * bb.y, qfw[vv.z] * bb.z)), qfw[vv.w] * bb.w);
-                }
-                const bool keep = in && !(m > 1.0f);
-                const unsigned km = __ballot_sync(0xffffffffu, keep);
-                amb_any |= __ballot_sync(0xffffffffu, keep && (m > kappa));
-                if (keep) {
+            {
+                const unsigned* cl = p.clist + cp.x;
+#pragma unroll 1
+                for (unsigned i0 = 0; i0 < cp.y; i0 += 32) {
+                    const unsigned i = i0 + lane;
+                    const bool in = i < cp.y;
+                    unsigned rec = 0u;
+                    if (in) rec = __ldg(cl + i);
+                    const unsigned ar = a_rec + (rec & 0xFFFFu) * REC;
+                    float m = 0.f;
+#pragma unroll
+                    for (int blk = 0; blk < NB; ++blk) {
+                        const uint2 vv = lds_u2(ar + OFF_VA + 8u * blk);
+                        const float4 bb = lds_f4(ar + 16u * blk);
+                        const float q0 = lds_f(a_q + (vv.x & 0xFFFFu)), q1 = lds_f(a_q + (vv.x >> 16));
+                        const float q2 = lds_f(a_q + (vv.y & 0xFFFFu)), q3 = lds_f(a_q + (vv.y >> 16));
+                        m = fmaxf(fmaxf(fmaxf(m, q0 * bb.x), fmaxf(q1 * bb.y, q2 * bb.z)), q3 * bb.w);
+                    }
+                    const bool keep = in && !(m > 1.0f);
+                    const unsigned km = __ballot_sync(0xffffffffu, keep);
+                    amb_any |= __ballot_sync(0xffffffffu, keep && (m > kappa));
                     const int q = nsurv + __popc(km & lanemask_lt());
-                    if (q < SURV_CAP) surv[q] = rec;
+                    if (keep && q < SURV_CAP) sts_u(a_surv + 4u * (unsigned)q, rec);
+                    nsurv += __popc(km);
                 }
-                nsurv += __popc(km);
             }
             if (amb_any != 0u || nsurv > SURV_CAP) {
                 if (lane == 0) flag_row(p, row, w0 + b, amb_any ? RECHECK_SUPPORT : RECHECK_LONG);
@@ -271,21 +302,22 @@ __global__ void __launch_bounds__(1024, 1) k_assign_fast(const __grid_constant__
                 cid[c] = 0x7FFF;
                 pr[c] = 0.f;
                 const int e = 32 * c + lane;
-                if (c * 32 < nsurv && e < nsurv) {
-                    const unsigned rec = surv[e];
-                    const int k = (int)(rec & 0xFFFFu);
+                if ((c == 0 || nsurv > 32) && e < nsurv) {
+                    const unsigned rec = lds_u(a_surv + 4u * (unsigned)e);
+                    const unsigned ar = a_rec + (rec & 0xFFFFu) * REC;
                     cid[c] = (int)(rec >> 16);
                     float P = 1.0f;
+#pragma unroll
                     for (int blk = 0; blk < NB; ++blk) {
-                        const ushort4 vv = tva[(size_t)blk * Lpad + k];
-                        const float4 aa = tac[(size_t)blk * Lpad + k];
-                        float e0 = f_ex2(fmaf(f_sqrt(qfw[vv.x]), aa.x, -bc));
-                        float e1 = f_ex2(fmaf(f_sqrt(qfw[vv.y]), aa.y, -bc));
-                        float e2 = f_ex2(fmaf(f_sqrt(qfw[vv.z]), aa.z, -bc));
-                        float e3 = f_ex2(fmaf(f_sqrt(qfw[vv.w]), aa.w, -bc));
+                        const uint2 vv = lds_u2(ar + OFF_VA + 8u * blk);
+                        const float4 aa = lds_f4(ar + OFF_AC + 16u * blk);
+                        const float e0 = f_ex2(fmaf(f_sqrt(lds_f(a_q + (vv.x & 0xFFFFu))), aa.x, -bc));
+                        const float e1 = f_ex2(fmaf(f_sqrt(lds_f(a_q + (vv.x >> 16))), aa.y, -bc));
+                        const float e2 = f_ex2(fmaf(f_sqrt(lds_f(a_q + (vv.y & 0xFFFFu))), aa.z, -bc));
+                        const float e3 = f_ex2(fmaf(f_sqrt(lds_f(a_q + (vv.y >> 16))), aa.w, -bc));
                         P = fmaf(P, e0, P); P = fmaf(P, e1, P); P = fmaf(P, e2, P); P = fmaf(P, e3, P);
                     }
-                    const float2 cw = tcw[k];
+                    const float2 cw = lds_f2(ar + OFF_CW);
                     pr[c] = f_ex2(f_lg2(P) * cw.y) * cw.x;
                 }
             }
@@ -331,18 +363,15 @@ __global__ void __launch_bounds__(1024, 1) k_assign_fast(const __grid_constant__
             }
 
             // 3e. decide (DotProdClassifier.pyx:181-186) if the decision holds for every value inside the error bound
-            const float B = p.tau * sumabs + 2.4e-7f * p.thr;
-            int decision;                   // 1 assigned, 0 unassigned, -1 undecided (top-2), -2 undecided (threshold)
-            if (best + B < p.thr) decision = 0;
-            else if (best - B > p.thr) decision = (best - second > 2.0f * B) ? 1 : -1;
-            else decision = -2;
             if (lane == 0) {
-                if (decision < 0) {
-                    flag_row(p, row, w0 + b, decision == -1 ? RECHECK_MARGIN : RECHECK_THRESHOLD);
+                const float B = p.tau * sumabs + 2.4e-7f * p.thr;
+                const bool assigned = best - B > p.thr;
+                if (best + B < p.thr || (assigned && best - second > 2.0f * B)) {
+                    p.labels[row] = assigned ? (long long)bestid : -1ll;
+                    p.confs[row] = assigned ? (double)best : 0.0;
+                    if (assigned && p.counts) atomicAdd(&hist[bestid], 1u);
                 } else {
-                    p.labels[row] = decision ? (long long)bestid : -1ll;
-                    p.confs[row] = decision ? (double)best : 0.0;
-                    if (decision && p.counts) atomicAdd(&hist[bestid], 1u);
+                    flag_row(p, row, w0 + b, assigned ? RECHECK_MARGIN : RECHECK_THRESHOLD);
                 }
             }
             __syncwarp();
@@ -356,38 +385,46 @@ __global__ void __launch_bounds__(1024, 1) k_assign_fast(const __grid_constant__
     }
 }
 
-cudaError_t launch_assign_fast(const FastParams& p, int n_sms, cudaStream_t stream) {
-    if (p.n_work <= 0) return cudaSuccess;
-    if (p.n_levels < 1) return cudaErrorInvalidConfiguration;
+template <int NB, bool DYN>
+static cudaError_t launch_fast_one(const FastParams& p, int n_sms, cudaStream_t stream) {
     const size_t budget = (size_t)227 * 1024 - 1024;
     int best_w = 0, best_fb = 0;
     size_t best_bytes = 0;
     for (int w = 32; w >= 4 && !best_w; w -= 4) {
         for (int fb = 16; fb >= 1; --fb) {
-            if (fb > 1 && (long long)fb * p.M > 16LL * w && (long long)(fb - 1) * p.M >= 8LL * w) continue;   // long enough
-            const size_t bytes = fast_layout(p.S, p.M, p.Lpad, p.NB, w, fb, p.n_clusters, p.dynamic, p.counts != nullptr).total;
+            if (fb > 1 && (long long)(fb - 1) * p.M >= 12LL * w) continue;      // ~12 tasks per warp and batch are enough
+            const size_t bytes = fast_layout(p.S, p.M, p.Lpad, NB, w, fb, p.n_clusters, DYN, p.counts != nullptr).total;
             if (bytes <= budget) { best_w = w; best_fb = fb; best_bytes = bytes; break; }
         }
     }
     if (!best_w) return cudaErrorInvalidConfiguration;
-    cudaError_t e = cudaFuncSetAttribute(k_assign_fast, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)best_bytes);
+    auto kern = k_assign_fast<NB, DYN>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)best_bytes);
     if (e != cudaSuccess) return e;
     const long long batches = (p.n_work + best_fb - 1) / best_fb;
     long long grid = n_sms;
     if (grid > batches) grid = batches;
-    const FastSmem lay = fast_layout(p.S, p.M, p.Lpad, p.NB, best_w, best_fb, p.n_clusters, p.dynamic, p.counts != nullptr);
-    k_assign_fast<<<(unsigned)grid, best_w * 32, best_bytes, stream>>>(p, best_fb, lay);
+    const FastSmem lay = fast_layout(p.S, p.M, p.Lpad, NB, best_w, best_fb, p.n_clusters, DYN, p.counts != nullptr);
+    kern<<<(unsigned)grid, best_w * 32, best_bytes, stream>>>(p, best_fb, lay);
     return cudaGetLastError();
+}
+
+cudaError_t launch_assign_fast(const FastParams& p, int n_sms, cudaStream_t stream) {
+    if (p.n_work <= 0) return cudaSuccess;
+    if (p.S > 16000 || p.M < 2 || p.M >= 16384 || (long long)p.S + p.M >= 65536) return cudaErrorInvalidConfiguration;
+    if (p.NB == 1) return p.dynamic ? launch_fast_one<1, true>(p, n_sms, stream) : launch_fast_one<1, false>(p, n_sms, stream);
+    if (p.NB == 2) return p.dynamic ? launch_fast_one<2, true>(p, n_sms, stream) : launch_fast_one<2, false>(p, n_sms, stream);
+    return cudaErrorInvalidConfiguration;
 }
 
 // ---- candidate lists of the first tier: the grid's landmark lists sorted by cluster, unclustered landmarks left out ----
 // one thread per box: filter, then insertion sort on (cluster << 16 | landmark) in the output segment
 __global__ void k_sort_box_lists(const unsigned* __restrict__ ptr, const uint16_t* __restrict__ list, const int* __restrict__ cid,
-                                 long long cells, uint2* __restrict__ cbox, unsigned* __restrict__ clist) {
+                                 long long cells, unsigned base, uint2* __restrict__ cbox, unsigned* __restrict__ clist) {
     const long long id = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (id >= cells) return;
     const unsigned beg = ptr[id], end = ptr[id + 1];
-    unsigned* out = clist + beg;
+    unsigned* out = clist + base + beg;
     unsigned n = 0;
     for (unsigned i = beg; i < end; ++i) {
         const unsigned k = list[i];
@@ -399,13 +436,13 @@ __global__ void k_sort_box_lists(const unsigned* __restrict__ ptr, const uint16_
         out[pos] = key;
         ++n;
     }
-    cbox[id] = make_uint2(beg, n);
+    cbox[id] = make_uint2(base + beg, n);
 }
 
-cudaError_t launch_sort_box_lists(const unsigned* ptr, const uint16_t* list, const int* cid, long long cells, uint2* cbox,
-                                  unsigned* clist, cudaStream_t stream) {
+cudaError_t launch_sort_box_lists(const unsigned* ptr, const uint16_t* list, const int* cid, long long cells, unsigned base,
+                                  uint2* cbox, unsigned* clist, cudaStream_t stream) {
     if (cells <= 0) return cudaSuccess;
-    k_sort_box_lists<<<(unsigned)((cells + 127) / 128), 128, 0, stream>>>(ptr, list, cid, cells, cbox, clist);
+    k_sort_box_lists<<<(unsigned)((cells + 127) / 128), 128, 0, stream>>>(ptr, list, cid, cells, base, cbox, clist);
     return cudaGetLastError();
 }
 
