@@ -29,6 +29,7 @@
 // vertex byte offsets, centre weight) read with immediate offsets from one base; positions as float4 per atom.
 #include "sitb_fill.cuh"
 #include <math_constants.h>
+#include <cstdlib>
 
 namespace sitb {
 
@@ -387,22 +388,37 @@ __global__ void __launch_bounds__(1024, 1) k_assign_fast(const __grid_constant__
 
 template <int NB, bool DYN>
 static cudaError_t launch_fast_one(const FastParams& p, int n_sms, cudaStream_t stream) {
-    const size_t budget = (size_t)227 * 1024 - 1024;
-    int best_w = 0, best_fb = 0;
+    // CTAs per SM x warps x frames per batch: as many resident warps as registers (32 per thread) and the 227 KB of
+    // shared memory allow (the landmark records are per CTA), batches of ~12 tasks per warp
+    auto kern = k_assign_fast<NB, DYN>;
+    int force_ctas = 0;
+    if (const char* env = getenv("SITB_FAST_CTAS")) force_ctas = atoi(env);       // developer knob
+    int best_w = 0, best_fb = 0, best_ctas = 0;
     size_t best_bytes = 0;
-    for (int w = 32; w >= 4 && !best_w; w -= 4) {
-        for (int fb = 16; fb >= 1; --fb) {
-            if (fb > 1 && (long long)(fb - 1) * p.M >= 12LL * w) continue;      // ~12 tasks per warp and batch are enough
-            const size_t bytes = fast_layout(p.S, p.M, p.Lpad, NB, w, fb, p.n_clusters, DYN, p.counts != nullptr).total;
-            if (bytes <= budget) { best_w = w; best_fb = fb; best_bytes = bytes; break; }
+    double best_score = -1.0;
+    for (int ctas = 2; ctas >= 1; --ctas) {
+        if (force_ctas && ctas != force_ctas) continue;
+        const size_t budget = (size_t)(227 * 1024) / ctas - 1024;
+        for (int w = 32; w >= 4; w -= 4) {
+            int fb_fit = 0;
+            size_t bytes_fit = 0;
+            for (int fb = 1; fb <= 16; ++fb) {
+                const size_t bytes = fast_layout(p.S, p.M, p.Lpad, NB, w, fb, p.n_clusters, DYN, p.counts != nullptr).total;
+                if (bytes > budget) break;
+                fb_fit = fb; bytes_fit = bytes;
+                if ((long long)fb * p.M >= 12LL * w) break;
+            }
+            if (!fb_fit) continue;
+            const double fill = (double)(fb_fit * p.M) / (6.0 * w);      // short batches: the CTA barrier costs
+            const double score = (double)(ctas * w) * (fill < 1.0 ? fill : 1.0);
+            if (score > best_score) { best_score = score; best_w = w; best_fb = fb_fit; best_ctas = ctas; best_bytes = bytes_fit; }
         }
     }
     if (!best_w) return cudaErrorInvalidConfiguration;
-    auto kern = k_assign_fast<NB, DYN>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)best_bytes);
     if (e != cudaSuccess) return e;
     const long long batches = (p.n_work + best_fb - 1) / best_fb;
-    long long grid = n_sms;
+    long long grid = (long long)n_sms * best_ctas;
     if (grid > batches) grid = batches;
     const FastSmem lay = fast_layout(p.S, p.M, p.Lpad, NB, best_w, best_fb, p.n_clusters, DYN, p.counts != nullptr);
     kern<<<(unsigned)grid, best_w * 32, best_bytes, stream>>>(p, best_fb, lay);
