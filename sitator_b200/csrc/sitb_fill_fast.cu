@@ -125,6 +125,7 @@ __global__ void __launch_bounds__(1024, 1) k_assign_fast(const __grid_constant__
     const unsigned a_surv = a_q + 4u * (unsigned)Spad;                                // unsigned[SURV_CAP]
     unsigned* hist = (unsigned*)(smem_raw + lay.off_hist);
     int* task_counter = (int*)(smem_raw + lay.off_misc);
+    const unsigned a_task = sbase + lay.off_misc;
     int* glevel = task_counter + 1;                          // [FB]
 
     // ---- stage the landmark records once per CTA ----
@@ -224,7 +225,7 @@ __global__ void __launch_bounds__(1024, 1) k_assign_fast(const __grid_constant__
         const unsigned row0 = (unsigned)(w0 * M);
         for (;;) {
             int jj = 0;
-            if (lane == 0) jj = atomicAdd(task_counter, 1);
+            if (lane == 0) asm volatile("atom.shared.add.u32 %0, [%1], 1;" : "=r"(jj) : "r"(a_task) : "memory");
             jj = __shfl_sync(0xffffffffu, jj, 0);
             if (jj >= ntask) break;
             const int b = (int)__umulhi((unsigned)jj, p.m_magic);
@@ -393,6 +394,8 @@ static cudaError_t launch_fast_one(const FastParams& p, int n_sms, cudaStream_t 
     auto kern = k_assign_fast<NB, DYN>;
     int force_ctas = 0;
     if (const char* env = getenv("SITB_FAST_CTAS")) force_ctas = atoi(env);       // developer knob
+    int tasks_per_warp = 12;
+    if (const char* env = getenv("SITB_FAST_TPW")) tasks_per_warp = atoi(env);   // developer knob
     int best_w = 0, best_fb = 0, best_ctas = 0;
     size_t best_bytes = 0;
     double best_score = -1.0;
@@ -406,7 +409,7 @@ static cudaError_t launch_fast_one(const FastParams& p, int n_sms, cudaStream_t 
                 const size_t bytes = fast_layout(p.S, p.M, p.Lpad, NB, w, fb, p.n_clusters, DYN, p.counts != nullptr).total;
                 if (bytes > budget) break;
                 fb_fit = fb; bytes_fit = bytes;
-                if ((long long)fb * p.M >= 12LL * w) break;
+                if ((long long)fb * p.M >= (long long)tasks_per_warp * w) break;
             }
             if (!fb_fit) continue;
             const double fill = (double)(fb_fit * p.M) / (6.0 * w);      // short batches: the CTA barrier costs
