@@ -20,6 +20,7 @@ this rank's contiguous block of the trajectory, rank order = frame order; the re
 import importlib
 import logging
 import math
+import time
 
 import numpy as np
 
@@ -184,38 +185,47 @@ class LandmarkAnalysis(object):
                                             self.SITE_CENTERS_REPRESENTATIVE_LANDMARK):
             raise ValueError("Invalid site centers method '%s'" % self.site_centers_method)
 
+        from ..util.phases import PhaseTimer
         n_frames = len(frames)
         logger.info("--- Running Landmark Analysis ---")
+        timer = PhaseTimer()
+        t_wall0 = time.perf_counter()
         comm = parallel.default_comm()
-        frame0 = 0 if comm is None else comm.exclusive_scan_int(n_frames)
+        with timer.phase("frame offsets (collective)"):
+            frame0 = 0 if comm is None else comm.exclusive_scan_int(n_frames)
 
         # -- Steps 0/1: context (cell, tables, site-vertex distances); frames resident on the device
         self._landmark_dimension = sn.n_sites
         t_start = torch.cuda.Event(enable_timing=True); t_end = torch.cuda.Event(enable_timing=True)
-        engine = LandmarkEngine.from_site_network(
-            sn, cutoff_midpoint=self._cutoff_midpoint, cutoff_steepness=self._cutoff_steepness,
-            static_movement_threshold=self.static_movement_threshold,
-            dynamic_lattice_mapping=self.dynamic_lattice_mapping,
-            relaxed_lattice_checks=self.relaxed_lattice_checks, device=self._device)
+        with timer.phase("context: tables + candidate grid"):
+            engine = LandmarkEngine.from_site_network(
+                sn, cutoff_midpoint=self._cutoff_midpoint, cutoff_steepness=self._cutoff_steepness,
+                static_movement_threshold=self.static_movement_threshold,
+                dynamic_lattice_mapping=self.dynamic_lattice_mapping,
+                relaxed_lattice_checks=self.relaxed_lattice_checks, device=self._device)
         self._engine = engine
         t_start.record()
-        if isinstance(frames, ChunkedFrames):
-            # a trajectory that arrives in blocks is assembled in HBM; the engine borrows the device array
-            engine.set_frames(frames.to_device(engine.device), frame0=frame0)
-        else:
-            engine.set_frames(frames, frame0=frame0)
-        engine.reset_status()
+        with timer.phase("upload frames (enqueue)"):
+            if isinstance(frames, ChunkedFrames):
+                # a trajectory that arrives in blocks is assembled in HBM; the engine borrows the device array
+                engine.set_frames(frames.to_device(engine.device), frame0=frame0)
+            else:
+                engine.set_frames(frames, frame0=frame0)
+            engine.reset_status()
 
         # -- Steps 2/3: landmark vectors + clustering
         logger.info("  - computing landmark vectors / clustering -")
         source = LandmarkVectorSource(engine, comm)
+        source.timer = timer
         clustermod = importlib.import_module("sitator_b200.landmark.cluster." + self._cluster_algo)
-        if hasattr(clustermod, "landmark_graph"):
-            clustermod.landmark_graph(source)          # pass A runs the lattice / zero-vector checks
-        elif hasattr(clustermod, "first_pass"):
-            clustermod.first_pass(source)
-        status = engine.status()
-        self._raise_first_error(status, comm, engine)
+        with timer.phase("pass A: fill + seen + Gram (+ H2D wait, all-reduce)"):
+            if hasattr(clustermod, "landmark_graph"):
+                clustermod.landmark_graph(source, self._clustering_params.get('gram_method', 'sparse'))   # pass A runs the lattice / zero-vector checks
+            elif hasattr(clustermod, "first_pass"):
+                clustermod.first_pass(source)
+        with timer.phase("status + first error (collective)"):
+            status = engine.status()
+            self._raise_first_error(status, comm, engine)
         if status.n_list_overflow:
             raise RuntimeError("%d landmark vectors have more than 128 non-zero components; "
                                "the device lists would truncate them" % status.n_list_overflow)
@@ -228,9 +238,10 @@ class LandmarkAnalysis(object):
                            % self.n_all_zero_lvecs)
 
         logger.info("  - clustering landmark vectors -")
-        clustering = clustermod.do_landmark_clustering(
-            source, clustering_params=self._clustering_params,
-            min_samples=self._minimum_site_occupancy / float(sn.n_mobile), verbose=self.verbose)
+        with timer.phase("clustering"):
+            clustering = clustermod.do_landmark_clustering(
+                source, clustering_params=self._clustering_params,
+                min_samples=self._minimum_site_occupancy / float(sn.n_mobile), verbose=self.verbose)
 
         cluster_counts = clustering[LandmarkAnalysis.CLUSTERING_CLUSTER_SIZE]
         lmk_lbls = clustering[LandmarkAnalysis.CLUSTERING_LABELS]
@@ -243,14 +254,18 @@ class LandmarkAnalysis(object):
             rep_lvecs = np.asarray(rep_lvecs)
             assert rep_lvecs.shape == (len(cluster_counts), engine.L)
 
-        if clustering.get('_dev_labels') is not None:
-            n_unassigned = int((clustering['_dev_labels'] < 0).sum().item())      # counted where the labels already are
-        else:
-            n_unassigned = int(np.sum(lmk_lbls < 0))
-        n_rows = len(lmk_lbls)
-        if comm is not None:
-            n_unassigned = comm.allreduce_sum_scalar(n_unassigned)
-            n_rows = comm.allreduce_sum_scalar(n_rows)
+        with timer.phase("unassigned count (collective)"):
+            if clustering.get('_n_unassigned') is not None:
+                n_unassigned = int(clustering['_n_unassigned'])                   # already reduced over the ranks
+                n_rows = source.n_total
+            else:
+                if clustering.get('_dev_labels') is not None:
+                    n_unassigned = int((clustering['_dev_labels'] < 0).sum().item())      # counted where the labels already are
+                else:
+                    n_unassigned = int(np.sum(lmk_lbls < 0))
+                n_rows = len(lmk_lbls)
+                if comm is not None:
+                    n_unassigned, n_rows = comm.allreduce_sum_scalars([n_unassigned, n_rows])
         logger.info("    Failed to assign %i%% of mobile particle positions to sites." % (100.0 * n_unassigned / float(n_rows)))
 
         lmk_lbls = lmk_lbls.reshape(n_frames, sn.n_mobile)
@@ -267,15 +282,16 @@ class LandmarkAnalysis(object):
         if dev_labels is None:
             dev_labels = torch.as_tensor(np.ascontiguousarray(lmk_lbls.reshape(-1)), device=engine.device)
             dev_confs = torch.as_tensor(np.ascontiguousarray(lmk_confs.reshape(-1)), device=engine.device)
-        if self.site_centers_method in (self.SITE_CENTERS_REAL_WEIGHTED, self.SITE_CENTERS_REAL_UNWEIGHTED):
-            weighted = self.site_centers_method == self.SITE_CENTERS_REAL_WEIGHTED
-            site_centers = engine.site_centers(dev_labels, dev_confs, n_sites, weighted,
-                                               clustering.get('_dev_site_best') if weighted else None, comm)
-        else:
-            if rep_lvecs is None:
-                raise ValueError("Chosen clustering method (with current parameters) didn't return representative "
-                                 "landmark vectors; can't use SITE_CENTERS_REPRESENTATIVE_LANDMARK.")
-            site_centers = engine.weighted_point_averages(np.asarray(sn.centers), rep_lvecs)
+        with timer.phase("site centres (collective)"):
+            if self.site_centers_method in (self.SITE_CENTERS_REAL_WEIGHTED, self.SITE_CENTERS_REAL_UNWEIGHTED):
+                weighted = self.site_centers_method == self.SITE_CENTERS_REAL_WEIGHTED
+                site_centers = engine.site_centers(dev_labels, dev_confs, n_sites, weighted,
+                                                   clustering.get('_dev_site_best') if weighted else None, comm)
+            else:
+                if rep_lvecs is None:
+                    raise ValueError("Chosen clustering method (with current parameters) didn't return representative "
+                                     "landmark vectors; can't use SITE_CENTERS_REPRESENTATIVE_LANDMARK.")
+                site_centers = engine.weighted_point_averages(np.asarray(sn.centers), rep_lvecs)
         out_sn.centers = site_centers
         if landmark_clusters is not None:
             out_sn.vertices = [set.union(*[set(sn.vertices[l]) for l in lclust]) for lclust in landmark_clusters]
@@ -285,13 +301,17 @@ class LandmarkAnalysis(object):
         out_st._comm = comm
 
         # Check that multiple particles are never assigned to one site at the same time
-        self.n_multiple_assignments, self.avg_mobile_per_site = out_st.check_multiple_occupancy(
-            max_mobile_per_site=self.max_mobile_per_site, _dev_traj=dev_labels.view(n_frames, sn.n_mobile))
+        with timer.phase("occupancy check (collective)"):
+            self.n_multiple_assignments, self.avg_mobile_per_site = out_st.check_multiple_occupancy(
+                max_mobile_per_site=self.max_mobile_per_site, _dev_traj=dev_labels.view(n_frames, sn.n_mobile))
 
         out_st.set_real_traj(frames)
         t_end.record()
         torch.cuda.synchronize(engine.device)
-        self.stats = {"run_ms": t_start.elapsed_time(t_end), "n_screen_rejects": status.n_screen_rejects,
-                      "nnz": status.nnz, "mcl_iterations": clustering.get('_mcl_iterations')}
+        self.stats = {"run_ms": t_start.elapsed_time(t_end), "wall_ms": (time.perf_counter() - t_wall0) * 1e3,
+                      "n_screen_rejects": status.n_screen_rejects,
+                      "nnz": status.nnz, "mcl_iterations": clustering.get('_mcl_iterations'),
+                      "gram_method": getattr(source, "gram_method", None),
+                      "phases_ms": timer.as_dict(), "phases_synchronised": timer.sync}
         self._has_run = True
         return out_st

@@ -99,6 +99,7 @@ def landmark_graph(source, gram_method='sparse'):
             source.comm.allreduce_sum_(seen)
             source.comm.allreduce_sum_(gram)
         source.seen, source.gram_upper = seen, gram
+        source.gram_method = gram_method
     L = eng.L
     cov = torch.empty((L, L), dtype=torch.float64, device=eng.device)
     graph = torch.empty((L, L), dtype=torch.float64, device=eng.device)
@@ -164,14 +165,17 @@ def _centre_tables(clusters, vectors, L):
 
 def do_landmark_clustering(landmark_vectors, clustering_params, min_samples, verbose):
     import torch
+    from ...util.phases import PhaseTimer
     source = landmark_vectors
     eng = source.engine
     comm = source.comm
     L = eng.L
     params = DEFAULT_PARAMS.copy()
     params.update(clustering_params)
+    timer = getattr(source, "timer", None) or PhaseTimer()
 
-    seen_ntimes, cov, graph = landmark_graph(source, params.pop('gram_method', 'sparse'))
+    with timer.phase("  graph: cov, corr, clip"):
+        seen_ntimes, cov, graph = landmark_graph(source, params.pop('gram_method', 'sparse'))
 
     predict_threshold = params.pop('assignment_threshold')
     good_site_normed_threshold = params.pop('good_site_normed_threshold', predict_threshold)
@@ -179,8 +183,10 @@ def do_landmark_clustering(landmark_vectors, clustering_params, min_samples, ver
     weighted_reps = params.pop('weighted_representative_landmarks', True)
 
     # -- cluster landmarks (mcl.py:66-68)
-    m2, n_iter = markov_clustering_device(graph, **params)
-    clusters = _clusters_on_device(m2)
+    with timer.phase("  Markov clustering"):
+        m2, n_iter = markov_clustering_device(graph, **params)
+    with timer.phase("  cluster read-out (D2H)"):
+        clusters = _clusters_on_device(m2)
     logger.debug("Markov clustering converged in %i iterations: %i clusters" % (n_iter, len(clusters)))
     clusters = [list(c) for c in clusters if seen_ntimes[c[0]] > 0]
     n_clusters = len(clusters)
@@ -188,15 +194,18 @@ def do_landmark_clustering(landmark_vectors, clustering_params, min_samples, ver
         raise ValueError("Markov clustering found no landmark cluster that was ever seen")
 
     # -- centres: principal eigenvector of each cluster's covariance block (mcl.py:73-80)
-    vectors = principal_vectors(_covariance_blocks(cov, clusters))
-    cid, w = _centre_tables(clusters, vectors, L)
+    with timer.phase("  centres: eigenvectors of the covariance blocks"):
+        vectors = principal_vectors(_covariance_blocks(cov, clusters))
+        cid, w = _centre_tables(clusters, vectors, L)
 
     # -- pass B: best matching landmark vector per cluster (mcl.py:81-89)
-    eng.set_centers(cid, w, n_clusters)
-    best = new_best_table(n_clusters, eng.device)
-    source.assign(float('nan'), best=best)
-    _, best_rows = read_best_table(best, comm)
-    best_lvecs = source.rows(best_rows)                                   # (n_clusters, L) float64
+    with timer.phase("  pass B: best row per cluster (collective)"):
+        eng.set_centers(cid, w, n_clusters)
+        best = new_best_table(n_clusters, eng.device)
+        source.assign(float('nan'), best=best)
+        _, best_rows = read_best_table(best, comm)
+    with timer.phase("  best rows materialised (collective)"):
+        best_lvecs = source.rows(best_rows)                                   # (n_clusters, L) float64
     good = np.zeros(n_clusters, dtype=bool)
     scale = np.ones(n_clusters)
     for i, cl in enumerate(clusters):
@@ -235,11 +244,12 @@ def do_landmark_clustering(landmark_vectors, clustering_params, min_samples, ver
         source.assign(predict_threshold, **out)
         return out
 
-    res = final_predict(n_clusters, True)
-    counts = res.pop('counts')
-    if comm is not None:
-        comm.allreduce_sum_(counts)
-    cluster_counts = counts.cpu().numpy()
+    with timer.phase("  pass C: predict + counts (collective)"):
+        res = final_predict(n_clusters, True)
+        counts = res.pop('counts')
+        if comm is not None:
+            comm.allreduce_sum_(counts)
+        cluster_counts = counts.cpu().numpy()
     total_n_assigned = int(cluster_counts.sum())
     if isinstance(min_samples, (int, np.integer)):
         ms = int(min_samples)
@@ -258,23 +268,27 @@ def do_landmark_clustering(landmark_vectors, clustering_params, min_samples, ver
 
     # -- pass D: final predict + representative landmark vectors (mcl.py:114-122) + per-site best row
     if not np.all(count_mask):
-        cid, w = _centre_tables(clusters, vectors, L)
-        eng.set_centers(cid, w, n_sites)
-        res = final_predict(n_sites, False)
+        with timer.phase("  pass D: predict with the kept centres"):
+            cid, w = _centre_tables(clusters, vectors, L)
+            eng.set_centers(cid, w, n_sites)
+            res = final_predict(n_sites, False)
     labels, confs, rep, rep_w, site_best = res['labels'], res['confs'], res['rep'], res['rep_w'], res['site_best']
-    if comm is not None:
-        comm.allreduce_sum_(rep)
-        comm.allreduce_sum_(rep_w)
-    if weighted_reps:
-        reps = (rep / rep_w[:, None]).cpu().numpy()
-    else:
-        raise NotImplementedError("weighted_representative_landmarks=False (the reference cannot reach it either: "
-                                  "the key is forwarded to markov_clustering, mcl.py:66,115)")
+    with timer.phase("  representative vectors (collective)"):
+        if comm is not None:
+            comm.allreduce_sum_(rep)
+            comm.allreduce_sum_(rep_w)
+        if weighted_reps:
+            reps = (rep / rep_w[:, None]).cpu().numpy()
+        else:
+            raise NotImplementedError("weighted_representative_landmarks=False (the reference cannot reach it either: "
+                                      "the key is forwarded to markov_clustering, mcl.py:66,115)")
+    with timer.phase("  labels + confidences D2H"):
+        host_labels, host_confs = _to_host(labels), _to_host(confs)
 
     return {
         CLUSTERING_CLUSTER_SIZE: kept_counts,
-        CLUSTERING_LABELS: _to_host(labels),
-        CLUSTERING_CONFIDENCES: _to_host(confs),
+        CLUSTERING_LABELS: host_labels,
+        CLUSTERING_CONFIDENCES: host_confs,
         CLUSTERING_LANDMARK_GROUPINGS: clusters,
         CLUSTERING_REPRESENTATIVE_LANDMARKS: reps,
         # device-side copies for the rest of LandmarkAnalysis.run (not part of the reference contract)

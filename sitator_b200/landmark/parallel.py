@@ -66,6 +66,12 @@ class Comm(object):
         self.dist.all_reduce(t, op=self.dist.ReduceOp.SUM, group=self.group)
         return int(t.item())
 
+    def allreduce_sum_scalars(self, values):
+        """Several integer sums in one collective."""
+        t = self._host_tensor(np.array([int(v) for v in values], dtype=np.int64))
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.SUM, group=self.group)
+        return [int(x) for x in t.cpu().numpy()]
+
     def allreduce_min_int(self, v):
         t = self._host_tensor(np.array([int(v)], dtype=np.int64))
         self.dist.all_reduce(t, op=self.dist.ReduceOp.MIN, group=self.group)
