@@ -145,6 +145,20 @@ int sitb_assign_sparse(sitb_ctx* ctx, const uint64_t* dev_row_ptr, const uint16_
                        uint64_t* dev_counts, uint64_t* dev_best, double* dev_rep, double* dev_rep_w,
                        uint64_t* dev_site_best);
 
+/* The min_samples filter of DotProdClassifier.fit_predict (util/DotProdClassifier.pyx:105-118) without a second
+ * full predict.  dev_remap[C_old]: new id of each first-predict cluster, -1 = removed.  sitb_relabel_select renumbers
+ * dev_labels in place and lists the rows of removed clusters (dev_row_list[<= n_rows], *dev_n_list += their number);
+ * sitb_assign_sparse_rows then predicts exactly those rows again with the current centres (sitb_set_centers with the
+ * surviving ones) and adds them to the reductions.  Rows of surviving clusters keep arg-max and confidence: the
+ * surviving centres are unchanged, and removing centres cannot lift another one above the old maximum. */
+int sitb_relabel_select(sitb_ctx* ctx, int64_t* dev_labels, int64_t n_rows, const int32_t* dev_remap,
+                        int64_t* dev_row_list, uint64_t* dev_n_list);
+int sitb_assign_sparse_rows(sitb_ctx* ctx, const uint64_t* dev_row_ptr, const uint16_t* dev_pool_k,
+                            const double* dev_pool_v, const int64_t* dev_row_list, const uint64_t* dev_n_list,
+                            int64_t max_rows, int64_t row0, double threshold, int64_t* dev_labels, double* dev_confs,
+                            uint64_t* dev_counts, uint64_t* dev_best, double* dev_rep, double* dev_rep_w,
+                            uint64_t* dev_site_best);
+
 /* Cluster centres (cluster/mcl.py:70-96): centres have disjoint supports, so they are given as a
  * landmark -> cluster map (-1 none) and a landmark weight. */
 int sitb_set_centers(sitb_ctx* ctx, const int32_t* host_cluster_of_landmark, const double* host_weight,
@@ -218,6 +232,15 @@ int sitb_landmark_graph(int device, const double* dev_gram_upper, int32_t n, dou
 int sitb_markov_clustering(int device, const double* dev_graph, int32_t n, int32_t expansion, double inflation,
                            double pruning_threshold, int32_t iterlimit, double* dev_result,
                            int32_t* n_iterations, int32_t* converged, void* cuda_stream);
+
+/* cluster/mcl.py:73-80: the principal eigenvector of cov[cluster][:, cluster] for every cluster (what
+ * scipy.sparse.linalg.eigsh(block, k=1) returns there; [1] for a singleton), float64 cyclic Jacobi, one CTA per cluster.
+ * dev_members[offsets[c] .. offsets[c+1]) = the landmarks of cluster c; the unit eigenvector is scattered into
+ * dev_weights[n_landmarks] (zero it first).  dev_sweeps[c] = Jacobi sweeps used, or -1 for a block larger than 64
+ * (left to the caller).  The sign of an eigenvector is arbitrary here as in the reference. */
+int sitb_principal_vectors(int device, const double* dev_cov, int32_t n_landmarks, const int32_t* dev_members,
+                           const int32_t* dev_offsets, int32_t n_clusters, double* dev_weights, int32_t* dev_sweeps,
+                           void* cuda_stream);
 
 /* ---- site centres: LandmarkAnalysis.py:276-287 via PBCCalculator.average (PBCCalculator.pyx:106-139) ----
  * The average is centred on one point per site (the max-confidence row, or the first row when

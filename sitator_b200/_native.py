@@ -64,6 +64,8 @@ SIGNATURES = {
     "sitb_pass_stats_cached": (C.c_int, [_P, C.c_int64, C.c_int64, _P, _P, _P, _P, _P, _P, C.c_uint64]),
     "sitb_gram_from_cached": (C.c_int, [_P, _P, _P, _P, C.c_int64, _P]),
     "sitb_assign_sparse": (C.c_int, [_P, _P, _P, _P, C.c_int64, C.c_int64, C.c_double] + [_P] * 7),
+    "sitb_relabel_select": (C.c_int, [_P, _P, C.c_int64, _P, _P, _P]),
+    "sitb_assign_sparse_rows": (C.c_int, [_P, _P, _P, _P, _P, _P, C.c_int64, C.c_int64, C.c_double] + [_P] * 7),
     "sitb_set_centers": (C.c_int, [_P, _P, _P, C.c_int32]),
     "sitb_pass_assign": (C.c_int, [_P, C.c_int64, C.c_int64, C.c_double] + [_P] * 7),
     "sitb_set_assign_mode": (C.c_int, [_P, C.c_int32]),
@@ -75,6 +77,7 @@ SIGNATURES = {
     "sitb_dotprod_predict": (C.c_int, [C.c_int, _P, _P, _P, C.c_int64, C.c_int32, C.c_int32, _P, _P, _P, C.c_double,
                                        _P, _P, _P, _P]),
     "sitb_landmark_graph": (C.c_int, [C.c_int, _P, C.c_int32, C.c_double, _P, _P, _P]),
+    "sitb_principal_vectors": (C.c_int, [C.c_int, _P, C.c_int32, _P, _P, C.c_int32, _P, _P, _P]),
     "sitb_markov_clustering": (C.c_int, [C.c_int, _P, C.c_int32, C.c_int32, C.c_double, C.c_double, C.c_int32, _P,
                                          C.POINTER(C.c_int32), C.POINTER(C.c_int32), _P]),
     "sitb_wrapped_mobile_rows": (C.c_int, [_P, _P, C.c_int32, _P]),

@@ -943,7 +943,10 @@ cudaError_t launch_assign_sparse(const unsigned long long* row_ptr, const uint16
                                  long long n_rows, long long row0, int L, const int* cid, const double* cw,
                                  int n_clusters, double thr, long long* labels, double* confs,
                                  unsigned long long* counts, unsigned long long* best, double* rep, double* rep_w,
-                                 unsigned long long* site_best, int n_sms, cudaStream_t st);
+                                 unsigned long long* site_best, int n_sms, cudaStream_t st, const long long* row_list = nullptr,
+                                 const unsigned long long* n_list = nullptr);
+cudaError_t launch_relabel_select(long long* labels, long long n_rows, const int* remap, long long* row_list,
+                                  unsigned long long* n_list, int n_sms, cudaStream_t st);
 }
 
 extern "C" int sitb_pass_stats_cached(sitb_ctx* c, int64_t begin, int64_t n, uint64_t* dev_seen, double* dev_gram,
@@ -974,6 +977,34 @@ extern "C" int sitb_assign_sparse(sitb_ctx* c, const uint64_t* dev_row_ptr, cons
                             c->d_cid_orig, c->d_cw_orig, c->n_clusters, thr, (long long*)labels, confs,
                             (unsigned long long*)counts, (unsigned long long*)best, rep, rep_w,
                             (unsigned long long*)site_best, c->n_sms, c->stream));
+    return SITB_OK;
+}
+
+extern "C" int sitb_relabel_select(sitb_ctx* c, int64_t* dev_labels, int64_t n_rows, const int32_t* dev_remap,
+                                   int64_t* dev_row_list, uint64_t* dev_n_list) {
+    if (!c || !dev_labels || !dev_remap || !dev_row_list || !dev_n_list || n_rows < 0)
+        return fail(SITB_E_INVALID, "sitb_relabel_select: bad argument");
+    CK(cudaSetDevice(c->device));
+    CK(launch_relabel_select((long long*)dev_labels, n_rows, dev_remap, (long long*)dev_row_list,
+                             (unsigned long long*)dev_n_list, c->n_sms, c->stream));
+    return SITB_OK;
+}
+
+extern "C" int sitb_assign_sparse_rows(sitb_ctx* c, const uint64_t* dev_row_ptr, const uint16_t* dev_pool_k,
+                                       const double* dev_pool_v, const int64_t* dev_row_list, const uint64_t* dev_n_list,
+                                       int64_t max_rows, int64_t row0, double thr, int64_t* labels, double* confs,
+                                       uint64_t* counts, uint64_t* best, double* rep, double* rep_w, uint64_t* site_best) {
+    if (!c || !dev_row_ptr || !dev_pool_k || !dev_pool_v || !dev_row_list || !dev_n_list || max_rows < 0)
+        return fail(SITB_E_INVALID, "sitb_assign_sparse_rows: bad argument");
+    if (!c->d_cid_orig) return fail(SITB_E_STATE, "sitb_assign_sparse_rows: no centres set (sitb_set_centers)");
+    CK(cudaSetDevice(c->device));
+    // the list is short (rows of the clusters the min_samples filter removed): a small grid is enough
+    const int64_t bound = max_rows < 262144 ? max_rows : 262144;
+    CK(launch_assign_sparse((const unsigned long long*)dev_row_ptr, dev_pool_k, dev_pool_v, bound > 0 ? bound : 1, row0, c->L,
+                            c->d_cid_orig, c->d_cw_orig, c->n_clusters, thr, (long long*)labels, confs,
+                            (unsigned long long*)counts, (unsigned long long*)best, rep, rep_w,
+                            (unsigned long long*)site_best, c->n_sms, c->stream, (const long long*)dev_row_list,
+                            (const unsigned long long*)dev_n_list));
     return SITB_OK;
 }
 

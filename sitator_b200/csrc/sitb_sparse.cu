@@ -131,7 +131,11 @@ __global__ void __launch_bounds__(128) k_assign_sparse(
     long long n_rows, long long row0, int L, const int* __restrict__ cid, const double* __restrict__ cw,
     int n_clusters, double thr, long long* __restrict__ labels, double* __restrict__ confs,
     unsigned long long* __restrict__ counts, unsigned long long* __restrict__ best_scratch, double* __restrict__ rep,
-    double* __restrict__ rep_w, unsigned long long* __restrict__ site_scratch) {
+    double* __restrict__ rep_w, unsigned long long* __restrict__ site_scratch,
+    const long long* __restrict__ row_list, const unsigned long long* __restrict__ n_list) {
+    // row_list / n_list (optional): only these rows, their number read on the device (the selective re-predict after
+    // the min_samples filter, DotProdClassifier.pyx:105-118)
+    if (n_list) n_rows = (long long)*n_list;
     // shared: per warp [C] best val | [C] best row | [C] site val | [C] site row ; [C] hist ; per warp staging
     extern __shared__ unsigned long long smem_u64[];
     const int C = n_clusters;
@@ -150,8 +154,9 @@ __global__ void __launch_bounds__(128) k_assign_sparse(
     __syncthreads();
     const long long n_groups = (n_rows + 31) >> 5;
     for (long long g = warp_global; g < n_groups; g += n_warps) {
-        const long long r = (g << 5) + lane;
-        const bool valid = r < n_rows;
+        const long long ri = (g << 5) + lane;
+        const bool valid = ri < n_rows;
+        const long long r = (row_list && valid) ? row_list[ri] : ri;
         const unsigned long long ptr = valid ? row_ptr[r] : 0ull;
         const int nent = (int)(ptr & 0xFF);
         bool hard = nent > 32;
@@ -260,11 +265,12 @@ __global__ void __launch_bounds__(128) k_assign_sparse(
             int k0 = 0;
             double v0 = 0.0;
             if (lane < n) { k0 = pk[off + lane]; v0 = pv[off + lane]; }
+            const long long rh = __shfl_sync(0xffffffffu, r, i);
             if (n <= 32)
-                assign_row<1>((g << 5) + i, n, off, lane, k0, v0, pk, pv, row0, L, cid, cw, thr, labels, confs, counts, hist,
+                assign_row<1>(rh, n, off, lane, k0, v0, pk, pv, row0, L, cid, cw, thr, labels, confs, counts, hist,
                               best_scratch, wb, rep, rep_w, site_scratch, ws);
             else
-                assign_row<ENTRY_CAP / 32>((g << 5) + i, n, off, lane, k0, v0, pk, pv, row0, L, cid, cw, thr, labels, confs,
+                assign_row<ENTRY_CAP / 32>(rh, n, off, lane, k0, v0, pk, pv, row0, L, cid, cw, thr, labels, confs,
                                            counts, hist, best_scratch, wb, rep, rep_w, site_scratch, ws);
             __syncwarp();
         }
@@ -320,7 +326,8 @@ cudaError_t launch_assign_sparse(const unsigned long long* row_ptr, const uint16
                                  long long n_rows, long long row0, int L, const int* cid, const double* cw,
                                  int n_clusters, double thr, long long* labels, double* confs,
                                  unsigned long long* counts, unsigned long long* best, double* rep, double* rep_w,
-                                 unsigned long long* site_best, int n_sms, cudaStream_t st) {
+                                 unsigned long long* site_best, int n_sms, cudaStream_t st, const long long* row_list,
+                                 const unsigned long long* n_list) {
     if (n_rows <= 0) return cudaSuccess;
     const int C = n_clusters > 0 ? n_clusters : 1;
     // per warp: 32 B of tables per cluster + the staging block; per CTA: the histogram
@@ -340,11 +347,42 @@ cudaError_t launch_assign_sparse(const unsigned long long* row_ptr, const uint16
     const int grid = (int)(want < (long long)n_sms * resident ? want : (long long)n_sms * resident);
     unsigned long long *sb = nullptr, *ss = nullptr;
     if (best) { e = cudaMallocAsync((void**)&sb, sizeof(unsigned long long) * 2 * (size_t)grid * C, st); if (e != cudaSuccess) return e; }
-    if (site_best) { e = cudaMallocAsync((void**)&ss, sizeof(unsigned long long) * 2 * (size_t)grid * C, st); if (e != cudaSuccess) return e; }
+    if (site_best) {
+        e = cudaMallocAsync((void**)&ss, sizeof(unsigned long long) * 2 * (size_t)grid * C, st);
+        if (e != cudaSuccess) { if (sb) cudaFreeAsync(sb, st); return e; }
+    }
     k_assign_sparse<<<grid, warps * 32, smem, st>>>(row_ptr, pk, pv, n_rows, row0, L, cid, cw, n_clusters, thr, labels, confs,
-                                            counts, sb, rep, rep_w, ss);
+                                            counts, sb, rep, rep_w, ss, row_list, n_list);
     if (best) { k_merge_best<<<(C + 31) / 32, 256, 0, st>>>(sb, grid, n_clusters, best); cudaFreeAsync(sb, st); }
     if (site_best) { k_merge_best<<<(C + 31) / 32, 256, 0, st>>>(ss, grid, n_clusters, site_best); cudaFreeAsync(ss, st); }
+    return cudaGetLastError();
+}
+
+// ---- the min_samples filter without a second full predict (DotProdClassifier.pyx:105-118) ----------------------------
+// The second predict uses the centres that survived the filter, unchanged.  A row whose first-predict cluster
+// survived keeps its arg-max and its confidence (removing other centres cannot raise another one above it); an
+// unassigned row stays unassigned.  Only rows of removed clusters have to be predicted again: this kernel renumbers
+// the labels and lists those rows.
+__global__ void k_relabel_select(long long* __restrict__ labels, long long n_rows, const int* __restrict__ remap,
+                                 long long* __restrict__ row_list, unsigned long long* __restrict__ n_list) {
+    for (long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x; r < n_rows; r += (long long)gridDim.x * blockDim.x) {
+        const long long l = labels[r];
+        if (l < 0) continue;
+        const int nl = remap[l];
+        if (nl >= 0) {
+            if (nl != l) labels[r] = nl;
+        } else {
+            row_list[atomicAdd(n_list, 1ull)] = r;
+        }
+    }
+}
+
+cudaError_t launch_relabel_select(long long* labels, long long n_rows, const int* remap, long long* row_list,
+                                  unsigned long long* n_list, int n_sms, cudaStream_t st) {
+    if (n_rows <= 0) return cudaSuccess;
+    long long blocks = (n_rows + 255) / 256;
+    if (blocks > (long long)n_sms * 8) blocks = (long long)n_sms * 8;
+    k_relabel_select<<<(unsigned)blocks, 256, 0, st>>>(labels, n_rows, remap, row_list, n_list);
     return cudaGetLastError();
 }
 

@@ -51,11 +51,13 @@ class EngineStatus(object):
 
 def vertex_table(vertices):
     """-1 padded (L, Vmax) int32 table of the landmark vertex lists (LandmarkAnalysis.py:194-195)."""
-    vmax = max(len(v) for v in vertices)
-    out = np.full((len(vertices), vmax), -1, dtype=np.int32)
-    for i, v in enumerate(vertices):
-        v = list(v)
-        out[i, :len(v)] = v
+    import itertools
+    n = len(vertices)
+    lens = np.fromiter((len(v) for v in vertices), dtype=np.int64, count=n)
+    vmax = int(lens.max())
+    flat = np.fromiter(itertools.chain.from_iterable(vertices), dtype=np.int32, count=int(lens.sum()))
+    out = np.full((n, vmax), -1, dtype=np.int32)
+    out[np.arange(vmax)[None, :] < lens[:, None]] = flat       # row-major fill: each list in its own order
     return out
 
 
@@ -342,6 +344,22 @@ class LandmarkEngine(object):
             self._ctx, self._ptr(rows.ptr), self._ptr(rows.k), self._ptr(rows.v), rows.n_rows, rows.row0,
             float(threshold), self._ptr(labels), self._ptr(confs), self._ptr(counts), self._ptr(best), self._ptr(rep),
             self._ptr(rep_w), self._ptr(site_best)))
+
+    def repredict_removed(self, rows, threshold, remap, labels, confs, rep=None, rep_w=None, site_best=None):
+        """After the min_samples filter (DotProdClassifier.pyx:105-118): renumber ``labels`` (device int64) by ``remap``
+        (new id per old cluster, -1 = removed) and predict only the rows of removed clusters again, with the current
+        centres.  Returns the device counter of such rows."""
+        torch = _torch()
+        remap_d = torch.as_tensor(np.ascontiguousarray(remap, dtype=np.int32), device=self.device)
+        row_list = self._empty((rows.n_rows,), torch.int64)
+        n_list = self._zeros((1,), torch.int64)
+        _native.check(self._lib.sitb_relabel_select(self._ctx, self._ptr(labels), rows.n_rows, self._ptr(remap_d),
+                                                    self._ptr(row_list), self._ptr(n_list)))
+        _native.check(self._lib.sitb_assign_sparse_rows(
+            self._ctx, self._ptr(rows.ptr), self._ptr(rows.k), self._ptr(rows.v), self._ptr(row_list), self._ptr(n_list),
+            rows.n_rows, rows.row0, float(threshold), self._ptr(labels), self._ptr(confs), self._ptr(None), self._ptr(None),
+            self._ptr(rep), self._ptr(rep_w), self._ptr(site_best)))
+        return n_list
 
     def set_centers(self, cluster_of_landmark, weight, n_clusters):
         cid = np.ascontiguousarray(cluster_of_landmark, dtype=np.int32)

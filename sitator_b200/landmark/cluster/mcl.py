@@ -140,6 +140,35 @@ def _covariance_blocks(cov, clusters):
     return out
 
 
+def principal_vectors_device(cov, clusters, L):
+    """mcl.py:73-80 on the device (csrc/sitb_eig.cu): per-landmark centre weights (L,) float64 numpy -- each cluster's
+    unit principal eigenvector scattered onto its landmarks.  Blocks larger than the kernel's limit use LAPACK."""
+    import torch
+    lib = _native.load()
+    members = np.concatenate([np.asarray(c, dtype=np.int32) for c in clusters])
+    offsets = np.zeros(len(clusters) + 1, dtype=np.int32)
+    offsets[1:] = np.cumsum([len(c) for c in clusters])
+    dev = cov.device
+    packed = torch.as_tensor(np.concatenate([offsets, members]), device=dev)
+    w = torch.zeros((L,), dtype=torch.float64, device=dev)
+    sweeps = torch.zeros((len(clusters),), dtype=torch.int32, device=dev)
+    stream = torch.cuda.current_stream(dev).cuda_stream
+    _native.check(lib.sitb_principal_vectors(dev.index, C.c_void_p(cov.data_ptr()), L,
+                                             C.c_void_p(packed.data_ptr() + 4 * len(offsets)), C.c_void_p(packed.data_ptr()),
+                                             len(clusters), C.c_void_p(w.data_ptr()), C.c_void_p(sweeps.data_ptr()),
+                                             C.c_void_p(stream)))
+    out = torch.empty((L + len(clusters),), dtype=torch.float64, device=dev)
+    out[:L] = w
+    out[L:] = sweeps.to(torch.float64)
+    h = out.cpu().numpy()                       # one small device -> host copy
+    w_h, sw = h[:L].copy(), h[L:]
+    for i in np.nonzero(sw < 0)[0]:             # blocks beyond the kernel's size limit
+        cl = np.asarray(clusters[i], dtype=np.int64)
+        blk = cov[torch.as_tensor(cl, device=dev)][:, torch.as_tensor(cl, device=dev)].cpu().numpy()
+        w_h[cl] = principal_vector(blk)
+    return w_h
+
+
 def _to_host(t):
     """Device -> host into page-locked memory (a pageable .cpu() runs at a fraction of PCIe speed).  The
     returned array owns the pinned block; torch's caching host allocator recycles it once the caller
@@ -181,6 +210,7 @@ def do_landmark_clustering(landmark_vectors, clustering_params, min_samples, ver
     good_site_normed_threshold = params.pop('good_site_normed_threshold', predict_threshold)
     good_site_project_thresh = params.pop('good_site_projected_threshold', predict_threshold)
     weighted_reps = params.pop('weighted_representative_landmarks', True)
+    eig_where = params.pop('eigenvectors', 'device')      # not in the reference: 'host' = LAPACK on gathered blocks
 
     # -- cluster landmarks (mcl.py:66-68)
     with timer.phase("  Markov clustering"):
@@ -195,7 +225,11 @@ def do_landmark_clustering(landmark_vectors, clustering_params, min_samples, ver
 
     # -- centres: principal eigenvector of each cluster's covariance block (mcl.py:73-80)
     with timer.phase("  centres: eigenvectors of the covariance blocks"):
-        vectors = principal_vectors(_covariance_blocks(cov, clusters))
+        if eig_where == 'host':
+            vectors = principal_vectors(_covariance_blocks(cov, clusters))
+        else:
+            w_all = principal_vectors_device(cov, clusters, L)
+            vectors = [w_all[np.asarray(cl, dtype=np.int64)] for cl in clusters]
         cid, w = _centre_tables(clusters, vectors, L)
 
     # -- pass B: best matching landmark vector per cluster (mcl.py:81-89)
@@ -271,7 +305,22 @@ def do_landmark_clustering(landmark_vectors, clustering_params, min_samples, ver
         with timer.phase("  pass D: predict with the kept centres"):
             cid, w = _centre_tables(clusters, vectors, L)
             eng.set_centers(cid, w, n_sites)
-            res = final_predict(n_sites, False)
+            if source.sparse is not None:
+                # the surviving centres are unchanged: rows of surviving clusters keep arg-max and confidence, only
+                # the rows of removed clusters are predicted again (sitb_relabel_select / sitb_assign_sparse_rows)
+                keep = torch.as_tensor(np.nonzero(count_mask)[0], device=eng.device)
+                n_old = len(count_mask)
+                sb_old = res['site_best']
+                res = dict(labels=res['labels'], confs=res['confs'], rep=res['rep'].index_select(0, keep).contiguous(),
+                           rep_w=res['rep_w'].index_select(0, keep).contiguous(),
+                           site_best=torch.cat([sb_old[:n_old].index_select(0, keep), sb_old[n_old:2 * n_old].index_select(0, keep),
+                                                torch.zeros((n_sites,), dtype=torch.int64, device=eng.device)]))
+                remap = np.full(n_old, -1, dtype=np.int32)
+                remap[count_mask] = np.arange(n_sites, dtype=np.int32)
+                eng.repredict_removed(source.sparse, predict_threshold, remap, res['labels'], res['confs'],
+                                      rep=res['rep'], rep_w=res['rep_w'], site_best=res['site_best'])
+            else:
+                res = final_predict(n_sites, False)
     labels, confs, rep, rep_w, site_best = res['labels'], res['confs'], res['rep'], res['rep_w'], res['site_best']
     with timer.phase("  representative vectors (collective)"):
         if comm is not None:
