@@ -29,6 +29,15 @@ import tempfile
 import threading
 import time
 
+# The reference arm pins its BLAS thread count to the same value at every --gpus N (torchrun exports OMP_NUM_THREADS=1
+# to its workers; the reference's np.dot / matrix_power calls would then run on one thread at N >= 2 and on all cores at
+# N = 1).  OpenBLAS sizes its pool when numpy is imported, so this has to happen first.
+REFERENCE_BLAS_THREADS = min(16, os.cpu_count() or 1)
+if "reference" in sys.argv:
+    os.environ["OMP_NUM_THREADS"] = str(REFERENCE_BLAS_THREADS)
+    os.environ["OPENBLAS_NUM_THREADS"] = str(REFERENCE_BLAS_THREADS)
+    os.environ["MKL_NUM_THREADS"] = str(REFERENCE_BLAS_THREADS)
+
 import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
@@ -50,6 +59,8 @@ def parse_args():
     ap.add_argument("--e2e-steps", type=int, default=2)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-frames", type=int, default=400)
+    ap.add_argument("--strong-frames", type=int, default=1000000,
+                    help="total frames of the strong-scaling leg (BASELINE configs[4]: 10^6 LLZO frames over the N GPUs); 0 = skip")
     ap.add_argument("--assign-mode", default="two_tier", choices=["two_tier", "exact"],
                     help="the timed fill+assign pass: FP32 first tier + float64 for undecided rows (default), or all float64")
     return ap.parse_args()
@@ -178,10 +189,13 @@ def reference_run_once(ref, system, cfg, frames):
     sn = syn.site_network_for(system, ref.SiteNetwork, ref.Atoms)
     la = ref.LandmarkAnalysis(clustering_algorithm='mcl', verbose=False, force_no_memmap=True,
                               max_mobile_per_site=cfg.get("max_mobile_per_site", 1))
-    # time the reference's own fill (helpers.pyx:12, the Cython function this repository replaces) inside its run:
-    # the unmodified function is called through a wrapper that only reads the clock
+    # time the reference's own fill (helpers.pyx:12, the Cython function this repository replaces) and its assign
+    # step (DotProdClassifier.predict, DotProdClassifier.pyx:129-197, called twice by fit_predict) inside its run:
+    # the unmodified functions are called through wrappers that only read the clock
     fill = ref.helpers._fill_landmark_vectors
+    predict = ref.DotProdClassifier.predict
     spent = [0.0]
+    spent_predict = []
 
     def timed_fill(*a, **k):
         t0 = time.perf_counter()
@@ -189,16 +203,30 @@ def reference_run_once(ref, system, cfg, frames):
             return fill(*a, **k)
         finally:
             spent[0] += time.perf_counter() - t0
+
+    def timed_predict(self, *a, **k):
+        t0 = time.perf_counter()
+        try:
+            return predict(self, *a, **k)
+        finally:
+            spent_predict.append(time.perf_counter() - t0)
     ref.helpers._fill_landmark_vectors = timed_fill
+    ref.DotProdClassifier.predict = timed_predict
     try:
         t = time.perf_counter()
         la.run(sn, frames)
         dt = time.perf_counter() - t
     finally:
         ref.helpers._fill_landmark_vectors = fill
+        ref.DotProdClassifier.predict = predict
+    fa = spent[0] + sum(spent_predict)
     LAST_REFERENCE_SPLIT["fill_seconds"] = spent[0]
-    LAST_REFERENCE_SPLIT["clustering_and_rest_seconds"] = dt - spent[0]
+    LAST_REFERENCE_SPLIT["predict_seconds"] = sum(spent_predict)
+    LAST_REFERENCE_SPLIT["predict_calls"] = len(spent_predict)
+    LAST_REFERENCE_SPLIT["clustering_and_rest_seconds"] = dt - fa
     LAST_REFERENCE_SPLIT["fill_only_value"] = len(frames) * system.n_total / max(spent[0], 1e-9)   # same unit as value
+    LAST_REFERENCE_SPLIT["fill_assign_seconds"] = fa
+    LAST_REFERENCE_SPLIT["fill_assign_value"] = len(frames) * system.n_total / max(fa, 1e-9)
     return dt
 
 
@@ -264,28 +292,41 @@ def run_reference_arm(args):
     from sitator_b200 import synthetic as syn
     system, cfg = syn.make_config(WORKLOAD)
     n_steps = args.steps + args.warmup
-    # bounded sample per step: the reference runs ~20 frames/s on this shape; keep the arm within ~150 s
-    per_step = max(40, min(600, int(150.0 / max(n_steps, 1) * 18.0)))
+    # bounded sample per step: the reference's whole run() takes ~26 ms per frame on this shape (most of it the
+    # clustering plugin's per-cluster passes over the dense matrix); 400 frames per step unless the step count
+    # would push the arm beyond ~4 minutes
+    per_step = max(60, min(400, int(240.0 / max(n_steps, 1) / 0.026)))
     frames = system.trajectory(per_step)
     ref = load_reference()
     kind = "reference" if ref is not None else "port"
-    times = []
+    times, fa_times = [], []
     for i in range(n_steps):
         dt = reference_run_once(ref, system, cfg, frames) if ref is not None else port_run_once(system, cfg, frames)
         if i >= args.warmup:
             times.append(dt)
-    t = float(np.mean(times))
+            fa_times.append(LAST_REFERENCE_SPLIT.get("fill_assign_seconds", dt))
+    t_run = float(np.mean(times))
+    t = float(np.mean(fa_times))
+    # like for like: `value` = the reference's fill (helpers._fill_landmark_vectors) + its assign step (the two
+    # DotProdClassifier.predict calls of fit_predict) -- what our fused fill + assign pass replaces; `e2e` = its whole run()
     value = per_step * system.n_total / t
+    e2e_value = per_step * system.n_total / t_run
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": t * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": workload_name(system, per_step), "frames_per_step": per_step},
+        "config": {"workload": workload_name(system, per_step), "frames_per_step": per_step,
+                   "step": "the reference's fill + assign (helpers._fill_landmark_vectors + both DotProdClassifier.predict calls) "
+                           "clocked inside its own LandmarkAnalysis.run (mcl); e2e = that whole run()"
+                           if kind == "reference" else "whole run of the NumPy port"},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": 1, "kind": kind, "blas_threads": blas_threads(),
-                         "host_cpus": os.cpu_count(),
+                         "blas_threads_pinned": REFERENCE_BLAS_THREADS, "host_cpus": os.cpu_count(),
+                         "whole_run_value": e2e_value, "whole_run_ms_per_step": t_run * 1e3,
                          **({k: round(v, 4) for k, v in LAST_REFERENCE_SPLIT.items()} if kind == "reference" else {}),
-                         "sample": "whole LandmarkAnalysis.run (mcl) on %d frames per step" % per_step},
-        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                         "sample": "%d frames per step; fill and assign are single-threaded in the reference, only "
+                                   "np.dot / matrix_power use the BLAS threads" % per_step},
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0,
+                "ms": t_run * 1e3, "what": "whole LandmarkAnalysis.run (mcl) of the compiled reference"},
     }
     emit(line)
 
@@ -383,6 +424,34 @@ def run_ours(args):
            "d2h_bytes_per_step": int(F * M * 16), "ms": e2e_t * 1e3, "steps": len(e2e_ms), "n_sites": int(n_sites),
            "what": "LandmarkAnalysis(clustering_algorithm='mcl').run(sn, frames) with frames in pinned host memory"}
 
+    # ---- e2e_strong: BASELINE configs[4], a fixed 10^6-frame LLZO trajectory split over the N ranks ------------
+    e2e_strong = None
+    if args.strong_frames and args.frames is None:
+        Fs = args.strong_frames // world
+        big = torch.empty((Fs, A, 3), dtype=torch.float64, pin_memory=True)
+        bf = big.numpy()
+        for f0 in range(0, Fs, F):          # the rank's share, tiled from its weak-scaling block (synthetic data either way)
+            n = min(F, Fs - f0)
+            bf[f0:f0 + n] = frames[:n]
+        sms = []
+        for i in range(3):
+            las = LandmarkAnalysis(clustering_algorithm='mcl', verbose=False, **kw)
+            sns = syn.site_network_for(system)
+            barrier()
+            a = torch.cuda.Event(enable_timing=True); b = torch.cuda.Event(enable_timing=True)
+            a.record()
+            sts = las.run(sns, bf)
+            b.record()
+            barrier()
+            if i >= 1:
+                sms.append(max_over_ranks(a.elapsed_time(b)))
+        ts = float(np.mean(sms)) * 1e-3
+        e2e_strong = {"value": Fs * world * A / ts, "unit": UNIT, "ms": ts * 1e3, "scaling": "strong", "steps": len(sms),
+                      "total_frames": Fs * world, "frames_per_gpu": Fs, "h2d_bytes_per_step": int(bf.nbytes),
+                      "d2h_bytes_per_step": int(Fs * M * 16), "n_sites": int(sts.site_network.n_sites),
+                      "what": "the same run() on BASELINE configs[4]: a fixed 10^6-frame trajectory split over the ranks"}
+        del las, sts, big, bf
+
     # ---- value: the fused fill + assign pass over the resident frames --------------------------------
     eng = la._engine                       # frames of the last run are still resident
     labels = torch.empty(F * M, dtype=torch.int64, device="cuda")
@@ -477,7 +546,7 @@ def run_ours(args):
                    "l2": "resident frames (%d MB) larger than L2 (126 MB); every step streams them from HBM" % (frames.nbytes >> 20),
                    "step": "one K1 pass (fill + assign) over all resident frames, centres from a previous run",
                    "assign_mode": args.assign_mode},
-        "e2e": e2e, "gpu_launches": args.steps * (2 if args.assign_mode == "two_tier" else 1), "clocks": clocks, "roofline": roofline,
+        "e2e": e2e, "e2e_strong": e2e_strong, "gpu_launches": args.steps * (2 if args.assign_mode == "two_tier" else 1), "clocks": clocks, "roofline": roofline,
         "labels_match_run": same,
         "assign_mode": args.assign_mode,
         "two_tier": {

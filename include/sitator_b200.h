@@ -286,6 +286,13 @@ int sitb_jump_analysis(int device, const int64_t* dev_traj, int64_t n_frames, in
                        double* dev_n_ij, uint64_t* dev_total_time, double* dev_lag_sum, uint64_t* dev_lag_n,
                        uint64_t* dev_n_problems, void* cuda_stream);
 
+/* Frame-sharded JumpAnalysis: one shard's per-atom summary dev_summary[n_mobile][4] = (first frame with a known site,
+ * that site, last known site, frame of the last jump decided inside the shard); local frame indices, -1 = none.
+ * The caller chains the shards' summaries in frame order into dev_carry_label / dev_carry_jump of sitb_jump_analysis
+ * (the sequential state of JumpAnalysis.py:46-49,91-96: last_known and time_at_current). */
+int sitb_jump_analysis_summary(int device, const int64_t* dev_traj, int64_t n_frames, int32_t n_mobile,
+                               int64_t* dev_summary, void* cuda_stream);
+
 /* ---- post-processing of the assignment stream ----
  * sitb_assign_last_known: SiteTrajectory.assign_to_last_known_site (SiteTrajectory.py:235-304), in place on dev_traj:
  *   an unknown entry takes the atom's last known site while fewer than frame_threshold frames have passed since

@@ -89,6 +89,7 @@ SIGNATURES = {
     "sitb_jump_scan": (C.c_int, [C.c_int, _P, C.c_int64, C.c_int32, C.c_int32, C.c_int32, _P, _P, _P, _P]),
     "sitb_jump_compact": (C.c_int, [C.c_int, _P, _P, C.c_int64, C.c_int32, C.c_int64, _P, C.c_uint64, _P]),
     "sitb_jump_analysis": (C.c_int, [C.c_int, _P, C.c_int64, C.c_int32, C.c_int32, C.c_int32] + [_P] * 8),
+    "sitb_jump_analysis_summary": (C.c_int, [C.c_int, _P, C.c_int64, C.c_int32, _P, _P]),
     "sitb_recenter": (C.c_int, [C.c_int, _P, C.c_int64, C.c_int32, _P, _P, _P]),
     "sitb_assign_last_known": (C.c_int, [C.c_int, _P, C.c_int64, C.c_int32, C.c_int64, C.c_int64, _P, _P, _P, _P, _P,
                                          C.c_int32, _P]),

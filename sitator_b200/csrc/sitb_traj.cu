@@ -230,6 +230,25 @@ __global__ void k_ja_carry(const JaSummary* __restrict__ sum, long long n_chunks
     }
 }
 
+// one shard's summary per atom, for the carry over frame shards: (first known frame, first label, last label, frame of
+// the last jump decided inside the shard), local frame indices, -1 = none
+__global__ void k_ja_shard_summary(const JaSummary* __restrict__ sum, long long n_chunks, int M, long long* __restrict__ out) {
+    const int a = blockIdx.x * blockDim.x + threadIdx.x;
+    if (a >= M) return;
+    long long first_frame = -1, first_label = -1, last_label = -1, last_jump = -1;
+    int lab = -1;
+    for (long long c = 0; c < n_chunks; ++c) {
+        const JaSummary s = sum[c * M + a];
+        if (s.first_known_frame < 0) continue;
+        if (first_frame < 0) { first_frame = s.first_known_frame; first_label = s.first_label; }
+        else if (s.first_label != lab) last_jump = s.first_known_frame;
+        if (s.last_internal_jump >= 0) last_jump = s.last_internal_jump;
+        lab = s.last_label;
+        last_label = lab;
+    }
+    out[4 * a + 0] = first_frame; out[4 * a + 1] = first_label; out[4 * a + 2] = last_label; out[4 * a + 3] = last_jump;
+}
+
 // per element: last known site, filled current site, frames at current site (JumpAnalysis.py:63-93)
 __global__ void k_ja_expand(const long long* __restrict__ traj, long long F, int M, const int2* __restrict__ carry,
                             int first_frame_is_start, int* __restrict__ last_o, int* __restrict__ cur_o,
@@ -485,6 +504,24 @@ extern "C" int sitb_jump_analysis(int device, const int64_t* dev_traj, int64_t n
     if (e == cudaSuccess) e = cudaStreamSynchronize(st);
     pool_free(sum, st); pool_free(carry, st); pool_free(la, st); pool_free(ca, st); pool_free(ta, st);
     if (e != cudaSuccess) return set_error(SITB_E_CUDA, "sitb_jump_analysis: %s", cudaGetErrorString(e));
+    return SITB_OK;
+}
+
+extern "C" int sitb_jump_analysis_summary(int device, const int64_t* dev_traj, int64_t n_frames, int32_t n_mobile,
+                                          int64_t* dev_summary, void* cuda_stream) {
+    if (!dev_traj || !dev_summary || n_frames <= 0 || n_mobile <= 0)
+        return set_error(SITB_E_INVALID, "sitb_jump_analysis_summary: bad argument");
+    CKT(cudaSetDevice(device));
+    cudaStream_t st = (cudaStream_t)cuda_stream;
+    const long long n_chunks = (n_frames + CHUNK - 1) / CHUNK;
+    JaSummary* sum = nullptr;
+    CKT(pool_alloc((void**)&sum, sizeof(JaSummary) * n_chunks * n_mobile, st));
+    k_ja_summary<<<(unsigned)n_chunks, 128, 0, st>>>((const long long*)dev_traj, n_frames, n_mobile, sum);
+    k_ja_shard_summary<<<(n_mobile + 127) / 128, 128, 0, st>>>(sum, n_chunks, n_mobile, (long long*)dev_summary);
+    cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    pool_free(sum, st);
+    if (e != cudaSuccess) return set_error(SITB_E_CUDA, "sitb_jump_analysis_summary: %s", cudaGetErrorString(e));
     return SITB_OK;
 }
 

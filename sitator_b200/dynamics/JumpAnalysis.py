@@ -32,8 +32,7 @@ class JumpAnalysis(object):
         """Adds edge/site attributes to ``st``'s ``SiteNetwork``; returns ``st``."""
         import torch
         assert isinstance(st, SiteTrajectory)
-        if getattr(st, "_comm", None) is not None:
-            raise NotImplementedError("JumpAnalysis on a frame-sharded SiteTrajectory: gather the shards first")
+        comm = getattr(st, "_comm", None)
         logger.info("Running JumpAnalysis...")
         lib = _native.load()
         n_mobile = st.site_network.n_mobile
@@ -41,16 +40,45 @@ class JumpAnalysis(object):
         n_sites = st.site_network.n_sites
         dev = torch.cuda.current_device()
         traj = torch.as_tensor(np.ascontiguousarray(st.traj, dtype=np.int64), device="cuda")
+        stream = torch.cuda.current_stream().cuda_stream
+        first_is_start, carry_label, carry_jump = 1, None, None
+        if comm is not None:
+            # frame-sharded: the scan's sequential state (last known site, frame of the last jump; JumpAnalysis.py:46-49,
+            # :91-96) enters each shard as a carry chained over the lower ranks' summaries
+            summ = torch.empty((n_mobile, 4), dtype=torch.int64, device="cuda")
+            _native.check(lib.sitb_jump_analysis_summary(dev, C.c_void_p(traj.data_ptr()), n_frames, n_mobile,
+                                                         C.c_void_p(summ.data_ptr()), C.c_void_p(stream)))
+            frame0 = int(st.frame0)
+            mine = summ.cpu().numpy()
+            for col in (0, 3):                                   # local -> global frame indices
+                mine[:, col] = np.where(mine[:, col] >= 0, mine[:, col] + frame0, -1)
+            alls = comm.allgather_numpy(mine)                    # (world, M, 4), rank order = frame order
+            lab = np.full(n_mobile, -1, dtype=np.int64)
+            jmp = np.full(n_mobile, -1, dtype=np.int64)          # global frame of the last jump; -1 = never
+            for r in range(comm.rank):
+                s = alls[r]
+                has = s[:, 0] >= 0
+                jmp = np.where(has & (lab >= 0) & (s[:, 1] != lab), s[:, 0], jmp)
+                jmp = np.where(has & (s[:, 3] >= 0), s[:, 3], jmp)
+                lab = np.where(has, s[:, 2], lab)
+            first_is_start = int(comm.rank == 0)
+            carry_label = torch.as_tensor(lab, device="cuda")
+            carry_jump = torch.as_tensor(jmp - frame0, device="cuda")      # local index (negative: an earlier shard)
+            n_frames_total = comm.allreduce_sum_scalar(n_frames)
+        else:
+            n_frames_total = n_frames
         n_ij = torch.zeros((n_sites, n_sites), dtype=torch.float64, device="cuda")
         lag_sum = torch.zeros((n_sites, n_sites), dtype=torch.float64, device="cuda")
         lag_n = torch.zeros((n_sites, n_sites), dtype=torch.int64, device="cuda")
         total_time = torch.zeros((n_sites,), dtype=torch.int64, device="cuda")
         n_problems = torch.zeros((1,), dtype=torch.int64, device="cuda")
-        stream = torch.cuda.current_stream().cuda_stream
-        P = lambda t: C.c_void_p(t.data_ptr())
-        _native.check(lib.sitb_jump_analysis(dev, P(traj), n_frames, n_mobile, n_sites, 1, C.c_void_p(0), C.c_void_p(0),
-                                             P(n_ij), P(total_time), P(lag_sum), P(lag_n), P(n_problems),
+        P = lambda t: C.c_void_p(0 if t is None else t.data_ptr())
+        _native.check(lib.sitb_jump_analysis(dev, P(traj), n_frames, n_mobile, n_sites, first_is_start, P(carry_label),
+                                             P(carry_jump), P(n_ij), P(total_time), P(lag_sum), P(lag_n), P(n_problems),
                                              C.c_void_p(stream)))
+        if comm is not None:
+            for t_ in (n_ij, lag_sum, lag_n, total_time, n_problems):
+                comm.allreduce_sum_(t_)
         n_ij = n_ij.cpu().numpy()
         avg_time_before_jump = lag_sum.cpu().numpy()
         avg_time_before_jump_n = lag_n.cpu().numpy()
@@ -78,8 +106,8 @@ class JumpAnalysis(object):
         for site in range(n_sites):                                # JumpAnalysis.py:122-129
             times = avg_time_before_jump[site]
             noninf = times < np.inf
-            res_times[site] = np.mean(times[noninf]) if np.any(noninf) else n_frames
+            res_times[site] = np.mean(times[noninf]) if np.any(noninf) else n_frames_total
         sn.add_site_attribute('residence_times', res_times)
-        sn.add_site_attribute('occupancy_freqs', np.sum(n_ij, axis=0) / st.n_frames)
+        sn.add_site_attribute('occupancy_freqs', np.sum(n_ij, axis=0) / n_frames_total)
         sn.add_site_attribute('total_corrected_residences', total_time_spent_at_site)
         return st

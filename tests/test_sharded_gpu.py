@@ -43,7 +43,12 @@ def _run_shard(rank, world, port, bounds, q):
         smooth = SmoothSiteTrajectory(remove_unoccupied_sites=False).run(st, 3).traj
         lk = st.copy()
         lk_info = lk.assign_to_last_known_site(frame_threshold=2)
-        q.put((rank, dict(traj=st.traj, confs=st.confidences, centers=np.asarray(st.site_network.centers),
+        # JumpAnalysis over the shard boundary: last known site and time-at-current-site are carried in
+        from sitator_b200.dynamics import JumpAnalysis
+        ja_st = JumpAnalysis().run(st.copy())
+        ja = {k: np.asarray(getattr(ja_st.site_network, k))
+              for k in ("n_ij", "p_ij", "jump_lag", "residence_times", "occupancy_freqs", "total_corrected_residences")}
+        q.put((rank, dict(traj=st.traj, confs=st.confidences, centers=np.asarray(st.site_network.centers), ja=ja,
                           smooth=smooth, lk=lk.traj, lk_info=lk_info,
                           verts=[sorted(v) for v in st.site_network.vertices], frame0=st.frame0,
                           n_multi=la.n_multiple_assignments, avg=la.avg_mobile_per_site, nzero=la.n_all_zero_lvecs,
@@ -66,6 +71,11 @@ def test_two_shards_equal_one():
     want_smooth = SmoothSiteTrajectory(remove_unoccupied_sites=False).run(st, 3).traj
     want_lk = st.copy()
     want_lk_info = want_lk.assign_to_last_known_site(frame_threshold=2)
+
+    from sitator_b200.dynamics import JumpAnalysis
+    ja_st = JumpAnalysis().run(st.copy())
+    want_ja = {k: np.asarray(getattr(ja_st.site_network, k))
+               for k in ("n_ij", "p_ij", "jump_lag", "residence_times", "occupancy_freqs", "total_corrected_residences")}
 
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
@@ -92,5 +102,9 @@ def test_two_shards_equal_one():
     assert np.array_equal(np.concatenate([res[0]["lk"], res[1]["lk"]]), want_lk.traj)
     for r in range(2):
         assert res[r]["lk_info"] == want_lk_info
+    # every JumpAnalysis attribute of the sharded run equals the single-rank run, on every rank (JumpAnalysis.py:68-129)
+    for r in range(2):
+        for k, want in want_ja.items():
+            assert np.array_equal(res[r]["ja"][k], want, equal_nan=True), (r, k)
     assert np.array_equal(np.concatenate([res[0]["jumps"], res[1]["jumps"]]), want_j)
     assert np.array_equal(np.concatenate([res[0]["jumps_u"], res[1]["jumps_u"]]), want_ju)
