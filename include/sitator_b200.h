@@ -82,6 +82,9 @@ typedef struct sitb_status {
 
 const char* sitb_last_error(void);
 int sitb_version(void);
+/* out[0] = sizeof(sitb_network_desc), out[1] = sizeof(sitb_status): a binding compares them with its own struct
+ * definitions before the first call that writes through such a pointer (sitb_get_status fills the whole struct). */
+int sitb_abi_sizes(uint64_t* out2);
 
 /* Context: device copies of the basis + precomputed tables (replaces LandmarkAnalysis.py:179, :191-202). */
 int sitb_create(const sitb_network_desc* desc, int device, sitb_ctx** out);

@@ -46,6 +46,7 @@ _P = C.c_void_p
 SIGNATURES = {
     "sitb_last_error": (C.c_char_p, []),
     "sitb_version": (C.c_int, []),
+    "sitb_abi_sizes": (C.c_int, [C.POINTER(C.c_uint64)]),
     "sitb_create": (C.c_int, [C.POINTER(NetworkDesc), C.c_int, C.POINTER(_P)]),
     "sitb_destroy": (None, [_P]),
     "sitb_set_stream": (C.c_int, [_P, _P]),
@@ -123,6 +124,12 @@ def load():
         fn = getattr(lib, name)          # AttributeError if the symbol is not exported
         fn.restype = res
         fn.argtypes = args
+    sizes = (C.c_uint64 * 2)()
+    lib.sitb_abi_sizes(sizes)
+    if (int(sizes[0]), int(sizes[1])) != (C.sizeof(NetworkDesc), C.sizeof(Status)):
+        raise ImportError("sitator_b200: %s was built from a different include/sitator_b200.h (struct sizes %d / %d, "
+                          "binding %d / %d); rebuild with `python -m sitator_b200.build --force`"
+                          % (_LIB_PATH, sizes[0], sizes[1], C.sizeof(NetworkDesc), C.sizeof(Status)))
     _lib = lib
     return lib
 

@@ -178,7 +178,13 @@ static int build_grid(sitb_ctx* c, double margin);
 extern "C" int sitb_reset_status(sitb_ctx* c);
 
 extern "C" const char* sitb_last_error(void) { return g_err; }
-extern "C" int sitb_version(void) { return 100; }
+extern "C" int sitb_version(void) { return 200; }
+extern "C" int sitb_abi_sizes(uint64_t* out) {
+    if (!out) return fail(SITB_E_INVALID, "sitb_abi_sizes: null argument");
+    out[0] = sizeof(sitb_network_desc);
+    out[1] = sizeof(sitb_status);
+    return SITB_OK;
+}
 
 extern "C" int sitb_create(const sitb_network_desc* d, int device, sitb_ctx** out) {
     if (!d || !out) return fail(SITB_E_INVALID, "sitb_create: null argument");

@@ -112,17 +112,22 @@ class LandmarkAnalysis(object):
         """Landmark vectors from the last ``run()``: materialised on demand as a read-only
         (n_frames * n_mobile, landmark_dimension) float64 array."""
         if self._landmark_vectors is None:
-            import torch
-            eng = self._engine
-            out = np.empty((eng.n_frames * eng.M, eng.L), dtype=np.float64)
-            step = max(1, (256 << 20) // (eng.M * eng.L * 8))
-            for f0 in range(0, eng.n_frames, step):
-                n = min(step, eng.n_frames - f0)
-                out[f0 * eng.M:(f0 + n) * eng.M] = eng.fill_dense(f0, n, dtype=torch.float64).cpu().numpy()
-            self._landmark_vectors = out
+            self._landmark_vectors = self._dense_landmark_vectors(self._engine)
         view = self._landmark_vectors[:]
         view.flags.writeable = False
         return view
+
+    @staticmethod
+    def _dense_landmark_vectors(eng):
+        """The reference's (n_frames * n_mobile, L) float64 matrix (LandmarkAnalysis.py:209-220) in host memory, filled
+        chunk by chunk from the device."""
+        import torch
+        out = np.empty((eng.n_frames * eng.M, eng.L), dtype=np.float64)
+        step = max(1, (256 << 20) // (eng.M * eng.L * 8))
+        for f0 in range(0, eng.n_frames, step):
+            n = min(step, eng.n_frames - f0)
+            out[f0 * eng.M:(f0 + n) * eng.M] = eng.fill_dense(f0, n, dtype=torch.float64).cpu().numpy()
+        return out
 
     @analysis_result
     def landmark_dimension(self):
@@ -217,12 +222,27 @@ class LandmarkAnalysis(object):
         logger.info("  - computing landmark vectors / clustering -")
         source = LandmarkVectorSource(engine, comm)
         source.timer = timer
-        clustermod = importlib.import_module("sitator_b200.landmark.cluster." + self._cluster_algo)
+        try:
+            clustermod = importlib.import_module("sitator_b200.landmark.cluster." + self._cluster_algo)
+        except ImportError:
+            # a dotted module path: a plugin written for the reference's contract (LandmarkAnalysis.py:234-242),
+            # do_landmark_clustering(landmark_vectors (N, L) ndarray, clustering_params, min_samples, verbose) -> dict
+            clustermod = importlib.import_module(self._cluster_algo)
+        native_plugin = hasattr(clustermod, "landmark_graph") or hasattr(clustermod, "first_pass")
+        cluster_input = source
         with timer.phase("pass A: fill + seen + Gram (+ H2D wait, all-reduce)"):
             if hasattr(clustermod, "landmark_graph"):
                 clustermod.landmark_graph(source, self._clustering_params.get('gram_method', 'sparse'))   # pass A runs the lattice / zero-vector checks
             elif hasattr(clustermod, "first_pass"):
                 clustermod.first_pass(source)
+            else:
+                if comm is not None:
+                    raise NotImplementedError("a clustering plugin with the reference's dense-matrix contract cannot run "
+                                              "frame-sharded; use 'mcl' or 'dotprod'")
+                # the reference's contract: the whole (N, L) matrix, here materialised from the device (this is the
+                # reference's memory footprint -- 12 KB per landmark vector at L = 1500 -- and meant for small runs)
+                self._landmark_vectors = self._dense_landmark_vectors(engine)
+                cluster_input = self._landmark_vectors
         with timer.phase("status + first error (collective)"):
             status = engine.status()
             self._raise_first_error(status, comm, engine)
@@ -240,7 +260,7 @@ class LandmarkAnalysis(object):
         logger.info("  - clustering landmark vectors -")
         with timer.phase("clustering"):
             clustering = clustermod.do_landmark_clustering(
-                source, clustering_params=self._clustering_params,
+                cluster_input, clustering_params=self._clustering_params,
                 min_samples=self._minimum_site_occupancy / float(sn.n_mobile), verbose=self.verbose)
 
         cluster_counts = clustering[LandmarkAnalysis.CLUSTERING_CLUSTER_SIZE]
@@ -285,8 +305,11 @@ class LandmarkAnalysis(object):
         with timer.phase("site centres (collective)"):
             if self.site_centers_method in (self.SITE_CENTERS_REAL_WEIGHTED, self.SITE_CENTERS_REAL_UNWEIGHTED):
                 weighted = self.site_centers_method == self.SITE_CENTERS_REAL_WEIGHTED
-                site_centers = engine.site_centers(dev_labels, dev_confs, n_sites, weighted,
-                                                   clustering.get('_dev_site_best') if weighted else None, comm)
+                site_best = clustering.get('_dev_site_best') if weighted else None
+                if weighted and site_best is None:      # a plugin with the reference's contract returns labels and confidences only
+                    from .cluster.dotprod import _site_best_table
+                    site_best = _site_best_table(dev_labels, dev_confs, n_sites, frame0 * sn.n_mobile)
+                site_centers = engine.site_centers(dev_labels, dev_confs, n_sites, weighted, site_best, comm)
             else:
                 if rep_lvecs is None:
                     raise ValueError("Chosen clustering method (with current parameters) didn't return representative "
@@ -312,6 +335,7 @@ class LandmarkAnalysis(object):
                       "n_screen_rejects": status.n_screen_rejects,
                       "nnz": status.nnz, "mcl_iterations": clustering.get('_mcl_iterations'),
                       "gram_method": getattr(source, "gram_method", None),
+                      "plugin_contract": "source" if native_plugin else "ndarray",
                       "phases_ms": timer.as_dict(), "phases_synchronised": timer.sync}
         self._has_run = True
         return out_st

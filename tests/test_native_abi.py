@@ -61,3 +61,22 @@ def test_product_never_imports_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 text = open(os.path.join(dirpath, f)).read()
                 assert not re.search(r"^\s*(from|import)\s+oracle\b", text, flags=re.M), os.path.join(dirpath, f)
+
+
+def test_struct_sizes_of_every_binding_match_the_library():
+    """sitb_get_status writes the whole struct: a binding with a shorter Status would be overrun (round-1 advice).  The
+    in-package binding, the reference-side binding INTEGRATION.md quotes, and the header must agree."""
+    from sitator_b200.build import build_native
+    build_native()
+    from sitator_b200 import _native
+    lib = _native.load()
+    sizes = (C.c_uint64 * 2)()
+    assert lib.sitb_abi_sizes(sizes) == 0
+    assert (sizes[0], sizes[1]) == (C.sizeof(_native.NetworkDesc), C.sizeof(_native.Status))
+    from sitator_b200.integration import reference_binding as rb      # asserts the same at import
+    assert (C.sizeof(rb.Desc), C.sizeof(rb.Status)) == (sizes[0], sizes[1])
+    # INTEGRATION.md shows that file's struct definitions verbatim
+    doc = open(os.path.join(ROOT, "INTEGRATION.md")).read()
+    src = open(os.path.join(ROOT, "sitator_b200", "integration", "reference_binding.py")).read()
+    block = src[src.index("class Status(C.Structure):"):src.index("_sizes = ")].strip()
+    assert block in doc, "INTEGRATION.md no longer quotes the Status struct of reference_binding.py"
