@@ -431,7 +431,7 @@ class LandmarkEngine(object):
     def weighted_point_averages(self, points, weights):
         """Per row of ``weights`` (n_sites, n_points): periodic weighted average of ``points`` with weight > 0."""
         torch = _torch()
-        pts = torch.as_tensor(np.ascontiguousarray(points, dtype=np.float64), device=self.device)
+        pts = torch.as_tensor(np.array(points, dtype=np.float64, order="C", copy=True), device=self.device)
         w = torch.as_tensor(np.ascontiguousarray(weights, dtype=np.float64), device=self.device)
         out = self._empty((w.shape[0], 3), torch.float64)
         _native.check(self._lib.sitb_weighted_point_average(self._ctx, self._ptr(pts), self._ptr(w), w.shape[0],

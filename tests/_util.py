@@ -55,7 +55,7 @@ def triclinic_system(seed=5, n_static=40, n_mobile=6, n_landmarks=90, n_frames=1
 
 
 GOLDEN_DIR = __import__("os").path.join(__import__("os").path.dirname(__import__("os").path.abspath(__file__)), "golden")
-GOLDEN_CASES = ["toy_bcc_300", "llzo_60", "lgps_dynamic_40"]
+GOLDEN_CASES = ["toy_bcc_300", "llzo_60", "lgps_dynamic_40", "toy_bcc_2000", "laso_16"]
 
 
 DOTPROD_GOLDEN_CASES = ["toy_bcc_300_dotprod", "llzo_60_dotprod", "lgps_dynamic_40_dotprod"]

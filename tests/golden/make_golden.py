@@ -23,6 +23,9 @@ CASES = [
     ("toy_bcc_300", "toy_bcc", 300, {}),
     ("llzo_60", "llzo", 60, {}),
     ("lgps_dynamic_40", "lgps_dynamic", 40, {"swap_statics_at": 13}),
+    # BASELINE configs[0] at its stated length, and the configs[3] shape (1400 + 200 atoms, 3000 landmarks)
+    ("toy_bcc_2000", "toy_bcc", 2000, {}),
+    ("laso_16", "laso", 16, {}),
 ]
 
 
@@ -155,6 +158,12 @@ if __name__ == "__main__":
         sys.exit("needs /root/reference to build oracle/_ref")
     ref = ref_loader.load()
     which = sys.argv[1:] or ["mcl", "dotprod", "post"]
+    only = [w[5:] for w in which if w.startswith("only:")]       # e.g. only:laso_16 (leaves the other fixtures untouched)
+    if only:
+        for case in CASES:
+            if case[0] in only:
+                run_case(ref, *case)
+        sys.exit(0)
     if "mcl" in which:
         for case in CASES:
             run_case(ref, *case)
