@@ -337,5 +337,8 @@ class LandmarkAnalysis(object):
                       "gram_method": getattr(source, "gram_method", None),
                       "plugin_contract": "source" if native_plugin else "ndarray",
                       "phases_ms": timer.as_dict(), "phases_synchronised": timer.sync}
+        # (landmark -> cluster map, landmark weight) of the final site centres, in the caller's landmark numbering: the
+        # rows of the reference's `centers` matrix (cluster/mcl.py:70-96) in sparse form; None for plugins that do not say
+        self.cluster_centers_ = clustering.get('_centers')
         self._has_run = True
         return out_st
