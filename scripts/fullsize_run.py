@@ -47,7 +47,13 @@ def main():
     ap.add_argument("--out", default=None)
     ap.add_argument("--ref-frames", type=int, default=0)
     ap.add_argument("--runs", type=int, default=3)
+    ap.add_argument("--chunk", type=int, default=5000, help="frames per seeded trajectory chunk (part of the trajectory's definition)")
+    ap.add_argument("--count-zero-vectors", action="store_true",
+                    help="check_for_zero_landmarks=False: count all-zero landmark vectors instead of raising (the synthetic "
+                         "LASO walk leaves an atom far from every landmark now and then)")
     args = ap.parse_args()
+    global CHUNK
+    CHUNK = args.chunk
     rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
     torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", 0)))
     if world > 1:
@@ -64,7 +70,7 @@ def main():
         frames[c * CHUNK:(c + 1) * CHUNK] = system.trajectory(CHUNK, seed=7919 * (c0 + c) + system.seed)
     gen_s = time.perf_counter() - t0
     kw = dict(max_mobile_per_site=max(4, cfg.get("max_mobile_per_site", 1)), dynamic_lattice_mapping=cfg["dynamic"],
-              check_for_zero_landmarks=cfg.get("check_for_zero_landmarks", True))
+              check_for_zero_landmarks=cfg.get("check_for_zero_landmarks", True) and not args.count_zero_vectors)
     sn = syn.site_network_for(system)
     ms = []
     for i in range(args.runs):
@@ -95,7 +101,7 @@ def main():
             cs ^= r["jump_checksum"]
         verts = [sorted(int(x) for x in v) for v in st.site_network.vertices]
         out = {
-            "config": args.config, "total_frames": args.total, "n_gpus": world, "frames_per_gpu": per, "n_atoms": A, "n_mobile": M,
+            "config": args.config, "total_frames": args.total, "chunk": CHUNK, "n_gpus": world, "frames_per_gpu": per, "n_atoms": A, "n_mobile": M,
             "n_landmarks": system.n_landmarks, "run_ms_all": ms, "run_ms_warm": ms[-1],
             "frame_atoms_per_s": args.total * A / (ms[-1] * 1e-3), "trajectory_generation_s_per_rank": [r["gen_s"] for r in allr],
             "n_sites": int(st.site_network.n_sites), "site_vertex_crc": zlib.crc32(json.dumps(verts).encode()),
@@ -103,7 +109,7 @@ def main():
             "label_block_crc32": [c for r in allr for c in r["crcs"]],
             "n_unassigned": sum(r["n_unassigned"] for r in allr), "conf_sum": sum(r["conf_sum"] for r in allr),
             "n_jumps": sum(r["n_jumps"] for r in allr), "jump_checksum": cs,
-            "n_multiple_assignments": int(la.n_multiple_assignments), "avg_mobile_per_site": float(la.avg_mobile_per_site),
+            "n_all_zero_lvecs": int(la.n_all_zero_lvecs), "n_multiple_assignments": int(la.n_multiple_assignments), "avg_mobile_per_site": float(la.avg_mobile_per_site),
             "phases_ms_rank0": la.stats.get("phases_ms"),
         }
         if args.ref_frames:
