@@ -48,7 +48,7 @@ typedef struct sitb_network_desc {
     int32_t n_static;      /* sn.n_static  */
     int32_t n_mobile;      /* sn.n_mobile  */
     int32_t n_landmarks;   /* sn.n_sites = landmark dimension */
-    int32_t max_verts;     /* columns of verts (<= 8) */
+    int32_t max_verts;     /* columns of verts (<= 16) */
     const double* host_cellmat;      /* [3][3] = cell^T           (PBCCalculator.pyx:33) */
     const double* host_cellmat_inv;  /* [3][3] inverse of cellmat (PBCCalculator.pyx:34); NULL: computed by adjugate */
     const int32_t* host_static_idx;  /* [n_static] frame index of each static-lattice atom, ascending */
@@ -140,6 +140,19 @@ int sitb_pass_stats_cached(sitb_ctx* ctx, int64_t frame_begin, int64_t n, uint64
  * (invalid configuration) when n_landmarks is too large for the shared-memory tables (> ~9000). */
 int sitb_gram_from_cached(sitb_ctx* ctx, const uint64_t* dev_row_ptr, const uint16_t* dev_pool_k,
                           const double* dev_pool_v, int64_t n_frames, double* dev_gram_upper);
+/* The same Gram, accumulated deterministically: every addend is split into three 64-bit integers (units of 2^-24,
+ * 2^-56, 2^-88; exact for addends >= 2^-36) and added with integer atomics, so the result is the exact sum rounded
+ * once -- independent of the order of addition, bit-identical from run to run, and for every frame sharding whose
+ * boundaries are multiples of the window length (16 frames; windows are aligned to global frame numbers, and the
+ * integer words of the shards are summed before sitb_gram_words_finish converts them).
+ * dev_gram_words: int64 [2 (n_landmarks + 1)][n_landmarks], zeroed by the caller (+=).  Plane 0: upper triangle =
+ * units of 2^-24, lower triangle = units of 2^-56 of the mirrored entry, row n_landmarks = units of 2^-56 of the
+ * diagonal; plane 1: units of 2^-88 at the positions of the 2^-56 words.
+ * sitb_gram_words_finish writes the float64 upper triangle (lower triangle zero) that sitb_landmark_graph reads. */
+int sitb_gram_words_from_cached(sitb_ctx* ctx, const uint64_t* dev_row_ptr, const uint16_t* dev_pool_k,
+                                const double* dev_pool_v, int64_t n_frames, int64_t* dev_gram_words);
+int sitb_gram_words_finish(int device, const int64_t* dev_gram_words, int32_t n_landmarks, double* dev_gram_upper,
+                           void* cuda_stream);
 /* sitb_pass_assign over rows cached by sitb_pass_stats_cached (same outputs, same semantics); row0 = global
  * index of the first row.  The later passes of the clustering plugin (cluster/mcl.py:81-83, :98-122) stream the
  * compressed rows instead of recomputing them. */
@@ -328,6 +341,17 @@ int sitb_seen_sites(int device, const int64_t* dev_traj, int64_t n_entries, int3
                     void* cuda_stream);
 int sitb_relabel_sites(int device, int64_t* dev_traj, int64_t n_entries, int32_t n_sites, const int64_t* dev_translation,
                        void* cuda_stream);
+
+/* Context-free periodic-boundary helpers for the steps after the path (site merging);
+ * host_cellmat = cell^T and its inverse, row major (PBCCalculator.pyx:33-34).
+ * sitb_pbc_distances: PBCCalculator.distances (PBCCalculator.pyx:64-103) of every a_i to every b_j -> dev_out [na][nb].
+ * sitb_pbc_weighted_average: PBCCalculator.average (PBCCalculator.pyx:106-139) of dev_points [n_points][3] under each
+ *   row of dev_weights [n_sets][n_points] (points with weight > 0 take part; centred on the first maximum weight). */
+int sitb_pbc_distances(int device, const double* host_cellmat, const double* host_cellmat_inv, const double* dev_a,
+                       const double* dev_b, int32_t na, int32_t nb, double* dev_out, void* cuda_stream);
+int sitb_pbc_weighted_average(int device, const double* host_cellmat, const double* host_cellmat_inv,
+                              const double* dev_points, const double* dev_weights, int32_t n_sets, int32_t n_points,
+                              double* dev_out, void* cuda_stream);
 
 /* Tensor-core alternative for the landmark Gram (the covariance input of cluster/mcl.py:53).
  * Staging buffers: two zero-filled fp16 arrays of lpad * ld elements (lpad % 128 == 0, ld % 64 == 0) holding the

@@ -52,6 +52,10 @@ MODULES = [
     "sitator/dynamics/JumpAnalysis.py",
     "sitator/dynamics/RemoveUnoccupiedSites.py",
     "sitator/dynamics/SmoothSiteTrajectory.pyx",
+    # site merging by Markov clustering of the jump statistics (pure Python; the package
+    # __init__ of sitator.network pulls in ase calculators, so ref_loader installs a namespace stub for it too)
+    "sitator/dynamics/MergeSitesByDynamics.py",
+    "sitator/network/merging.py",
 ]
 
 

@@ -142,6 +142,19 @@ def load():
     from sitator.dynamics.RemoveUnoccupiedSites import RemoveUnoccupiedSites
     sitator.dynamics.RemoveUnoccupiedSites = RemoveUnoccupiedSites      # what the package __init__ would export
     from sitator.dynamics.SmoothSiteTrajectory import SmoothSiteTrajectory
+    # site merging: namespace stub for sitator.network, the class names the package
+    # __init__ files would export, then the two modules
+    sitator.dynamics.JumpAnalysis = JumpAnalysis
+    if "sitator.network" not in sys.modules:
+        net = types.ModuleType("sitator.network")
+        net.__path__ = [os.path.join(REF_DIR, "sitator", "network")]
+        sys.modules["sitator.network"] = net
+        sitator.network = net
+    try:
+        from sitator.network import merging
+        from sitator.dynamics.MergeSitesByDynamics import MergeSitesByDynamics
+    except ImportError:                       # an oracle/_ref built before these modules were added
+        merging = MergeSitesByDynamics = None
     from sitator import SiteNetwork, SiteTrajectory
     import sitator.errors as errors
     import sitator.landmark.errors as lerrors
@@ -151,7 +164,7 @@ def load():
         cluster_mcl=cluster_mcl, PBCCalculator=PBCCalculator,
         DotProdClassifier=DotProdClassifier, markov_clustering=markov_clustering,
         JumpAnalysis=JumpAnalysis, RemoveUnoccupiedSites=RemoveUnoccupiedSites,
-        SmoothSiteTrajectory=SmoothSiteTrajectory,
+        SmoothSiteTrajectory=SmoothSiteTrajectory, merging=merging, MergeSitesByDynamics=MergeSitesByDynamics,
         SiteNetwork=SiteNetwork, SiteTrajectory=SiteTrajectory,
         errors=errors, landmark_errors=lerrors, Atoms=StubAtoms,
     )

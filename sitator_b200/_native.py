@@ -64,6 +64,8 @@ SIGNATURES = {
     "sitb_pass_stats": (C.c_int, [_P, C.c_int64, C.c_int64, _P, _P]),
     "sitb_pass_stats_cached": (C.c_int, [_P, C.c_int64, C.c_int64, _P, _P, _P, _P, _P, _P, C.c_uint64]),
     "sitb_gram_from_cached": (C.c_int, [_P, _P, _P, _P, C.c_int64, _P]),
+    "sitb_gram_words_from_cached": (C.c_int, [_P, _P, _P, _P, C.c_int64, _P]),
+    "sitb_gram_words_finish": (C.c_int, [C.c_int, _P, C.c_int32, _P, _P]),
     "sitb_assign_sparse": (C.c_int, [_P, _P, _P, _P, C.c_int64, C.c_int64, C.c_double] + [_P] * 7),
     "sitb_relabel_select": (C.c_int, [_P, _P, C.c_int64, _P, _P, _P]),
     "sitb_assign_sparse_rows": (C.c_int, [_P, _P, _P, _P, _P, _P, C.c_int64, C.c_int64, C.c_double] + [_P] * 7),
@@ -98,6 +100,8 @@ SIGNATURES = {
                                      C.c_int64, _P, C.c_int64, _P, _P]),
     "sitb_seen_sites": (C.c_int, [C.c_int, _P, C.c_int64, C.c_int32, _P, _P]),
     "sitb_relabel_sites": (C.c_int, [C.c_int, _P, C.c_int64, C.c_int32, _P, _P]),
+    "sitb_pbc_distances": (C.c_int, [C.c_int, _P, _P, _P, _P, C.c_int32, C.c_int32, _P, _P]),
+    "sitb_pbc_weighted_average": (C.c_int, [C.c_int, _P, _P, _P, _P, C.c_int32, C.c_int32, _P, _P]),
     "sitb_upload_chunk_frames": (C.c_int, [_P, C.POINTER(C.c_int64)]),
     "sitb_pass_stage": (C.c_int, [_P, C.c_int64, C.c_int64, _P, _P, _P, C.c_int64]),
     "sitb_gram_syrk_tc": (C.c_int, [C.c_int, _P, _P, C.c_int32, C.c_int32, C.c_int64, C.c_int64, _P, _P]),

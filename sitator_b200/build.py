@@ -36,7 +36,8 @@ def build_native(force=False, verbose=False, extra_flags=()):
         return LIB
     nvcc = os.environ.get("NVCC", "nvcc")
     os.makedirs(os.path.dirname(LIB), exist_ok=True)
-    cmd = [nvcc] + NVCC_FLAGS + list(extra_flags) + ["-o", LIB] + sources()
+    extra_flags = list(extra_flags) + os.environ.get("SITB_NVCC_FLAGS", "").split()      # developer experiments (-DSITB_...)
+    cmd = [nvcc] + NVCC_FLAGS + extra_flags + ["-o", LIB] + sources()
     if verbose:
         print(" ".join(cmd))
     subprocess.check_call(cmd)

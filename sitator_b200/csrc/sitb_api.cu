@@ -191,7 +191,7 @@ extern "C" int sitb_create(const sitb_network_desc* d, int device, sitb_ctx** ou
     *out = nullptr;
     if (d->n_atoms <= 0 || d->n_static <= 0 || d->n_mobile <= 0 || d->n_landmarks <= 0 || d->max_verts <= 0)
         return fail(SITB_E_INVALID, "sitb_create: sizes must be positive");
-    if (d->max_verts > 8) return fail(SITB_E_LIMIT, "sitb_create: max_verts %d > 8", d->max_verts);
+    if (d->max_verts > MAX_VERTS) return fail(SITB_E_LIMIT, "sitb_create: max_verts %d > %d", d->max_verts, MAX_VERTS);
     if (d->n_static >= 65535) return fail(SITB_E_LIMIT, "sitb_create: n_static %d >= 65535", d->n_static);
     if (d->n_landmarks >= 65535) return fail(SITB_E_LIMIT, "sitb_create: n_landmarks %d >= 65535", d->n_landmarks);
     if (!d->host_cellmat || !d->host_static_idx || !d->host_mobile_idx || !d->host_ideal_static ||
@@ -1017,7 +1017,8 @@ extern "C" int sitb_assign_sparse_rows(sitb_ctx* c, const uint64_t* dev_row_ptr,
 // ---- Gram from the cached rows (sitb_gram_sparse.cu) -------------------------------------------------
 namespace sitb {
 cudaError_t launch_gram_sparse(const unsigned long long* row_ptr, const uint16_t* pk, const double* pv, long long n_frames,
-                               int M, int L, double* gram, int n_sms, cudaStream_t st);
+                               int M, int L, double* gram, int n_sms, cudaStream_t st, int exact, long long frame0);
+cudaError_t launch_gram_words_finish(const long long* words, int L, double* out, cudaStream_t st);
 }
 extern "C" int sitb_gram_from_cached(sitb_ctx* c, const uint64_t* dev_row_ptr, const uint16_t* dev_pool_k,
                                      const double* dev_pool_v, int64_t n_frames, double* dev_gram) {
@@ -1025,7 +1026,25 @@ extern "C" int sitb_gram_from_cached(sitb_ctx* c, const uint64_t* dev_row_ptr, c
         return fail(SITB_E_INVALID, "sitb_gram_from_cached: bad argument");
     CK(cudaSetDevice(c->device));
     CK(launch_gram_sparse((const unsigned long long*)dev_row_ptr, dev_pool_k, dev_pool_v, n_frames, c->M, c->L, dev_gram,
-                          c->n_sms, c->stream));
+                          c->n_sms, c->stream, 0, 0));
+    return SITB_OK;
+}
+
+extern "C" int sitb_gram_words_from_cached(sitb_ctx* c, const uint64_t* dev_row_ptr, const uint16_t* dev_pool_k,
+                                           const double* dev_pool_v, int64_t n_frames, int64_t* dev_gram_words) {
+    if (!c || !dev_row_ptr || !dev_pool_k || !dev_pool_v || !dev_gram_words || n_frames < 0)
+        return fail(SITB_E_INVALID, "sitb_gram_words_from_cached: bad argument");
+    CK(cudaSetDevice(c->device));
+    CK(launch_gram_sparse((const unsigned long long*)dev_row_ptr, dev_pool_k, dev_pool_v, n_frames, c->M, c->L,
+                          (double*)dev_gram_words, c->n_sms, c->stream, 1, c->frame0));
+    return SITB_OK;
+}
+
+extern "C" int sitb_gram_words_finish(int device, const int64_t* dev_gram_words, int32_t n_landmarks, double* dev_gram_upper,
+                                      void* cuda_stream) {
+    if (!dev_gram_words || !dev_gram_upper || n_landmarks <= 0) return fail(SITB_E_INVALID, "sitb_gram_words_finish: bad argument");
+    CK(cudaSetDevice(device));
+    CK(launch_gram_words_finish((const long long*)dev_gram_words, n_landmarks, dev_gram_upper, (cudaStream_t)cuda_stream));
     return SITB_OK;
 }
 

@@ -135,18 +135,23 @@ __device__ __forceinline__ double sqrt_bounded(double q) {
     return fma(fma(-g, g, q), h, g);
 }
 
-// P^(-1/n) for 1 <= P < 3e38, 1 <= n <= 8: float seed, two Newton steps on y^-n = P (same code for every n)
+// P^(-1/n) for 1 <= P < 1e300, 1 <= n <= 16: float seed from the exponent and the mantissa's log2 (P itself can exceed
+// the float range with more than nine vertices), two Newton steps on y^-n = P (same code for every n)
 __device__ __forceinline__ double inv_root(double P, int n) {
     const float rn = __fdividef(1.0f, (float)n);     // approximate is enough: it only scales the Newton step
-    double y = (double)ex2_approx(-lg2_approx((float)P) * rn);
+    const int hi = __double2hiint(P);
+    const float l2 = (float)((hi >> 20) - 1023) +
+                     lg2_approx((float)__hiloint2double((hi & 0x000FFFFF) | 0x3FF00000, __double2loint(P)));
+    double y = (double)ex2_approx(-l2 * rn);
     const double rnd = (double)rn;
 #pragma unroll
     for (int it = 0; it < 2; ++it) {
-        const double y2 = y * y, y4 = y2 * y2;
+        const double y2 = y * y, y4 = y2 * y2, y8 = y4 * y4;
         double t = (n & 1) ? y : 1.0;
         if (n & 2) t *= y2;
         if (n & 4) t *= y4;
-        if (n & 8) t = y4 * y4;
+        if (n & 8) t *= y8;
+        if (n & 16) t *= y8 * y8;
         y = fma(y * fma(-P, t, 1.0), rnd, y);
     }
     return y;
@@ -532,7 +537,8 @@ __global__ void __launch_bounds__(DIAG ? SITB_K1_WARPS * 32 : 512) k_fill(const 
                 if (active == 0u) break;
                 }
             }
-            if (nsurv > ENTRY_CAP) { if (lane == 0) ++loc_over; nsurv = ENTRY_CAP; }
+            bool over = nsurv > ENTRY_CAP;
+            if (over) nsurv = ENTRY_CAP;
 
             // 3d. exact test + value for the survivors (in-place: ek[i] -> ek[pos], ev[pos], pos <= i)
             int nent = 0;
@@ -576,6 +582,8 @@ __global__ void __launch_bounds__(DIAG ? SITB_K1_WARPS * 32 : 512) k_fill(const 
                 nent += __popc(m);
             }
             __syncwarp();
+            if (nent > 255) { over = true; nent = 255; }          // 8-bit entry count of a compressed row
+            if (over && lane == 0) ++loc_over;
             if (lane == 0) {
                 loc_nnz += (unsigned long long)nent;
                 if (nent == 0) {
@@ -596,6 +604,16 @@ __global__ void __launch_bounds__(DIAG ? SITB_K1_WARPS * 32 : 512) k_fill(const 
                     double mypr[1] = {0.0};
                     if (lane < nent) { const int k = ek[lane]; myc[0] = tcid[k]; mypr[0] = ev[lane] * tcw[k]; }
                     peel_clusters<1>(myc, mypr, lane, p.best, p.n_clusters, row_global, bestc, bestid);
+                } else if (nent <= 128) {
+                    int myc[4];
+                    double mypr[4];
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) {
+                        const int e = 32 * c + lane;
+                        myc[c] = -1; mypr[c] = 0.0;
+                        if (e < nent) { const int k = ek[e]; myc[c] = tcid[k]; mypr[c] = ev[e] * tcw[k]; }
+                    }
+                    peel_clusters<4>(myc, mypr, lane, p.best, p.n_clusters, row_global, bestc, bestid);
                 } else {
                     int myc[ENTRY_CAP / 32];
                     double mypr[ENTRY_CAP / 32];

@@ -14,9 +14,10 @@ enum FillMode : int {
     MODE_ASSIGN = 3,  // centre similarity, threshold, argmax (+ optional reductions)
 };
 
-static constexpr int ENTRY_CAP = 128;        // non-zero components kept per landmark vector
+static constexpr int ENTRY_CAP = 256;        // survivors of the float screen kept per landmark vector; a compressed row holds
+                                             // at most 255 entries (8-bit count), more is reported as n_list_overflow
 static constexpr int CAND_CAP = 512;         // landmarks screened per block (= candidate list capacity)
-static constexpr int MAX_VERTS = 8;
+static constexpr int MAX_VERTS = 16;
 
 // counters[] slots
 enum : int { CNT_ZERO_ROWS = 0, CNT_DUP_NEAREST = 1, CNT_LIST_OVERFLOW = 2, CNT_NNZ = 3,

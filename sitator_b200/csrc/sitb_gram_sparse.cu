@@ -12,17 +12,57 @@
 //        ~35 atomics per row instead of 253, and ~50 instructions per row instead of ~300
 //   windows whose union exceeds GW_CAP slots (an atom in transit through many sites) add directly.
 // The sums are the same FP64 products in a different association; G is exact to rounding either way.
+//
+// Deterministic accumulation (EXACT = true, the default of the clustering plugin): FP64 atomics add in arrival
+// order, so two runs differed in the last bits of G.  Here every addend (a window's tile entry, or a single pair
+// product on the direct path) is split into THREE 64-bit integers -- units of 2^-24, 2^-56 and 2^-88 -- and added
+// with integer atomics.  An FP64 addend >= 2^-36 is represented exactly (addends below that are rounded to 2^-88),
+// and integer addition is associative: G is the exact sum of the addends, rounded once at the end, bit-identical
+// from run to run and, with the windows aligned to GLOBAL frame numbers, for every sharding whose boundaries are
+// multiples of GW_T frames (the integer words are all-reduced before they are converted).  The third word is
+// touched only by addends with bits below 2^-56 (addends < 2^-4).  Layout of the word matrix
+// long long[2 (L + 1)][L]: plane 0: upper triangle = the 2^-24 words, lower triangle = the 2^-56 words of the
+// mirrored entry, row L = the 2^-56 words of the diagonal; plane 1, same positions as the 2^-56 words: the 2^-88 words.
 #include "../../include/sitator_b200.h"
 #include "sitb_common.cuh"
 
 namespace sitb {
 
-constexpr int GW_T = 16;         // frames per window = K of the local product (4 mma k-steps)
+#ifndef SITB_GW_T
+#define SITB_GW_T 16
+#endif
+#ifndef SITB_GW_WARPS
+#define SITB_GW_WARPS 14
+#endif
+constexpr int GW_T = SITB_GW_T;  // frames per window = K of the local product (mma k-steps of 4)
 constexpr int GW_CAP = 48;       // landmark slots per window (6 tiles of 8)
 constexpr int GW_STRIDE = 52;    // row stride of X in doubles: = 4 mod 16, so the 4 x 8 fragment loads are conflict-free
-constexpr int GW_WARPS = 14;     // warps per CTA (two CTAs per SM)
+constexpr int GW_WARPS = SITB_GW_WARPS;   // warps per CTA (two CTAs per SM; X is GW_T x GW_STRIDE doubles per warp)
 constexpr int GW_NT = GW_CAP / 8;
 
+// add x >= 0 to entry (r <= c): FP64 atomic, or the two integer words described above
+template <bool EXACT>
+__device__ __forceinline__ void gram_add(double* __restrict__ gram, int L, unsigned r, unsigned c, double x) {
+    if (!EXACT) {
+        atomicAdd(&gram[(size_t)r * L + c], x);
+    } else {
+        unsigned long long* w = (unsigned long long*)gram;
+        const size_t plane = (size_t)(L + 1) * L;
+        const double s = x * 16777216.0;                        // 2^24: exact
+        const double h = floor(s);
+        const double s2 = (s - h) * 4294967296.0;               // 2^32: exact
+        const double m = floor(s2);
+        const unsigned long long hi = (unsigned long long)(long long)h;
+        const unsigned long long mid = (unsigned long long)(long long)m;
+        const unsigned long long lo = (unsigned long long)__double2ll_rn((s2 - m) * 4294967296.0);   // grid 2^-88
+        const size_t at = (r == c) ? ((size_t)L * L + r) : ((size_t)c * L + r);
+        if (hi) atomicAdd(&w[(size_t)r * L + c], hi);
+        if (mid) atomicAdd(&w[at], mid);
+        if (lo) atomicAdd(&w[plane + at], lo);
+    }
+}
+
+template <bool EXACT>
 __device__ __forceinline__ void gram_row_direct(const uint16_t* __restrict__ pk, const double* __restrict__ pv,
                                                 unsigned long long off, int n, int lane, int L,
                                                 double* __restrict__ gram) {
@@ -32,7 +72,7 @@ __device__ __forceinline__ void gram_row_direct(const uint16_t* __restrict__ pk,
         for (int b = a + lane; b < n; b += 32) {
             const unsigned kb = pk[off + b];
             const unsigned lo = ka < kb ? ka : kb, hi = ka < kb ? kb : ka;
-            atomicAdd(&gram[(size_t)lo * L + hi], va * pv[off + b]);
+            gram_add<EXACT>(gram, L, lo, hi, va * pv[off + b]);
         }
     }
 }
@@ -47,10 +87,13 @@ __host__ __device__ inline size_t gram_warp_bytes(int words) {
     return ((sizeof(double) * GW_T * GW_STRIDE + 4 * (size_t)words + 2 * (size_t)words + 2 * GW_CAP) + 15) & ~(size_t)15;
 }
 
+template <bool EXACT>
 __global__ void __launch_bounds__(GW_WARPS * 32, 2)
 k_gram_windows(const unsigned long long* __restrict__ row_ptr, const uint16_t* __restrict__ pk,
                const double* __restrict__ pv, long long n_frames, int M, int L, int words,
-               double* __restrict__ gram) {
+               double* __restrict__ gram, int lead) {
+    // lead: frames before the first multiple of GW_T in GLOBAL frame numbers (windows are aligned to those, so that
+    // a window holds the same frames however the trajectory is sharded); 0 = the shard starts on a boundary
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     // per warp: X [GW_T][GW_STRIDE] f64 | bitmap [words] u32 | slot offset of each word [words] u16 | ids [GW_CAP] u16
@@ -61,12 +104,16 @@ k_gram_windows(const unsigned long long* __restrict__ row_ptr, const uint16_t* _
     uint16_t* ids = wofs + words;
     const int r4 = lane & 3, c8 = lane >> 2;
 
-    const long long n_windows = (n_frames + GW_T - 1) / GW_T;
+    const long long shift = lead ? (GW_T - lead) : 0;             // window w covers local frames [w GW_T - shift, ...)
+    const long long n_windows = (n_frames + shift + GW_T - 1) / GW_T;
     const long long n_tasks = n_windows * M;
     for (long long t = (long long)blockIdx.x * GW_WARPS + warp; t < n_tasks; t += (long long)gridDim.x * GW_WARPS) {
         const int j = (int)(t % M);
-        const long long f0 = (t / M) * GW_T;
-        const int nf = (int)((n_frames - f0 < GW_T) ? (n_frames - f0) : GW_T);
+        long long f0 = (t / M) * GW_T - shift;
+        long long f1 = f0 + GW_T;
+        if (f0 < 0) f0 = 0;
+        if (f1 > n_frames) f1 = n_frames;
+        const int nf = (int)(f1 - f0);
         // lane i holds row i of the window
         unsigned long long my_off = 0;
         int my_n = 0;
@@ -118,7 +165,7 @@ k_gram_windows(const unsigned long long* __restrict__ row_ptr, const uint16_t* _
         __syncwarp();
         if (u > GW_CAP) {
             for (int i = 0; i < nf; ++i)
-                gram_row_direct(pk, pv, __shfl_sync(0xffffffffu, my_off, i), __shfl_sync(0xffffffffu, my_n, i), lane, L, gram);
+                gram_row_direct<EXACT>(pk, pv, __shfl_sync(0xffffffffu, my_off, i), __shfl_sync(0xffffffffu, my_n, i), lane, L, gram);
             continue;
         }
         for (int w = lane; w < words; w += 32) {
@@ -164,14 +211,13 @@ k_gram_windows(const unsigned long long* __restrict__ row_ptr, const uint16_t* _
             }
             const int r = ti * 8 + c8;                    // accumulator row (slot)
             if (r < u) {
-                const size_t ra = (size_t)ids[r] * L;
 #pragma unroll
                 for (int d = 0; d < GW_NT; ++d) {
                     if (ti + d >= nt) break;
 #pragma unroll
                     for (int q = 0; q < 2; ++q) {
                         const int c = (ti + d) * 8 + r4 * 2 + q;
-                        if (c < u && c >= r && acc[d][q] != 0.0) atomicAdd(&gram[ra + ids[c]], acc[d][q]);
+                        if (c < u && c >= r && acc[d][q] != 0.0) gram_add<EXACT>(gram, L, ids[r], ids[c], acc[d][q]);
                     }
                 }
             }
@@ -180,15 +226,53 @@ k_gram_windows(const unsigned long long* __restrict__ row_ptr, const uint16_t* _
     }
 }
 
+// exact = 0: gram is double[L][L] (upper triangle, FP64 atomics).  exact = 1: gram is the word matrix long long[(L+1)][L]
+// (see the top of this file), windows aligned to global frame numbers (frame0 = global index of the first cached frame).
 cudaError_t launch_gram_sparse(const unsigned long long* row_ptr, const uint16_t* pk, const double* pv, long long n_frames,
-                               int M, int L, double* gram, int n_sms, cudaStream_t st) {
+                               int M, int L, double* gram, int n_sms, cudaStream_t st, int exact, long long frame0) {
     if (n_frames <= 0) return cudaSuccess;
     const int words = (L + 31) / 32;
     const size_t smem = gram_warp_bytes(words) * GW_WARPS;
     if (smem > 110 * 1024) return cudaErrorInvalidConfiguration;      // L > ~9000: the caller keeps the in-kernel Gram
-    cudaError_t e = cudaFuncSetAttribute(k_gram_windows, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    k_gram_windows<<<n_sms * 2, GW_WARPS * 32, smem, st>>>(row_ptr, pk, pv, n_frames, M, L, words, gram);
+    const int lead = exact ? (int)((GW_T - (frame0 % GW_T)) % GW_T) : 0;
+    cudaError_t e;
+    if (exact) {
+        e = cudaFuncSetAttribute(k_gram_windows<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        k_gram_windows<true><<<n_sms * 2, GW_WARPS * 32, smem, st>>>(row_ptr, pk, pv, n_frames, M, L, words, gram, lead);
+    } else {
+        e = cudaFuncSetAttribute(k_gram_windows<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        k_gram_windows<false><<<n_sms * 2, GW_WARPS * 32, smem, st>>>(row_ptr, pk, pv, n_frames, M, L, words, gram, 0);
+    }
+    return cudaGetLastError();
+}
+
+// word matrix -> double[L][L] upper triangle (lower triangle zero): value = hi 2^-24 + lo 2^-56, one rounding
+__global__ void k_gram_words_finish(const long long* __restrict__ w, int L, double* __restrict__ out) {
+    const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (size_t)L * L) return;
+    const int r = (int)(idx / L), c = (int)(idx % L);
+    double v = 0.0;
+    if (c >= r) {
+        const size_t plane = (size_t)(L + 1) * L;
+        const size_t at = (r == c) ? ((size_t)L * L + r) : ((size_t)c * L + r);
+        const unsigned long long hi = (unsigned long long)w[(size_t)r * L + c];
+        const unsigned long long mid = (unsigned long long)w[at];
+        const unsigned long long lo = (unsigned long long)w[plane + at];
+        // the exact sum is (hi 2^64 + mid 2^32 + lo) 2^-88: assemble it as a 128-bit integer (hi < 2^56 by the row
+        // limit, so hi 2^64 needs care: keep hi's top part separate), convert the pieces and add from small to large
+        const unsigned __int128 low = ((unsigned __int128)mid << 32) + (unsigned __int128)lo;     // < 2^97
+        const unsigned long long carry = (unsigned long long)(low >> 64);                          // units of 2^-24
+        const unsigned long long rest = (unsigned long long)low;                                   // units of 2^-88
+        v = ldexp((double)rest, -88) + ldexp((double)(hi + carry), -24);
+    }
+    out[idx] = v;
+}
+
+cudaError_t launch_gram_words_finish(const long long* words, int L, double* out, cudaStream_t st) {
+    const size_t cnt = (size_t)L * L;
+    k_gram_words_finish<<<(unsigned)((cnt + 255) / 256), 256, 0, st>>>(words, L, out);
     return cudaGetLastError();
 }
 

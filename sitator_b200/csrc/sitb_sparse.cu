@@ -269,6 +269,9 @@ __global__ void __launch_bounds__(128) k_assign_sparse(
             if (n <= 32)
                 assign_row<1>(rh, n, off, lane, k0, v0, pk, pv, row0, L, cid, cw, thr, labels, confs, counts, hist,
                               best_scratch, wb, rep, rep_w, site_scratch, ws);
+            else if (n <= 128)
+                assign_row<4>(rh, n, off, lane, k0, v0, pk, pv, row0, L, cid, cw, thr, labels, confs,
+                              counts, hist, best_scratch, wb, rep, rep_w, site_scratch, ws);
             else
                 assign_row<ENTRY_CAP / 32>(rh, n, off, lane, k0, v0, pk, pv, row0, L, cid, cw, thr, labels, confs,
                                            counts, hist, best_scratch, wb, rep, rep_w, site_scratch, ws);

@@ -26,13 +26,16 @@ int set_error(int code, const char* fmt, ...);
 __global__ void k_occupancy(const long long* __restrict__ traj, long long F, int M, long long frame0,
                             int max_per_site, unsigned long long* __restrict__ out,
                             unsigned long long* __restrict__ first_bad) {
-    extern __shared__ long long row[];
+    extern __shared__ int row[];               // site ids fit 32 bits (sitb_set_centers: < 32768 sites)
     unsigned long long n_more = 0, n_assigned = 0, n_distinct = 0;
     for (long long f = blockIdx.x; f < F; f += gridDim.x) {
-        for (int a = threadIdx.x; a < M; a += blockDim.x) row[a] = traj[f * M + a];
+        for (int a = threadIdx.x; a < M; a += blockDim.x) {
+            const long long v = traj[f * M + a];
+            row[a] = v < 0 ? -1 : (int)v;
+        }
         __syncthreads();
         for (int a = threadIdx.x; a < M; a += blockDim.x) {
-            const long long s = row[a];
+            const int s = row[a];
             if (s < 0) continue;
             int cnt = 0;
             bool first = true;
@@ -419,7 +422,11 @@ extern "C" int sitb_check_multiple_occupancy(int device, const int64_t* dev_traj
         return set_error(SITB_E_INVALID, "sitb_check_multiple_occupancy: bad argument");
     CKT(cudaSetDevice(device));
     long long grid = n_frames < 148 * 8 ? n_frames : 148 * 8;
-    k_occupancy<<<(unsigned)grid, 128, sizeof(long long) * n_mobile, (cudaStream_t)cuda_stream>>>(
+    const size_t occ_smem = sizeof(int) * (size_t)n_mobile;
+    if (occ_smem > 200 * 1024) return set_error(SITB_E_LIMIT, "sitb_check_multiple_occupancy: %d mobile atoms (limit 51200)", n_mobile);
+    if (occ_smem > 48 * 1024)
+        CKT(cudaFuncSetAttribute(k_occupancy, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)occ_smem));
+    k_occupancy<<<(unsigned)grid, 128, occ_smem, (cudaStream_t)cuda_stream>>>(
         (const long long*)dev_traj, n_frames, n_mobile, frame0, max_mobile_per_site,
         (unsigned long long*)dev_out3, (unsigned long long*)dev_first_bad);
     CKT(cudaGetLastError());
@@ -628,4 +635,54 @@ cudaError_t launch_weighted_point_average(const Cell& cell, const double* pts, c
     return cudaGetLastError();
 }
 
+// PBCCalculator.distances (PBCCalculator.pyx:64-103) for every (a_i, b_j): shift so that a_i sits on the cell centroid,
+// wrap, distance to the centroid
+__global__ void k_pbc_distances(Cell cell, const double* __restrict__ a, const double* __restrict__ b, int na, int nb,
+                                double* __restrict__ out) {
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (long long)na * nb) return;
+    const int i = (int)(idx / nb), j = (int)(idx % nb);
+    const double ox = __dsub_rn(cell.cen[0], a[3 * i]), oy = __dsub_rn(cell.cen[1], a[3 * i + 1]), oz = __dsub_rn(cell.cen[2], a[3 * i + 2]);
+    const double q = cell.diag ? shifted_dist2<true, false>(cell, b[3 * j], b[3 * j + 1], b[3 * j + 2], ox, oy, oz)
+                               : shifted_dist2<false, false>(cell, b[3 * j], b[3 * j + 1], b[3 * j + 2], ox, oy, oz);
+    out[idx] = __dsqrt_rn(q);
+}
+
+// the cell block of a context-free call: cellmat = cell^T and its inverse, row major, as PBCCalculator.__init__ builds them
+static Cell cell_from_host(const double* cellmat, const double* cellmat_inv) {
+    Cell c;
+    for (int i = 0; i < 9; ++i) { c.c[i] = cellmat[i]; c.ci[i] = cellmat_inv[i]; }
+    for (int k = 0; k < 3; ++k) c.cen[k] = (0.5 * c.c[3 * k + 0] + 0.5 * c.c[3 * k + 1]) + 0.5 * c.c[3 * k + 2];
+    bool diag = true;
+    for (int i = 0; i < 3; ++i)
+        for (int j = 0; j < 3; ++j)
+            if (i != j && (c.c[3 * i + j] != 0.0 || c.ci[3 * i + j] != 0.0)) diag = false;
+    c.diag = diag ? 1 : 0;
+    return c;
+}
+
 }  // namespace sitb
+
+extern "C" int sitb_pbc_distances(int device, const double* host_cellmat, const double* host_cellmat_inv, const double* dev_a,
+                                  const double* dev_b, int32_t na, int32_t nb, double* dev_out, void* cuda_stream) {
+    if (!host_cellmat || !host_cellmat_inv || !dev_a || !dev_b || !dev_out || na <= 0 || nb <= 0)
+        return sitb::set_error(SITB_E_INVALID, "sitb_pbc_distances: bad argument");
+    CKT(cudaSetDevice(device));
+    const long long n = (long long)na * nb;
+    sitb::k_pbc_distances<<<(unsigned)((n + 127) / 128), 128, 0, (cudaStream_t)cuda_stream>>>(
+        sitb::cell_from_host(host_cellmat, host_cellmat_inv), dev_a, dev_b, na, nb, dev_out);
+    CKT(cudaGetLastError());
+    return SITB_OK;
+}
+
+extern "C" int sitb_pbc_weighted_average(int device, const double* host_cellmat, const double* host_cellmat_inv,
+                                         const double* dev_points, const double* dev_weights, int32_t n_sets, int32_t n_points,
+                                         double* dev_out, void* cuda_stream) {
+    if (!host_cellmat || !host_cellmat_inv || !dev_points || !dev_weights || !dev_out || n_sets <= 0 || n_points <= 0)
+        return sitb::set_error(SITB_E_INVALID, "sitb_pbc_weighted_average: bad argument");
+    CKT(cudaSetDevice(device));
+    CKT(sitb::launch_weighted_point_average(sitb::cell_from_host(host_cellmat, host_cellmat_inv), dev_points, dev_weights, n_sets,
+                                            n_points, dev_out, (cudaStream_t)cuda_stream));
+    return SITB_OK;
+}
+

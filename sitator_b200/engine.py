@@ -292,7 +292,17 @@ class LandmarkEngine(object):
                                                       C.c_void_p(stream)))
         return seen, gram
 
-    def pass_stats_cached(self, seen=None, gram=None, entries_per_row=40, gram_from_rows=None, want_gram=True):
+    def gram_words_finish(self, words):
+        """Deterministic Gram: the integer word matrix (2 (L + 1), L) -> float64 (L, L) upper triangle."""
+        torch = _torch()
+        out = self._empty((self.L, self.L), torch.float64)
+        stream = torch.cuda.current_stream(self.device).cuda_stream
+        _native.check(self._lib.sitb_gram_words_finish(self.device.index, self._ptr(words), self.L, self._ptr(out),
+                                                       C.c_void_p(stream)))
+        return out
+
+    def pass_stats_cached(self, seen=None, gram=None, entries_per_row=40, gram_from_rows=None, want_gram=True,
+                          gram_words=False):
         """Pass A that also caches every landmark vector compressed (SparseRows); grows the pool on overflow.
         ``gram_from_rows`` (default: whenever the shared-memory tables fit, L <= 8192): build the Gram from the
         cached rows per (atom, window of frames) instead of with one atomic per pair product inside K1."""
@@ -304,8 +314,10 @@ class LandmarkEngine(object):
         n_rows = self.n_frames * self.M
         if seen is None:
             seen = self._zeros((self.L,), torch.int64)
+        gram_words = bool(gram_words and gram_from_rows and want_gram)
         if gram is None and want_gram:
-            gram = self._zeros((self.L, self.L), torch.float64)
+            # gram_words: the deterministic integer form (sitb_gram_words_from_cached), finished by gram_words_finish
+            gram = self._zeros((2 * (self.L + 1), self.L), torch.int64) if gram_words else self._zeros((self.L, self.L), torch.float64)
         while True:
             # (warps reserve the pool in slices of 256 entries and leave the tail of a slice unused at the end of a launch)
             step = self.upload_chunk_frames() or self.n_frames
@@ -329,8 +341,9 @@ class LandmarkEngine(object):
                 if not want_gram:
                     pass
                 elif gram_from_rows:
-                    _native.check(self._lib.sitb_gram_from_cached(self._ctx, self._ptr(rows.ptr), self._ptr(rows.k),
-                                                                  self._ptr(rows.v), self.n_frames, self._ptr(gram)))
+                    fn = self._lib.sitb_gram_words_from_cached if gram_words else self._lib.sitb_gram_from_cached
+                    _native.check(fn(self._ctx, self._ptr(rows.ptr), self._ptr(rows.k), self._ptr(rows.v), self.n_frames,
+                                     self._ptr(gram)))
                 else:
                     gram.copy_(gram_try)
                 rows.used = used

@@ -162,6 +162,14 @@ class LandmarkAnalysis(object):
             raise ZeroLandmarkError(mobile_index=index, frame=frame)
 
     def run(self, sn, frames):
+        """Run the landmark analysis (see :meth:`_run`); every device allocation and launch happens on ``device``."""
+        import torch
+        if self._device is None:
+            return self._run(sn, frames)
+        with torch.cuda.device(int(self._device)):      # helpers that allocate on "cuda" follow the analysis' device
+            return self._run(sn, frames)
+
+    def _run(self, sn, frames):
         """Run the landmark analysis.
 
         Args:
@@ -246,9 +254,11 @@ class LandmarkAnalysis(object):
         with timer.phase("status + first error (collective)"):
             status = engine.status()
             self._raise_first_error(status, comm, engine)
-        if status.n_list_overflow:
-            raise RuntimeError("%d landmark vectors have more than 128 non-zero components; "
-                               "the device lists would truncate them" % status.n_list_overflow)
+        n_overflow = status.n_list_overflow if comm is None else comm.allreduce_sum_scalar(status.n_list_overflow)
+        if n_overflow:          # (reduced over the ranks first: every rank raises, none is left waiting in a collective)
+            raise RuntimeError("%d landmark vectors have more than %d candidate components after the FP32 screen; the "
+                               "per-warp lists of the fill kernel would truncate them (a very wide or soft cut-off on a "
+                               "dense lattice: lower cutoff_midpoint or raise cutoff_steepness)" % (n_overflow, 255))
         self.n_all_zero_lvecs = status.n_zero_rows if comm is None else comm.allreduce_sum_scalar(status.n_zero_rows)
         if status.n_duplicate_nearest:
             logger.warning("%i times a static atom was the closest to more than one static lattice position"

@@ -75,15 +75,16 @@ def principal_vectors(blocks):
 def landmark_graph(source, gram_method='sparse'):
     """Pass A + mcl.py:53-59.  Returns (seen (L,) int64 numpy, cov (L,L) numpy, graph torch tensor).
 
-    ``gram_method``: ``'sparse'`` (default) accumulates the Gram exactly in FP64 from the ~1.5 % dense rows and
-    caches them; ``'tcgen05'`` runs it as a dense SYRK on the tensor cores (fp16 hi/lo operands, FP32 TMEM
+    ``gram_method``: ``'sparse'`` (default) accumulates the Gram in FP64 products from the ~1.5 % dense rows, added
+    as integers so that the result is independent of the order of addition (``'sparse_atomic'``: FP64 atomics), and
+    caches the rows; ``'tcgen05'`` runs it as a dense SYRK on the tensor cores (fp16 hi/lo operands, FP32 TMEM
     accumulators drained to FP64; agrees to ~1e-6, see tests/test_gram_tc_gpu.py) and leaves passes B-D to the
     fused fill+assign kernel."""
     import torch
     eng = source.engine
     lib = _native.load()
-    if gram_method not in ('sparse', 'tcgen05'):
-        raise ValueError("gram_method must be 'sparse' or 'tcgen05', not %r" % (gram_method,))
+    if gram_method not in ('sparse', 'sparse_atomic', 'tcgen05'):
+        raise ValueError("gram_method must be 'sparse', 'sparse_atomic' or 'tcgen05', not %r" % (gram_method,))
     if source.gram_upper is None:
         # keep the rows compressed for the later passes when they fit comfortably (~400 B per row)
         # (torch's cached totals, not cudaMemGetInfo: that driver query can take tens of milliseconds)
@@ -92,12 +93,16 @@ def landmark_graph(source, gram_method='sparse'):
         if gram_method == 'tcgen05':
             seen, gram = eng.pass_stats_tc()
         elif source.cache_rows and source.n_local * 420 < 0.5 * free_bytes:
-            seen, gram, source.sparse = eng.pass_stats_cached()
+            # 'sparse': deterministic integer accumulation (order independent: equal for every run and sharding);
+            # 'sparse_atomic': FP64 atomics (round 1)
+            seen, gram, source.sparse = eng.pass_stats_cached(gram_words=(gram_method == 'sparse'))
         else:
             seen, gram = eng.pass_stats()
         if source.comm is not None:
             source.comm.allreduce_sum_(seen)
-            source.comm.allreduce_sum_(gram)
+            source.comm.allreduce_sum_(gram)               # integer words when deterministic: the sum is exact
+        if gram.dtype == torch.int64:
+            gram = eng.gram_words_finish(gram)
         source.seen, source.gram_upper = seen, gram
         source.gram_method = gram_method
     L = eng.L

@@ -183,3 +183,47 @@ def dotprod_param_cases():
         "toy_tight": ("toy_bcc_300_dotprod", {"clustering_threshold": 0.7, "assignment_threshold": 0.9}, 0.1),
         "llzo_tight": ("llzo_60_dotprod", {"clustering_threshold": 0.6, "assignment_threshold": 0.85}, 0.05),
     }
+
+
+MERGE_CASES = {
+    # case: (golden input, distance_threshold, post_check_thresh_factor, markov_parameters, weighted_spatial_average)
+    "toy_default": ("toy_bcc_2000", 2.0, 1.5, {}, True),
+    "toy_inflation": ("toy_bcc_2000", 3.4, 3.0, {"inflation": 1.25, "expansion": 2}, False),
+    "llzo_loose": ("llzo_60", 3.0, 3.0, {"inflation": 1.4}, True),
+    # atoms flicker between the members of eight close site pairs every few frames: strong i <-> j flux, pairs merge
+    "toy_flicker": ("toy_bcc_2000+flicker", 3.0, 2.0, {}, True),
+}
+
+
+def merge_case_inputs(gname):
+    """Inputs of the site-merging fixtures: a golden's SiteTrajectory without the sites that never hold an atom for
+    two consecutive frames (their n_ii = 0, which the reference's markov_clustering refuses, util/mcl.py:20).
+    Returns (system, frames, labels (F, M), confidences, site centres, site vertex lists)."""
+    flicker = gname.endswith("+flicker")
+    gname = gname.split("+")[0]
+    g, system, cfg, frames = load_golden(gname)
+    keep = np.diag(g["n_ij"]) != 0
+    remap = np.full(len(keep) + 1, -1, dtype=np.int64)
+    remap[:-1][keep] = np.arange(int(keep.sum()))
+    labels = remap[g["labels"].astype(np.int64)]
+    confs = np.where(labels >= 0, g["confs"], 0.0)
+    verts = [sorted(v) for v, k in zip(g["site_vertex_sets"], keep) if k]
+    centers = g["site_centers"][keep].copy()
+    if flicker:
+        from oracle import landmark_oracle as orc
+        pbc = orc.PBC(system.cell)
+        rng = np.random.default_rng(17)
+        partner = np.full(len(centers), -1, dtype=np.int64)
+        for s_ in range(len(centers)):
+            if partner[s_] >= 0:
+                continue
+            d = pbc.distances(centers[s_], centers)
+            d[s_] = np.inf
+            d[partner >= 0] = np.inf
+            j = int(np.argmin(d))
+            if d[j] < 2.9 and (partner >= 0).sum() < 16:
+                partner[s_], partner[j] = j, s_
+        swap = (rng.random(labels.shape) < 0.35) & (labels >= 0)
+        swap &= partner[np.clip(labels, 0, None)] >= 0
+        labels = np.where(swap, partner[np.clip(labels, 0, None)], labels)
+    return system, frames, labels, confs, centers, verts

@@ -291,3 +291,29 @@ def test_unassigned_static_atoms_are_reported():
         la.run(syn.site_network_for(system), frames)
     assert e.value.frame == 7
     assert list(e.value.lattice_atoms) == list(o.value.lattice_atoms) == [4]
+
+
+def test_landmarks_with_up_to_twelve_vertices():
+    """More than 8 vertices per landmark (the reference has no limit, helpers.pyx:188-209): vertex blocks 3 of 4."""
+    import torch
+    from oracle import landmark_oracle as orc
+    system, cfg = syn.make_config("toy_bcc")
+    pbc = orc.PBC(system.cell)
+    rng = np.random.default_rng(3)
+    verts = []
+    for c in system.lm_centers:
+        d = pbc.distances(c, system.static_pos)
+        verts.append([int(x) for x in np.argsort(d, kind="stable")[:int(rng.integers(3, 13))]])
+    frames = system.trajectory(30)
+    from sitator_b200.engine import LandmarkEngine
+    eng = LandmarkEngine(system.cell, system.static_idx, system.mobile_idx, system.n_total, system.static_pos,
+                         system.lm_centers, verts, cutoff_midpoint=1.6, cutoff_steepness=20.0)
+    eng.set_frames(frames)
+    got = eng.fill_dense(dtype=torch.float64).cpu().numpy()
+    want, _, _ = orc.fill_landmark_vectors(system.cell, system.static_pos, system.static_idx, system.mobile_idx,
+                                           system.lm_centers, verts, frames, midpoint=1.6, steepness=20.0,
+                                           check_for_zeros=False)
+    assert np.array_equal(got != 0, want != 0)
+    nz = want != 0
+    assert nz.sum() > 100
+    assert np.max(np.abs(got[nz] - want[nz]) / want[nz]) < U.LV_RTOL
