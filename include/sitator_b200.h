@@ -140,14 +140,14 @@ int sitb_pass_stats_cached(sitb_ctx* ctx, int64_t frame_begin, int64_t n, uint64
  * (invalid configuration) when n_landmarks is too large for the shared-memory tables (> ~9000). */
 int sitb_gram_from_cached(sitb_ctx* ctx, const uint64_t* dev_row_ptr, const uint16_t* dev_pool_k,
                           const double* dev_pool_v, int64_t n_frames, double* dev_gram_upper);
-/* The same Gram, accumulated deterministically: every addend is split into three 64-bit integers (units of 2^-24,
- * 2^-56, 2^-88; exact for addends >= 2^-36) and added with integer atomics, so the result is the exact sum rounded
+/* The same Gram, accumulated deterministically: every addend is split into three 64-bit integers (units of 2^-30,
+ * 2^-62, 2^-94; exact for addends >= 2^-42) and added with integer atomics, so the result is the exact sum rounded
  * once -- independent of the order of addition, bit-identical from run to run, and for every frame sharding whose
  * boundaries are multiples of the window length (16 frames; windows are aligned to global frame numbers, and the
  * integer words of the shards are summed before sitb_gram_words_finish converts them).
  * dev_gram_words: int64 [2 (n_landmarks + 1)][n_landmarks], zeroed by the caller (+=).  Plane 0: upper triangle =
- * units of 2^-24, lower triangle = units of 2^-56 of the mirrored entry, row n_landmarks = units of 2^-56 of the
- * diagonal; plane 1: units of 2^-88 at the positions of the 2^-56 words.
+ * units of 2^-30, lower triangle = units of 2^-62 of the mirrored entry, row n_landmarks = units of 2^-62 of the
+ * diagonal; plane 1: units of 2^-94 at the positions of the 2^-62 words.
  * sitb_gram_words_finish writes the float64 upper triangle (lower triangle zero) that sitb_landmark_graph reads. */
 int sitb_gram_words_from_cached(sitb_ctx* ctx, const uint64_t* dev_row_ptr, const uint16_t* dev_pool_k,
                                 const double* dev_pool_v, int64_t n_frames, int64_t* dev_gram_words);

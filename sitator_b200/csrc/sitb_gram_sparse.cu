@@ -15,14 +15,16 @@
 //
 // Deterministic accumulation (EXACT = true, the default of the clustering plugin): FP64 atomics add in arrival
 // order, so two runs differed in the last bits of G.  Here every addend (a window's tile entry, or a single pair
-// product on the direct path) is split into THREE 64-bit integers -- units of 2^-24, 2^-56 and 2^-88 -- and added
-// with integer atomics.  An FP64 addend >= 2^-36 is represented exactly (addends below that are rounded to 2^-88),
+// product on the direct path) is split into THREE 64-bit integers -- units of 2^-30, 2^-62 and 2^-94 -- and added
+// with integer atomics.  An FP64 addend >= 2^-42 is represented exactly (addends below that are rounded to 2^-94),
 // and integer addition is associative: G is the exact sum of the addends, rounded once at the end, bit-identical
 // from run to run and, with the windows aligned to GLOBAL frame numbers, for every sharding whose boundaries are
 // multiples of GW_T frames (the integer words are all-reduced before they are converted).  The third word is
-// touched only by addends with bits below 2^-56 (addends < 2^-4).  Layout of the word matrix
-// long long[2 (L + 1)][L]: plane 0: upper triangle = the 2^-24 words, lower triangle = the 2^-56 words of the
-// mirrored entry, row L = the 2^-56 words of the diagonal; plane 1, same positions as the 2^-56 words: the 2^-88 words.
+// touched only by addends with bits below 2^-62 (addends < 2^-10; a product of two components is rarely that small).
+// Sums stay below 2^63: an entry is at most the number of rows (< 2^32, sitb_api.cu), i.e. < 2^62 units of 2^-30.
+// Layout of the word matrix long long[2 (L + 1)][L]: plane 0: upper triangle = the 2^-30 words, lower triangle = the
+// 2^-62 words of the mirrored entry, row L = the 2^-62 words of the diagonal; plane 1, same positions as the 2^-62
+// words: the 2^-94 words.
 #include "../../include/sitator_b200.h"
 #include "sitb_common.cuh"
 
@@ -48,13 +50,13 @@ __device__ __forceinline__ void gram_add(double* __restrict__ gram, int L, unsig
     } else {
         unsigned long long* w = (unsigned long long*)gram;
         const size_t plane = (size_t)(L + 1) * L;
-        const double s = x * 16777216.0;                        // 2^24: exact
+        const double s = x * 1073741824.0;                      // 2^30: exact
         const double h = floor(s);
         const double s2 = (s - h) * 4294967296.0;               // 2^32: exact
         const double m = floor(s2);
         const unsigned long long hi = (unsigned long long)(long long)h;
         const unsigned long long mid = (unsigned long long)(long long)m;
-        const unsigned long long lo = (unsigned long long)__double2ll_rn((s2 - m) * 4294967296.0);   // grid 2^-88
+        const unsigned long long lo = (unsigned long long)__double2ll_rn((s2 - m) * 4294967296.0);   // grid 2^-94
         const size_t at = (r == c) ? ((size_t)L * L + r) : ((size_t)c * L + r);
         if (hi) atomicAdd(&w[(size_t)r * L + c], hi);
         if (mid) atomicAdd(&w[at], mid);
@@ -260,12 +262,12 @@ __global__ void k_gram_words_finish(const long long* __restrict__ w, int L, doub
         const unsigned long long hi = (unsigned long long)w[(size_t)r * L + c];
         const unsigned long long mid = (unsigned long long)w[at];
         const unsigned long long lo = (unsigned long long)w[plane + at];
-        // the exact sum is (hi 2^64 + mid 2^32 + lo) 2^-88: assemble it as a 128-bit integer (hi < 2^56 by the row
-        // limit, so hi 2^64 needs care: keep hi's top part separate), convert the pieces and add from small to large
+        // the exact sum is (hi 2^64 + mid 2^32 + lo) 2^-94: the two low words as a 128-bit integer, its carry into hi,
+        // then two conversions and one addition (a fixed function of the words; error below one ulp of the result)
         const unsigned __int128 low = ((unsigned __int128)mid << 32) + (unsigned __int128)lo;     // < 2^97
-        const unsigned long long carry = (unsigned long long)(low >> 64);                          // units of 2^-24
-        const unsigned long long rest = (unsigned long long)low;                                   // units of 2^-88
-        v = ldexp((double)rest, -88) + ldexp((double)(hi + carry), -24);
+        const unsigned long long carry = (unsigned long long)(low >> 64);                          // units of 2^-30
+        const unsigned long long rest = (unsigned long long)low;                                   // units of 2^-94
+        v = ldexp((double)rest, -94) + ldexp((double)(hi + carry), -30);
     }
     out[idx] = v;
 }
