@@ -161,6 +161,11 @@ int sitb_assign_sparse(sitb_ctx* ctx, const uint64_t* dev_row_ptr, const uint16_
                        uint64_t* dev_counts, uint64_t* dev_best, double* dev_rep, double* dev_rep_w,
                        uint64_t* dev_site_best);
 
+/* |lvec|^2 of selected cached rows (dev_rows[n]: indices local to the cache; out of range -> 0, so shards can be summed):
+ * the norm of each cluster's best-matching landmark vector (cluster/mcl.py:84-88) without materialising the rows. */
+int sitb_sparse_row_norm2(sitb_ctx* ctx, const uint64_t* dev_row_ptr, const double* dev_pool_v, int64_t n_rows,
+                          const int64_t* dev_rows, int32_t n, double* dev_out);
+
 /* The min_samples filter of DotProdClassifier.fit_predict (util/DotProdClassifier.pyx:105-118) without a second
  * full predict.  dev_remap[C_old]: new id of each first-predict cluster, -1 = removed.  sitb_relabel_select renumbers
  * dev_labels in place and lists the rows of removed clusters (dev_row_list[<= n_rows], *dev_n_list += their number);

@@ -67,6 +67,7 @@ SIGNATURES = {
     "sitb_gram_words_from_cached": (C.c_int, [_P, _P, _P, _P, C.c_int64, _P]),
     "sitb_gram_words_finish": (C.c_int, [C.c_int, _P, C.c_int32, _P, _P]),
     "sitb_assign_sparse": (C.c_int, [_P, _P, _P, _P, C.c_int64, C.c_int64, C.c_double] + [_P] * 7),
+    "sitb_sparse_row_norm2": (C.c_int, [_P, _P, _P, C.c_int64, _P, C.c_int32, _P]),
     "sitb_relabel_select": (C.c_int, [_P, _P, C.c_int64, _P, _P, _P]),
     "sitb_assign_sparse_rows": (C.c_int, [_P, _P, _P, _P, _P, _P, C.c_int64, C.c_int64, C.c_double] + [_P] * 7),
     "sitb_set_centers": (C.c_int, [_P, _P, _P, C.c_int32]),

@@ -953,6 +953,8 @@ cudaError_t launch_assign_sparse(const unsigned long long* row_ptr, const uint16
                                  const unsigned long long* n_list = nullptr);
 cudaError_t launch_relabel_select(long long* labels, long long n_rows, const int* remap, long long* row_list,
                                   unsigned long long* n_list, int n_sms, cudaStream_t st);
+cudaError_t launch_sparse_row_norm2(const unsigned long long* row_ptr, const double* pv, long long n_rows,
+                                    const long long* rows, int n, double* out, cudaStream_t st);
 }
 
 extern "C" int sitb_pass_stats_cached(sitb_ctx* c, int64_t begin, int64_t n, uint64_t* dev_seen, double* dev_gram,
@@ -983,6 +985,16 @@ extern "C" int sitb_assign_sparse(sitb_ctx* c, const uint64_t* dev_row_ptr, cons
                             c->d_cid_orig, c->d_cw_orig, c->n_clusters, thr, (long long*)labels, confs,
                             (unsigned long long*)counts, (unsigned long long*)best, rep, rep_w,
                             (unsigned long long*)site_best, c->n_sms, c->stream));
+    return SITB_OK;
+}
+
+extern "C" int sitb_sparse_row_norm2(sitb_ctx* c, const uint64_t* dev_row_ptr, const double* dev_pool_v, int64_t n_rows,
+                                     const int64_t* dev_rows, int32_t n, double* dev_out) {
+    if (!c || !dev_row_ptr || !dev_pool_v || !dev_rows || !dev_out || n < 0 || n_rows < 0)
+        return fail(SITB_E_INVALID, "sitb_sparse_row_norm2: bad argument");
+    CK(cudaSetDevice(c->device));
+    CK(launch_sparse_row_norm2((const unsigned long long*)dev_row_ptr, dev_pool_v, n_rows, (const long long*)dev_rows, n, dev_out,
+                               c->stream));
     return SITB_OK;
 }
 

@@ -50,13 +50,20 @@ __device__ __forceinline__ void gram_add(double* __restrict__ gram, int L, unsig
     } else {
         unsigned long long* w = (unsigned long long*)gram;
         const size_t plane = (size_t)(L + 1) * L;
-        const double s = x * 1073741824.0;                      // 2^30: exact
-        const double h = floor(s);
-        const double s2 = (s - h) * 4294967296.0;               // 2^32: exact
-        const double m = floor(s2);
-        const unsigned long long hi = (unsigned long long)(long long)h;
-        const unsigned long long mid = (unsigned long long)(long long)m;
-        const unsigned long long lo = (unsigned long long)__double2ll_rn((s2 - m) * 4294967296.0);   // grid 2^-94
+        // x = m 2^(ex - 1075) as a 128-bit fixed-point number in units of 2^-94 (integer shifts: the float64
+        // floor / convert sequence cost more than the atomics).  x < 2^33 (an entry is bounded by the row count).
+        const unsigned long long bits = (unsigned long long)__double_as_longlong(x);
+        const int ex = (int)(bits >> 52);
+        if (ex == 0) return;                                    // zero (or subnormal: below any grid)
+        const unsigned long long m = (bits & 0x000FFFFFFFFFFFFFull) | 0x0010000000000000ull;
+        const int sh = ex - 981;                                // = (ex - 1075) + 94
+        unsigned __int128 F;
+        if (sh >= 0) F = (unsigned __int128)m << sh;            // exact
+        else if (sh > -54) F = (unsigned __int128)((m + (1ull << (-sh - 1))) >> -sh);      // rounded to 2^-94
+        else return;
+        const unsigned long long hi = (unsigned long long)(F >> 64);
+        const unsigned long long mid = ((unsigned long long)F) >> 32;
+        const unsigned long long lo = ((unsigned long long)F) & 0xFFFFFFFFull;
         const size_t at = (r == c) ? ((size_t)L * L + r) : ((size_t)c * L + r);
         if (hi) atomicAdd(&w[(size_t)r * L + c], hi);
         if (mid) atomicAdd(&w[at], mid);

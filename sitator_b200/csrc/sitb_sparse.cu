@@ -380,6 +380,33 @@ __global__ void k_relabel_select(long long* __restrict__ labels, long long n_row
     }
 }
 
+// |row|^2 of selected cached rows (cluster/mcl.py:86: np.linalg.norm of each cluster's best-matching landmark vector);
+// rows[i] < 0 or >= n_rows (not resident on this rank) give 0, so the shards' results can be summed
+__global__ void k_sparse_row_norm2(const unsigned long long* __restrict__ row_ptr, const double* __restrict__ pv,
+                                   long long n_rows, const long long* __restrict__ rows, int n, double* __restrict__ out) {
+    const int i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (i >= n) return;
+    const long long r = rows[i];
+    double s = 0.0;
+    if (r >= 0 && r < n_rows) {
+        const unsigned long long ptr = row_ptr[r];
+        const int cnt = (int)(ptr & 0xFF);
+        const unsigned long long off = ptr >> 8;
+        for (int e = lane; e < cnt; e += 32) { const double v = pv[off + e]; s = fma(v, v, s); }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (lane == 0) out[i] = s;
+}
+
+cudaError_t launch_sparse_row_norm2(const unsigned long long* row_ptr, const double* pv, long long n_rows,
+                                    const long long* rows, int n, double* out, cudaStream_t st) {
+    if (n <= 0) return cudaSuccess;
+    k_sparse_row_norm2<<<(n + 3) / 4, 128, 0, st>>>(row_ptr, pv, n_rows, rows, n, out);
+    return cudaGetLastError();
+}
+
 cudaError_t launch_relabel_select(long long* labels, long long n_rows, const int* remap, long long* row_list,
                                   unsigned long long* n_list, int n_sms, cudaStream_t st) {
     if (n_rows <= 0) return cudaSuccess;

@@ -230,6 +230,7 @@ class LandmarkAnalysis(object):
         logger.info("  - computing landmark vectors / clustering -")
         source = LandmarkVectorSource(engine, comm)
         source.timer = timer
+        source.defer_d2h = True           # the plugin may leave the labels' device -> host copy in flight (see below)
         try:
             clustermod = importlib.import_module("sitator_b200.landmark.cluster." + self._cluster_algo)
         except ImportError:
@@ -332,6 +333,10 @@ class LandmarkAnalysis(object):
         out_st = SiteTrajectory(out_sn, lmk_lbls, lmk_confs, _copy=False)     # the arrays are this run's own
         out_st.frame0 = frame0
         out_st._comm = comm
+
+        if clustering.get('_d2h_done') is not None:
+            with timer.phase("labels + confidences D2H (wait)"):
+                clustering['_d2h_done'].synchronize()       # st.traj / st.confidences are complete from here on
 
         # Check that multiple particles are never assigned to one site at the same time
         with timer.phase("occupancy check (collective)"):

@@ -185,6 +185,32 @@ def _to_host(t):
     return h.numpy()
 
 
+_COPY_STREAMS = {}
+
+
+def _to_host_async(tensors):
+    """Start device -> page-locked host copies on a side stream (after everything queued on the current stream).
+    Returns (numpy arrays, event): the arrays are valid once the event has been synchronised."""
+    import torch
+    dev = tensors[0].device
+    side = _COPY_STREAMS.get(dev.index)
+    if side is None:
+        side = _COPY_STREAMS[dev.index] = torch.cuda.Stream(device=dev)
+    ready = torch.cuda.Event()
+    ready.record(torch.cuda.current_stream(dev))
+    outs = []
+    with torch.cuda.stream(side):
+        side.wait_event(ready)
+        for t in tensors:
+            h = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
+            h.copy_(t, non_blocking=True)
+            t.record_stream(side)
+            outs.append(h)
+        done = torch.cuda.Event()
+        done.record(side)
+    return [h.numpy() for h in outs], done
+
+
 def _centre_tables(clusters, vectors, L):
     cid = np.full(L, -1, dtype=np.int32)
     w = np.zeros(L, dtype=np.float64)
@@ -242,18 +268,16 @@ def do_landmark_clustering(landmark_vectors, clustering_params, min_samples, ver
         eng.set_centers(cid, w, n_clusters)
         best = new_best_table(n_clusters, eng.device)
         source.assign(float('nan'), best=best)
-        _, best_rows = read_best_table(best, comm)
-    with timer.phase("  best rows materialised (collective)"):
-        best_lvecs = source.rows(best_rows)                                   # (n_clusters, L) float64
+        best_vals, best_rows = read_best_table(best, comm)
+    with timer.phase("  best rows: norms (collective)"):
+        # best_vals[i] = |best lvec . centre| (mcl.py:84-85) came out of the pass; only the row's norm (:86) is missing
+        best_norms = np.sqrt(source.row_norms2(best_rows))
     good = np.zeros(n_clusters, dtype=bool)
     scale = np.ones(n_clusters)
     for i, cl in enumerate(clusters):
-        centre = np.zeros(L)
-        centre[cl] = vectors[i]
-        best_match_dot = abs(float(np.dot(best_lvecs[i], centre)))
-        norm = np.linalg.norm(best_lvecs[i])
+        best_match_dot = float(best_vals[i])
         with np.errstate(divide='ignore', invalid='ignore'):
-            best_match_dot_norm = best_match_dot / norm
+            best_match_dot_norm = best_match_dot / best_norms[i]
         good[i] = (best_match_dot_norm >= good_site_normed_threshold) and (best_match_dot >= good_site_project_thresh)
         scale[i] = best_match_dot
     logger.debug("Kept %i/%i landmark clusters as good sites" % (int(np.sum(good)), len(good)))
@@ -336,8 +360,19 @@ def do_landmark_clustering(landmark_vectors, clustering_params, min_samples, ver
         else:
             raise NotImplementedError("weighted_representative_landmarks=False (the reference cannot reach it either: "
                                       "the key is forwarded to markov_clustering, mcl.py:66,115)")
+    d2h_done = None
+    n_unassigned = None
     with timer.phase("  labels + confidences D2H"):
-        host_labels, host_confs = _to_host(labels), _to_host(confs)
+        if getattr(source, "defer_d2h", False):
+            # (counted before the big copy starts: a scalar read queued behind it would wait for all of it)
+            n_unassigned = int((labels < 0).sum().item())
+            if comm is not None:
+                n_unassigned = comm.allreduce_sum_scalar(n_unassigned)
+            # LandmarkAnalysis.run goes on with device work (site centres, occupancy check) while the 16 bytes per
+            # landmark vector cross PCIe on a side stream; it waits for `_d2h_done` before it returns
+            (host_labels, host_confs), d2h_done = _to_host_async([labels, confs])
+        else:
+            host_labels, host_confs = _to_host(labels), _to_host(confs)
 
     return {
         CLUSTERING_CLUSTER_SIZE: kept_counts,
@@ -347,5 +382,6 @@ def do_landmark_clustering(landmark_vectors, clustering_params, min_samples, ver
         CLUSTERING_REPRESENTATIVE_LANDMARKS: reps,
         # device-side copies for the rest of LandmarkAnalysis.run (not part of the reference contract)
         '_dev_labels': labels, '_dev_confs': confs, '_dev_site_best': site_best,
-        '_centers': (cid, w), '_mcl_iterations': n_iter,
+        '_centers': (cid, w), '_mcl_iterations': n_iter, '_d2h_done': d2h_done,
+        '_n_unassigned': n_unassigned,
     }

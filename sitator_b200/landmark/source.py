@@ -59,6 +59,23 @@ class LandmarkVectorSource(object):
             out = self.comm.allreduce_sum_numpy(out)
         return out
 
+    def row_norms2(self, global_rows):
+        """|landmark vector|^2 of the given global rows (float64 numpy), each resident on some rank."""
+        import torch
+        eng = self.engine
+        global_rows = np.asarray(global_rows, dtype=np.int64)
+        if self.sparse is None:
+            lv = self.rows(global_rows)
+            return np.einsum('ij,ij->i', lv, lv)
+        local = torch.as_tensor(global_rows - self.row0, device=eng.device)
+        out = torch.empty((len(global_rows),), dtype=torch.float64, device=eng.device)
+        from .. import _native
+        _native.check(eng._lib.sitb_sparse_row_norm2(eng._ctx, eng._ptr(self.sparse.ptr), eng._ptr(self.sparse.v),
+                                                     self.sparse.n_rows, eng._ptr(local), len(global_rows), eng._ptr(out)))
+        if self.comm is not None:
+            self.comm.allreduce_sum_(out)
+        return out.cpu().numpy()
+
     # set by the plugin's first pass when the rows were cached (engine.SparseRows)
     sparse = None
     cache_rows = True
