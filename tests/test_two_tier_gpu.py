@@ -100,3 +100,63 @@ def test_two_tier_falls_back_for_triclinic_cells():
     lf, cf, nf, info = _assign(eng, "two_tier", 0.3, N)
     assert not info["available"]
     assert np.array_equal(lf, le) and np.array_equal(cf, ce) and np.array_equal(nf, ne)
+
+
+@pytest.mark.parametrize("dynamic", [False, True])
+def test_two_tier_with_two_vertex_blocks_and_soft_cutoff(dynamic):
+    """Landmarks with 3..8 vertices (two vertex blocks: the <2, *> kernels), a softer and wider cut-off (larger tau),
+    against the float64 pass and against DotProdClassifier.predict restated on the oracle's landmark vectors."""
+    import torch
+    from oracle import landmark_oracle as orc
+    from sitator_b200.engine import LandmarkEngine
+    system, cfg = syn.make_config("toy_bcc")
+    pbc = orc.PBC(system.cell)
+    rng = np.random.default_rng(5)
+    verts = []
+    for c in system.lm_centers:
+        d = pbc.distances(c, system.static_pos)
+        verts.append([int(x) for x in np.argsort(d, kind="stable")[:int(rng.integers(3, 9))]])
+    frames = system.trajectory(80)
+    mid, steep = 1.4, 18.0
+    eng = LandmarkEngine(system.cell, system.static_idx, system.mobile_idx, system.n_total, system.static_pos,
+                         system.lm_centers, verts, cutoff_midpoint=mid, cutoff_steepness=steep, dynamic_lattice_mapping=dynamic)
+    eng.set_frames(frames)
+    d = system.lm_centers[:, None, :] - system.site_pos[None, :, :]
+    d -= system.lengths * np.round(d / system.lengths)
+    dist = np.sqrt((d ** 2).sum(-1))
+    cid = np.where(dist.min(1) < 2.0, dist.argmin(1), -1).astype(np.int32)
+    n_sites = len(system.site_pos)
+    w = 0.5 + rng.random(system.n_landmarks)
+    eng.set_centers(cid, w, n_sites)
+    N = len(frames) * system.n_mobile
+    thr = 0.9
+    le, ce, ne, _ = _assign(eng, "exact", thr, N)
+    lf, cf, nf, info = _assign(eng, "two_tier", thr, N)
+    assert info["available"]
+    assert np.array_equal(lf, le) and np.array_equal(nf, ne)
+    assert float(np.max(np.abs(cf - ce))) < 20 * info["tau"] + 1e-6
+    assert info["recheck_rows"] < 0.1 * N
+    want, _, _ = orc.fill_landmark_vectors(system.cell, system.static_pos, system.static_idx, system.mobile_idx,
+                                           system.lm_centers, verts, frames, midpoint=mid, steepness=steep,
+                                           check_for_zeros=False, dynamic_lattice_mapping=dynamic)
+    centers = np.zeros((n_sites, system.n_landmarks))
+    sel = cid >= 0
+    centers[cid[sel], np.nonzero(sel)[0]] = w[sel]
+    dots = np.abs(want @ centers.T)
+    srt = np.sort(dots, axis=1)
+    decided = np.minimum(srt[:, -1] - srt[:, -2], np.abs(srt[:, -1] - thr)) > 1e-9
+    want_labels = np.where((srt[:, -1] >= thr) & want.any(1), dots.argmax(1), -1)
+    assert np.array_equal(lf[decided], want_labels[decided])
+
+
+def test_two_tier_falls_back_for_large_centre_weights():
+    """Centre weights beyond the fixed-point range of the error bound's sum: the float64 kernel runs alone."""
+    system, frames, la, st = _run_and_engine("toy_bcc", 60)
+    eng = la._engine
+    cid, w = la.cluster_centers_
+    eng.set_centers(cid, np.asarray(w) * 1000.0, st.site_network.n_sites)
+    N = 60 * system.n_mobile
+    le, ce, ne, _ = _assign(eng, "exact", 700.0, N)
+    lf, cf, nf, info = _assign(eng, "two_tier", 700.0, N)
+    assert info["recheck_rows"] == 0                       # the first tier did not run
+    assert np.array_equal(lf, le) and np.array_equal(cf, ce) and np.array_equal(nf, ne)
