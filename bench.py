@@ -420,8 +420,23 @@ def run_ours(args):
             e2e_ms.append(max_over_ranks(a.elapsed_time(b)))
     n_sites = st.site_network.n_sites
     e2e_t = float(np.mean(e2e_ms)) * 1e-3
+    # what the e2e number is made of on the host side: all ranks upload their block at once (as inside run()); with N > 1
+    # the ranks share the host's memory / PCIe root bandwidth, which is what separates the N-GPU e2e from the 1-GPU one
+    # (profiles/r02_h2d_concurrency.md)
+    barrier()
+    ua = torch.cuda.Event(enable_timing=True); ub = torch.cuda.Event(enable_timing=True)
+    ua.record()
+    la._engine.set_frames(frames, frame0=la._engine.frame0)
+    la._engine.fill_dense(begin=F - 1, n=1)          # a pass over the last frame waits for every upload chunk
+    ub.record()
+    barrier()
+    up_ms = ua.elapsed_time(ub)
+    up_max = max_over_ranks(up_ms)
+    up_min = -max_over_ranks(-up_ms)
     e2e = {"value": F * A * world / e2e_t, "unit": UNIT, "h2d_bytes_per_step": int(frames.nbytes),
            "d2h_bytes_per_step": int(F * M * 16), "ms": e2e_t * 1e3, "steps": len(e2e_ms), "n_sites": int(n_sites),
+           "upload_alone_ms_slowest_rank": up_max, "upload_alone_ms_fastest_rank": up_min,
+           "upload_gbs_slowest_rank": frames.nbytes / (up_max * 1e-3) / 1e9,
            "what": "LandmarkAnalysis(clustering_algorithm='mcl').run(sn, frames) with frames in pinned host memory"}
 
     # ---- e2e_strong: BASELINE configs[4], a fixed 10^6-frame LLZO trajectory split over the N ranks ------------
