@@ -2,6 +2,7 @@
 #include "../../include/sitator_b200.h"
 #include "sitb_fill.cuh"
 
+#include <chrono>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
@@ -17,12 +18,15 @@ cudaError_t launch_tables(const Cell& cell, const double* centers, const double*
 void build_landmark_tables(const Cell& cell, int L, int V, int Lpad, int NB, int S, double steep_log2e,
                            const int* verts_in, const double* ideal, const double* svd, const double* q,
                            HostTables& out);
-cudaError_t launch_grid_static_lists(const Cell& cell, const double* ideal, const double* rmax, int S, int gx, int gy,
-                                     int gz, double margin, const unsigned* ptr, unsigned* count, uint16_t* list,
+cudaError_t launch_grid_static_masks(const Cell& cell, const double* ideal, const double* rmax, int S, int gx, int gy,
+                                     int gz, double margin0, double margin1, uint2* masks, unsigned* count,
                                      cudaStream_t stream);
-cudaError_t launch_grid_lists(const Cell& cell, const double* ideal, const ushort4* va, const double* q64, int L,
-                              int Lpad, int NB, int S, int gx, int gy, int gz, double margin, const unsigned* ptr,
-                              unsigned* count, uint16_t* list, cudaStream_t stream);
+cudaError_t launch_grid_masks(const Cell& cell, const double* ideal, const ushort4* va, const double* q64, int L,
+                              int Lpad, int NB, int S, int gx, int gy, int gz, double margin0, double margin1, uint2* masks,
+                              unsigned* count, cudaStream_t stream);
+cudaError_t launch_grid_lists_from_masks(const uint2* masks, int n_chunks, long long cells, const unsigned* ptr0,
+                                         const unsigned* ptr1, uint16_t* list0, uint16_t* list1, uint16_t* cat_list,
+                                         uint2* cat_box, cudaStream_t stream);
 }
 
 using namespace sitb;
@@ -61,8 +65,7 @@ struct GridLevelDev {
     uint16_t* slist = nullptr;
     double margin = 0.0;
     unsigned long long entries = 0, static_entries = 0;
-    std::vector<unsigned> h_sptr;     // host copy of sptr (first tier of the two-tier assign pass)
-};
+};                                    // (the four arrays of both levels live in one block: sitb_ctx::d_grid_block)
 
 struct sitb_ctx {
     int device = 0;
@@ -94,6 +97,7 @@ struct sitb_ctx {
     uint8_t* d_nverts = nullptr;
     // candidate grid (orthorhombic cells)
     GridLevelDev grid[2];             // [0] half the margin, [1] the margin
+    unsigned char* d_grid_block = nullptr;   // every list of both levels + the first tier's site lists, one allocation
     int n_grid_levels = 0;
     double* d_rmax = nullptr;
     double* d_ideal_wrapped = nullptr;   // static-lattice positions wrapped into the cell (grid builder)
@@ -150,11 +154,7 @@ static void free_ctx(sitb_ctx* c) {
     for (cudaEvent_t ev : c->up_events) cudaEventDestroy(ev);
     pool_free(c->d_static_idx, c->stream); pool_free(c->d_mobile_idx, c->stream); pool_free(c->d_ideal, c->stream); pool_free(c->d_centers, c->stream);
     pool_free(c->d_chunk_atoms, c->stream); pool_free(c->d_chunk_bound, c->stream);
-    for (int l = 0; l < 2; ++l) {
-        pool_free(c->grid[l].ptr, c->stream); pool_free(c->grid[l].list, c->stream);
-        pool_free(c->grid[l].sptr, c->stream); pool_free(c->grid[l].slist, c->stream);
-    }
-    pool_free(c->d_fast_sbox, c->stream); pool_free(c->d_fast_slist, c->stream);
+    pool_free(c->d_grid_block, c->stream);
     pool_free(c->d_fast_cbox, c->stream); pool_free(c->d_fast_clist, c->stream);
     pool_free(c->d_fast_ib, c->stream); pool_free(c->d_fast_ac, c->stream); pool_free(c->d_fast_cw, c->stream);
     pool_free(c->d_ideal_frac, c->stream); pool_free(c->d_recheck, c->stream); pool_free(c->d_frame_flag, c->stream);
@@ -174,7 +174,29 @@ static cudaError_t upload(T** dst, const T* src, size_t n, cudaStream_t st) {
     return e;
 }
 
+// the same without the wait: the caller keeps src alive until it has synchronised the stream
+template <typename T>
+static cudaError_t upload_async(T** dst, const T* src, size_t n, cudaStream_t st) {
+    cudaError_t e = pool_alloc((void**)dst, sizeof(T) * n, st);
+    if (e != cudaSuccess) return e;
+    if (n) e = cudaMemcpyAsync(*dst, src, sizeof(T) * n, cudaMemcpyHostToDevice, st);
+    return e;
+}
+
 static int build_grid(sitb_ctx* c, double margin);
+
+// developer aid: SITB_TIMING=1 prints the host wall time of the stages of sitb_create / the grid build to stderr
+struct StageClock {
+    bool on;
+    std::chrono::steady_clock::time_point t;
+    StageClock() : on(getenv("SITB_TIMING") != nullptr), t(std::chrono::steady_clock::now()) {}
+    void lap(const char* what) {
+        if (!on) return;
+        const auto now = std::chrono::steady_clock::now();
+        fprintf(stderr, "[sitb timing] %-44s %8.3f ms\n", what, std::chrono::duration<double, std::milli>(now - t).count());
+        t = now;
+    }
+};
 extern "C" int sitb_reset_status(sitb_ctx* c);
 
 extern "C" const char* sitb_last_error(void) { return g_err; }
@@ -210,6 +232,7 @@ extern "C" int sitb_create(const sitb_network_desc* d, int device, sitb_ctx** ou
             if (d->host_verts[(size_t)k * d->max_verts + h] >= d->n_static)
                 return fail(SITB_E_INVALID, "sitb_create: verts[%d][%d] out of range", k, h);
     }
+    StageClock clk;
     int ndev = 0;
     cudaError_t e = cudaGetDeviceCount(&ndev);
     if (e != cudaSuccess || ndev == 0)
@@ -262,6 +285,7 @@ extern "C" int sitb_create(const sitb_network_desc* d, int device, sitb_ctx** ou
     c->bcoef = c->steepness * c->midpoint;
 
     const size_t LV = (size_t)c->L * c->V;
+    clk.lap("create: validation, device, cell");
 #define CKC(call)                                                                          \
     do {                                                                                   \
         cudaError_t e2_ = (call);                                                          \
@@ -270,11 +294,11 @@ extern "C" int sitb_create(const sitb_network_desc* d, int device, sitb_ctx** ou
             return fail(SITB_E_CUDA, "%s failed: %s", #call, cudaGetErrorString(e2_));     \
         }                                                                                  \
     } while (0)
-    CKC(upload(&c->d_static_idx, d->host_static_idx, (size_t)c->S, c->stream));
-    CKC(upload(&c->d_mobile_idx, d->host_mobile_idx, (size_t)c->M, c->stream));
-    CKC(upload(&c->d_ideal, d->host_ideal_static, (size_t)c->S * 3, c->stream));
-    CKC(upload(&c->d_centers, d->host_centers, (size_t)c->L * 3, c->stream));
-    CKC(upload(&c->d_verts_in, d->host_verts, LV, c->stream));
+    CKC(upload_async(&c->d_static_idx, d->host_static_idx, (size_t)c->S, c->stream));
+    CKC(upload_async(&c->d_mobile_idx, d->host_mobile_idx, (size_t)c->M, c->stream));
+    CKC(upload_async(&c->d_ideal, d->host_ideal_static, (size_t)c->S * 3, c->stream));
+    CKC(upload_async(&c->d_centers, d->host_centers, (size_t)c->L * 3, c->stream));
+    CKC(upload_async(&c->d_verts_in, d->host_verts, LV, c->stream));
     CKC(pool_alloc((void**)&c->d_svd, sizeof(double) * LV, c->stream));
     CKC(pool_alloc((void**)&c->d_qorig, sizeof(double) * LV, c->stream));
     CKC(pool_alloc((void**)&c->d_cid, sizeof(int) * (size_t)c->L, c->stream));
@@ -287,13 +311,15 @@ extern "C" int sitb_create(const sitb_network_desc* d, int device, sitb_ctx** ou
     c->h_svd.resize(LV); c->h_qorig.resize(LV);
     CKC(cudaMemcpy(c->h_svd.data(), c->d_svd, sizeof(double) * LV, cudaMemcpyDeviceToHost));
     CKC(cudaMemcpy(c->h_qorig.data(), c->d_qorig, sizeof(double) * LV, cudaMemcpyDeviceToHost));
+    clk.lap("create: uploads, site-vertex distances, D2H");
     {
         HostTables ht;
         build_landmark_tables(c->cell, c->L, c->V, c->Lpad, c->NB, c->S, steep_log2e, d->host_verts,
                               d->host_ideal_static, c->h_svd.data(), c->h_qorig.data(), ht);
-        CKC(upload(&c->d_chunk_atoms, ht.chunk_atoms.data(), ht.chunk_atoms.size(), c->stream));
-        CKC(upload(&c->d_chunk_bound, ht.chunk_bound.data(), ht.chunk_bound.size(), c->stream));
-        CKC(upload(&c->d_rmax, ht.rmax.data(), ht.rmax.size(), c->stream));
+        clk.lap("create: host landmark tables");
+        CKC(upload_async(&c->d_chunk_atoms, ht.chunk_atoms.data(), ht.chunk_atoms.size(), c->stream));
+        CKC(upload_async(&c->d_chunk_bound, ht.chunk_bound.data(), ht.chunk_bound.size(), c->stream));
+        CKC(upload_async(&c->d_rmax, ht.rmax.data(), ht.rmax.size(), c->stream));
         {
             // what the grid builder reads per (box, landmark, vertex): wrapped Cartesian positions and radii, once
             std::vector<double> iw((size_t)c->S * 3, 0.0), rad(ht.q64.size());
@@ -305,19 +331,21 @@ extern "C" int sitb_create(const sitb_network_desc* d, int device, sitb_ctx** ou
                         iw[(size_t)s * 3 + k] = f * c->cell.c[4 * k];
                     }
             for (size_t i = 0; i < rad.size(); ++i) rad[i] = (ht.q64[i] >= 0.0) ? std::sqrt(ht.q64[i]) : -1.0;
-            CKC(upload(&c->d_ideal_wrapped, iw.data(), iw.size(), c->stream));
-            CKC(upload(&c->d_radius, rad.data(), rad.size(), c->stream));
+            CKC(upload_async(&c->d_ideal_wrapped, iw.data(), iw.size(), c->stream));
+            CKC(upload_async(&c->d_radius, rad.data(), rad.size(), c->stream));
+            CKC(cudaStreamSynchronize(c->stream));                 // iw, rad go out of scope
         }
         c->internal_of = ht.internal_of;
-        CKC(upload(&c->d_v0, ht.v0.data(), ht.v0.size(), c->stream));
-        CKC(upload(&c->d_b0, ht.b0.data(), ht.b0.size(), c->stream));
-        CKC(upload(&c->d_va, ht.va.data(), ht.va.size(), c->stream));
-        CKC(upload(&c->d_ba, ht.ba.data(), ht.ba.size(), c->stream));
-        CKC(upload(&c->d_q64, ht.q64.data(), ht.q64.size(), c->stream));
-        CKC(upload(&c->d_acoef, ht.acoef.data(), ht.acoef.size(), c->stream));
-        CKC(upload(&c->d_nverts, ht.nverts.data(), ht.nverts.size(), c->stream));
-        CKC(upload(&c->d_orig_of, ht.orig_of.data(), ht.orig_of.size(), c->stream));
+        CKC(upload_async(&c->d_v0, ht.v0.data(), ht.v0.size(), c->stream));
+        CKC(upload_async(&c->d_b0, ht.b0.data(), ht.b0.size(), c->stream));
+        CKC(upload_async(&c->d_va, ht.va.data(), ht.va.size(), c->stream));
+        CKC(upload_async(&c->d_ba, ht.ba.data(), ht.ba.size(), c->stream));
+        CKC(upload_async(&c->d_q64, ht.q64.data(), ht.q64.size(), c->stream));
+        CKC(upload_async(&c->d_acoef, ht.acoef.data(), ht.acoef.size(), c->stream));
+        CKC(upload_async(&c->d_nverts, ht.nverts.data(), ht.nverts.size(), c->stream));
+        CKC(upload_async(&c->d_orig_of, ht.orig_of.data(), ht.orig_of.size(), c->stream));
         c->h_nverts = ht.nverts;
+        clk.lap("create: table uploads");
         if (c->cell.diag) {
             // ---- float tables and error model of the two-tier assign pass (sitb_fill_fast.cu) ----
             // Squared distances are formed in FP32 from float fractional coordinates as |(u - round(u)) L|^2.  With
@@ -361,16 +389,17 @@ extern "C" int sitb_create(const sitb_network_desc* d, int device, sitb_ctx** ou
                 }
                 idf[s2] = make_float4(fr[0], fr[1], fr[2], 0.f);
             }
-            CKC(upload(&c->d_fast_ib, ib.data(), ib.size(), c->stream));
-            CKC(upload(&c->d_fast_ac, ac.data(), ac.size(), c->stream));
-            CKC(upload(&c->d_ideal_frac, idf.data(), idf.size(), c->stream));
+            CKC(upload_async(&c->d_fast_ib, ib.data(), ib.size(), c->stream));
+            CKC(upload_async(&c->d_fast_ac, ac.data(), ac.size(), c->stream));
+            CKC(upload_async(&c->d_ideal_frac, idf.data(), idf.size(), c->stream));
             CKC(pool_alloc((void**)&c->d_fast_cw, sizeof(float2) * (size_t)c->Lpad, c->stream));
             CKC(pool_alloc((void**)&c->d_two_tier, sizeof(unsigned long long) * (1 + RECHECK_SLOTS), c->stream));
             CKC(cudaMemsetAsync(c->d_two_tier, 0, sizeof(unsigned long long) * (1 + RECHECK_SLOTS), c->stream));
             c->fast_tables_ok = c->fast_kappa > 0.9 && c->fast_tau < 1e-2;
         }
+        CKC(cudaStreamSynchronize(c->stream));                     // ht and the float tables go out of scope
     }
-    CKC(cudaStreamSynchronize(c->stream));
+    clk.lap("create: float tables of the first tier");
 #undef CKC
     *out = c;
     int rc = sitb_reset_status(c);
@@ -380,56 +409,16 @@ extern "C" int sitb_create(const sitb_network_desc* d, int device, sitb_ctx** ou
         double margin = 0.5;
         if (const char* env = getenv("SITB_GRID_MARGIN")) margin = atof(env);
         rc = build_grid(c, margin);
+        clk.lap("create: candidate grid (total)");
     }
     if (rc != SITB_OK) { free_ctx(c); *out = nullptr; return rc; }
     return SITB_OK;
 }
 
-// (Re)build the candidate grid for a static-atom margin (Angstrom); margin <= 0 or a triclinic cell: no grid.
-// one level of the candidate grid: the landmark lists and the static-site lists of every box for one margin
-static int build_grid_level(sitb_ctx* c, const int g[3], double margin, GridLevelDev& out) {
-    const size_t cells = (size_t)g[0] * g[1] * g[2];
-    for (int pass = 0; pass < 2; ++pass) {                // 0: landmarks, 1: static-lattice sites
-        unsigned* d_count = nullptr;
-        CK(pool_alloc((void**)&d_count, sizeof(unsigned) * cells, c->stream));
-        cudaError_t e = pass == 0
-            ? launch_grid_lists(c->cell, c->d_ideal_wrapped, c->d_va, c->d_radius, c->L, c->Lpad, c->NB, c->S, g[0], g[1], g[2], margin,
-                                nullptr, d_count, nullptr, c->stream)
-            : launch_grid_static_lists(c->cell, c->d_ideal_wrapped, c->d_rmax, c->S, g[0], g[1], g[2], margin, nullptr, d_count, nullptr,
-                                       c->stream);
-        std::vector<unsigned> ptr(cells + 1, 0u);
-        if (e == cudaSuccess) e = cudaMemcpyAsync(ptr.data() + 1, d_count, sizeof(unsigned) * cells, cudaMemcpyDeviceToHost, c->stream);
-        if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
-        pool_free(d_count, c->stream);
-        if (e != cudaSuccess) return fail(SITB_E_CUDA, "candidate grid (count): %s", cudaGetErrorString(e));
-        unsigned long long total = 0;
-        for (size_t i = 1; i <= cells; ++i) { total += ptr[i]; ptr[i] = (unsigned)total; }
-        if (total >= 0xFFFFFFFFull) return fail(SITB_E_LIMIT, "candidate grid: more than 2^32 list entries");
-        unsigned** d_ptr = pass == 0 ? &out.ptr : &out.sptr;
-        uint16_t** d_list = pass == 0 ? &out.list : &out.slist;
-        CK(upload(d_ptr, ptr.data(), cells + 1, c->stream));
-        CK(pool_alloc((void**)d_list, sizeof(uint16_t) * (size_t)(total ? total : 1), c->stream));
-        if (pass == 0) {
-            CK(launch_grid_lists(c->cell, c->d_ideal_wrapped, c->d_va, c->d_radius, c->L, c->Lpad, c->NB, c->S, g[0], g[1], g[2], margin,
-                                 *d_ptr, nullptr, *d_list, c->stream));
-            out.entries = total;
-        } else {
-            CK(launch_grid_static_lists(c->cell, c->d_ideal_wrapped, c->d_rmax, c->S, g[0], g[1], g[2], margin, *d_ptr, nullptr, *d_list,
-                                        c->stream));
-            out.static_entries = total;
-            out.h_sptr = ptr;
-        }
-    }
-    return SITB_OK;
-}
-
 static void free_grid(sitb_ctx* c) {
-    for (int l = 0; l < 2; ++l) {
-        pool_free(c->grid[l].ptr, c->stream); pool_free(c->grid[l].list, c->stream);
-        pool_free(c->grid[l].sptr, c->stream); pool_free(c->grid[l].slist, c->stream);
-        c->grid[l] = GridLevelDev();
-    }
-    pool_free(c->d_fast_sbox, c->stream); pool_free(c->d_fast_slist, c->stream);
+    pool_free(c->d_grid_block, c->stream);
+    c->d_grid_block = nullptr;
+    for (int l = 0; l < 2; ++l) c->grid[l] = GridLevelDev();
     pool_free(c->d_fast_cbox, c->stream); pool_free(c->d_fast_clist, c->stream);
     c->d_fast_sbox = nullptr; c->d_fast_slist = nullptr; c->d_fast_cbox = nullptr; c->d_fast_clist = nullptr;
     c->fast_lists_dirty = true;
@@ -465,32 +454,82 @@ static int build_grid(sitb_ctx* c, double margin) {
     const double lmax = std::max(len[0], std::max(len[1], len[2]));
     const double eps = 1e-5 * lmax + 1e-9;
     const double margins[2] = {0.5 * margin, margin};
-    for (int l = 0; l < 2; ++l) {
-        const int rc = build_grid_level(c, g, margins[l] + eps, c->grid[l]);
-        if (rc != SITB_OK) { free_grid(c); return rc == SITB_E_LIMIT ? SITB_OK : rc; }   // absurdly large: keep the full walk
-        c->grid[l].margin = margins[l];
+    // Both levels in one sweep (sitb_tables.cu): a ballot mask per (box, 32 landmarks) and margin, the list lengths to the
+    // host for the prefix sums (the allocation needs the totals), then the lists are written from the masks -- no second
+    // round of distance tests, one device block, one round trip.
+    StageClock clk;
+    const size_t cells = (size_t)g[0] * g[1] * g[2];
+    const int chL = (c->L + 31) / 32, chS = (c->S + 31) / 32;
+    unsigned char* scratch = nullptr;
+    const size_t mask_bytes = sizeof(uint2) * cells * (size_t)(chL + chS);
+    CK(pool_alloc((void**)&scratch, mask_bytes + sizeof(unsigned) * 4 * cells, c->stream));
+    uint2* masksL = (uint2*)scratch;
+    uint2* masksS = masksL + cells * (size_t)chL;
+    unsigned* d_count = (unsigned*)(scratch + mask_bytes);         // [0, 2 cells): landmarks, levels 0 / 1; then sites
+    cudaError_t e = launch_grid_masks(c->cell, c->d_ideal_wrapped, c->d_va, c->d_radius, c->L, c->Lpad, c->NB, c->S, g[0], g[1], g[2],
+                                      margins[0] + eps, margins[1] + eps, masksL, d_count, c->stream);
+    if (e == cudaSuccess)
+        e = launch_grid_static_masks(c->cell, c->d_ideal_wrapped, c->d_rmax, c->S, g[0], g[1], g[2], margins[0] + eps,
+                                     margins[1] + eps, masksS, d_count + 2 * cells, c->stream);
+    std::vector<unsigned> ptr(4 * (cells + 1), 0u);                // four prefix arrays: ptr0, ptr1, sptr0, sptr1
+    {
+        std::vector<unsigned> cnt(4 * cells);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(cnt.data(), d_count, sizeof(unsigned) * 4 * cells, cudaMemcpyDeviceToHost, c->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+        if (e != cudaSuccess) { pool_free(scratch, c->stream); return fail(SITB_E_CUDA, "candidate grid (count): %s", cudaGetErrorString(e)); }
+        clk.lap("  grid: masks of both levels + counts D2H");
+        unsigned long long totals[4];
+        for (int a = 0; a < 4; ++a) {
+            unsigned long long total = 0;
+            unsigned* pa = ptr.data() + (size_t)a * (cells + 1);
+            for (size_t i = 0; i < cells; ++i) { pa[i] = (unsigned)total; total += cnt[(size_t)a * cells + i]; }
+            pa[cells] = (unsigned)total;
+            totals[a] = total;
+        }
+        if (totals[0] + totals[1] >= 0xFFFFFFFFull || totals[2] + totals[3] >= 0xFFFFFFFFull) {
+            pool_free(scratch, c->stream);
+            return SITB_OK;                                        // absurdly large: keep the full walk
+        }
+        c->grid[0].entries = totals[0]; c->grid[1].entries = totals[1];
+        c->grid[0].static_entries = totals[2]; c->grid[1].static_entries = totals[3];
     }
-    CK(cudaStreamSynchronize(c->stream));
+    const size_t nL0 = (size_t)c->grid[0].entries, nL1 = (size_t)c->grid[1].entries;
+    const size_t nS0 = (size_t)c->grid[0].static_entries, nS1 = (size_t)c->grid[1].static_entries;
+    const bool first_tier = c->fast_tables_ok && c->S <= 16000;
+    // block layout: 4 prefix arrays | (offset, count) boxes of the first tier | the lists (uint16)
+    size_t o = 0;
+    const size_t off_ptr = o;   o += sizeof(unsigned) * 4 * (cells + 1);
+    o = (o + 7) & ~(size_t)7;
+    const size_t off_sbox = o;  o += first_tier ? sizeof(uint2) * 2 * cells : 0;
+    const size_t off_list = o;  o += sizeof(uint16_t) * (nL0 + nL1 + nS0 + nS1 + (first_tier ? nS0 + nS1 : 0) + 8);
+    CK(pool_alloc((void**)&c->d_grid_block, o, c->stream));
+    unsigned* d_ptr = (unsigned*)(c->d_grid_block + off_ptr);
+    uint16_t* d_lists = (uint16_t*)(c->d_grid_block + off_list);
+    CK(cudaMemcpyAsync(d_ptr, ptr.data(), sizeof(unsigned) * ptr.size(), cudaMemcpyHostToDevice, c->stream));
+    c->grid[0].ptr = d_ptr;                       c->grid[1].ptr = d_ptr + (cells + 1);
+    c->grid[0].sptr = d_ptr + 2 * (cells + 1);    c->grid[1].sptr = d_ptr + 3 * (cells + 1);
+    c->grid[0].list = d_lists;                    c->grid[1].list = d_lists + nL0;
+    c->grid[0].slist = d_lists + nL0 + nL1;       c->grid[1].slist = d_lists + nL0 + nL1 + nS0;
+    if (first_tier) {
+        // first tier of the two-tier assign pass: both levels' static-site lists in one array (entries = 4 * site)
+        c->d_fast_slist = d_lists + nL0 + nL1 + nS0 + nS1;
+        c->d_fast_sbox = (uint2*)(c->d_grid_block + off_sbox);
+    }
+    CK(launch_grid_lists_from_masks(masksL, chL, (long long)cells, c->grid[0].ptr, c->grid[1].ptr, c->grid[0].list, c->grid[1].list,
+                                    nullptr, nullptr, c->stream));
+    CK(launch_grid_lists_from_masks(masksS, chS, (long long)cells, c->grid[0].sptr, c->grid[1].sptr, c->grid[0].slist,
+                                    c->grid[1].slist, c->d_fast_slist, c->d_fast_sbox, c->stream));
+    pool_free(scratch, c->stream);
+    CK(cudaStreamSynchronize(c->stream));          // (ptr is a temporary)
+    for (int l = 0; l < 2; ++l) c->grid[l].margin = margins[l];
     c->gx = g[0]; c->gy = g[1]; c->gz = g[2];
     c->n_grid_levels = 2;
-    if (c->fast_tables_ok && c->S <= 16000) {
-        // first tier of the two-tier assign pass: both levels' static-site lists in one array (entries = 4 * site)
-        const size_t cells = (size_t)g[0] * g[1] * g[2];
-        const size_t n0 = (size_t)c->grid[0].static_entries, n1 = (size_t)c->grid[1].static_entries;
-        std::vector<uint16_t> sl(n0 + n1 + 1);
-        CK(cudaMemcpy(sl.data(), c->grid[0].slist, sizeof(uint16_t) * n0, cudaMemcpyDeviceToHost));
-        CK(cudaMemcpy(sl.data() + n0, c->grid[1].slist, sizeof(uint16_t) * n1, cudaMemcpyDeviceToHost));
-        for (size_t i = 0; i < n0 + n1; ++i) sl[i] = (uint16_t)(4u * sl[i]);
-        std::vector<uint2> sbox(2 * cells);
-        for (int l = 0; l < 2; ++l)
-            for (size_t i = 0; i < cells; ++i)
-                sbox[l * cells + i] = make_uint2((unsigned)(l ? n0 : 0) + c->grid[l].h_sptr[i], c->grid[l].h_sptr[i + 1] - c->grid[l].h_sptr[i]);
-        CK(upload(&c->d_fast_slist, sl.data(), sl.size(), c->stream));
-        CK(upload(&c->d_fast_sbox, sbox.data(), sbox.size(), c->stream));
+    if (first_tier) {
         CK(pool_alloc((void**)&c->d_fast_cbox, sizeof(uint2) * 2 * cells, c->stream));
-        CK(pool_alloc((void**)&c->d_fast_clist, sizeof(unsigned) * (size_t)(c->grid[0].entries + c->grid[1].entries + 1), c->stream));
+        CK(pool_alloc((void**)&c->d_fast_clist, sizeof(unsigned) * (nL0 + nL1 + 1), c->stream));
         c->fast_lists_dirty = true;
     }
+    clk.lap("  grid: prefix sums, lists from the masks");
     return SITB_OK;
 }
 

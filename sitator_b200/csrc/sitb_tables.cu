@@ -79,32 +79,33 @@ cudaError_t launch_tables(const Cell& cell, const double* centers, const double*
 // frame with a static atom beyond the margin walks all landmarks as before.  One warp per box; lists
 // are in ascending internal landmark order, the same order the full walk produces.
 // (ideal = the static-lattice positions wrapped into the cell, Cartesian; q64 holds the cut-off RADII sqrt(Q) here)
-__global__ void k_grid_lists(Cell cell, const double* __restrict__ ideal, const ushort4* __restrict__ va,
+// Both margins are tested in one sweep: masks[box * n_chunks + chunk] = (ballot for margin0, ballot for margin1) over the
+// chunk's 32 landmarks, count[box] / count[cells + box] = list lengths.  margin0 <= margin1 (level 0 is a subset of level 1).
+__global__ void k_grid_masks(Cell cell, const double* __restrict__ ideal, const ushort4* __restrict__ va,
                              const double* __restrict__ q64, int L, int Lpad, int NB, int S, int gx, int gy, int gz,
-                             double margin, const unsigned* __restrict__ ptr, unsigned* __restrict__ count,
-                             uint16_t* __restrict__ list) {
+                             double margin0, double margin1, uint2* __restrict__ masks, unsigned* __restrict__ count) {
     const int lane = threadIdx.x & 31;
+    const long long cells = (long long)gx * gy * gz;
     const long long id = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    if (id >= (long long)gx * gy * gz) return;
+    if (id >= cells) return;
     const int iz = (int)(id % gz), iy = (int)((id / gz) % gy), ix = (int)(id / ((long long)gz * gy));
     const double len[3] = {cell.c[0], cell.c[4], cell.c[8]};
     const double inv_len[3] = {1.0 / len[0], 1.0 / len[1], 1.0 / len[2]};
     const double half[3] = {0.5 * len[0] / gx, 0.5 * len[1] / gy, 0.5 * len[2] / gz};
     const double mid[3] = {(2 * ix + 1) * half[0], (2 * iy + 1) * half[1], (2 * iz + 1) * half[2]};
     const int W = 4 * NB;
-    const unsigned base = ptr ? ptr[id] : 0u;
-    unsigned n = 0;
-    for (int k0 = 0; k0 < L; k0 += 32) {
-        const int k = k0 + lane;
-        bool in = k < L;
-        for (int blk = 0; blk < NB && in; ++blk) {
+    const int n_chunks = (L + 31) >> 5;
+    unsigned n0 = 0, n1 = 0;
+    for (int ch = 0; ch < n_chunks; ++ch) {
+        const int k = 32 * ch + lane;
+        bool in1 = k < L, in0 = in1;
+        for (int blk = 0; blk < NB && in1; ++blk) {
             const ushort4 vv = va[(size_t)blk * Lpad + k];
             const unsigned vs[4] = {vv.x, vv.y, vv.z, vv.w};
-            for (int h = 0; h < 4 && in; ++h) {
+            for (int h = 0; h < 4 && in1; ++h) {
                 if (vs[h] == (unsigned)S) continue;
                 const double R = q64[(size_t)k * W + 4 * blk + h];
-                if (!(R >= 0.0)) { in = false; break; }           // degenerate landmark: never non-zero
-                const double r = R + margin;
+                if (!(R >= 0.0)) { in1 = false; break; }          // degenerate landmark: never non-zero
                 double d2 = 0.0;
 #pragma unroll
                 for (int d = 0; d < 3; ++d) {
@@ -113,40 +114,41 @@ __global__ void k_grid_lists(Cell cell, const double* __restrict__ ideal, const 
                     const double a = fmax(fabs(x) - half[d], 0.0);
                     d2 += a * a;
                 }
-                if (d2 > r * r) in = false;
+                if (d2 > (R + margin1) * (R + margin1)) in1 = false;
+                if (d2 > (R + margin0) * (R + margin0)) in0 = false;
             }
         }
-        const unsigned m = __ballot_sync(0xffffffffu, in);
-        if (ptr && in) list[base + n + __popc(m & lanemask_lt())] = (uint16_t)k;
-        n += __popc(m);
+        in0 = in0 && in1;
+        const unsigned m0 = __ballot_sync(0xffffffffu, in0), m1 = __ballot_sync(0xffffffffu, in1);
+        if (lane == 0) masks[id * n_chunks + ch] = make_uint2(m0, m1);
+        n0 += __popc(m0); n1 += __popc(m1);
     }
-    if (!ptr && lane == 0) count[id] = n;
+    if (lane == 0) { count[id] = n0; count[cells + id] = n1; }
 }
 
 // The same grid for the static atoms: a box lists every static-lattice site that is a vertex of one of the
 // box's candidate landmarks, i.e. lies within rmax[s] + margin of the box (rmax[s] = the largest cut-off
 // radius of any landmark vertex on s).  K1 then computes screen distances for those sites only.
-__global__ void k_grid_static_lists(Cell cell, const double* __restrict__ ideal, const double* __restrict__ rmax, int S,
-                                    int gx, int gy, int gz, double margin, const unsigned* __restrict__ ptr,
-                                    unsigned* __restrict__ count, uint16_t* __restrict__ list) {
+__global__ void k_grid_static_masks(Cell cell, const double* __restrict__ ideal, const double* __restrict__ rmax, int S,
+                                    int gx, int gy, int gz, double margin0, double margin1, uint2* __restrict__ masks,
+                                    unsigned* __restrict__ count) {
     const int lane = threadIdx.x & 31;
+    const long long cells = (long long)gx * gy * gz;
     const long long id = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    if (id >= (long long)gx * gy * gz) return;
+    if (id >= cells) return;
     const int iz = (int)(id % gz), iy = (int)((id / gz) % gy), ix = (int)(id / ((long long)gz * gy));
     const double len[3] = {cell.c[0], cell.c[4], cell.c[8]};
     const double inv_len[3] = {1.0 / len[0], 1.0 / len[1], 1.0 / len[2]};
     const double half[3] = {0.5 * len[0] / gx, 0.5 * len[1] / gy, 0.5 * len[2] / gz};
     const double mid[3] = {(2 * ix + 1) * half[0], (2 * iy + 1) * half[1], (2 * iz + 1) * half[2]};
-    const unsigned base = ptr ? ptr[id] : 0u;
-    unsigned n = 0;
-    for (int s0 = 0; s0 < S; s0 += 32) {
-        const int s = s0 + lane;
-        bool in = s < S;
-        if (in) {
+    const int n_chunks = (S + 31) >> 5;
+    unsigned n0 = 0, n1 = 0;
+    for (int ch = 0; ch < n_chunks; ++ch) {
+        const int s = 32 * ch + lane;
+        bool in0 = false, in1 = false;
+        if (s < S) {
             const double r = rmax[s];
-            if (!(r >= 0.0)) {
-                in = false;                                       // not a vertex of any landmark
-            } else {
+            if (r >= 0.0) {                                       // (< 0: not a vertex of any landmark)
                 double d2 = 0.0;
 #pragma unroll
                 for (int d = 0; d < 3; ++d) {
@@ -155,33 +157,76 @@ __global__ void k_grid_static_lists(Cell cell, const double* __restrict__ ideal,
                     const double a = fmax(fabs(x) - half[d], 0.0);
                     d2 += a * a;
                 }
-                in = !(d2 > (r + margin) * (r + margin));
+                in1 = !(d2 > (r + margin1) * (r + margin1));
+                in0 = in1 && !(d2 > (r + margin0) * (r + margin0));
             }
         }
-        const unsigned m = __ballot_sync(0xffffffffu, in);
-        if (ptr && in) list[base + n + __popc(m & lanemask_lt())] = (uint16_t)s;
-        n += __popc(m);
+        const unsigned m0 = __ballot_sync(0xffffffffu, in0), m1 = __ballot_sync(0xffffffffu, in1);
+        if (lane == 0) masks[id * n_chunks + ch] = make_uint2(m0, m1);
+        n0 += __popc(m0); n1 += __popc(m1);
     }
-    if (!ptr && lane == 0) count[id] = n;
+    if (lane == 0) { count[id] = n0; count[cells + id] = n1; }
 }
 
-cudaError_t launch_grid_static_lists(const Cell& cell, const double* ideal, const double* rmax, int S, int gx, int gy,
-                                     int gz, double margin, const unsigned* ptr, unsigned* count, uint16_t* list,
+// masks -> lists (ascending index, as the full walk produces them), one warp per box.  cat_list / cat_box (optional): both
+// levels in one array with entries 4 * index and (offset, count) per box -- the form the two-tier first tier reads.
+__global__ void k_grid_lists_from_masks(const uint2* __restrict__ masks, int n_chunks, long long cells,
+                                        const unsigned* __restrict__ ptr0, const unsigned* __restrict__ ptr1,
+                                        uint16_t* __restrict__ list0, uint16_t* __restrict__ list1,
+                                        uint16_t* __restrict__ cat_list, uint2* __restrict__ cat_box) {
+    const int lane = threadIdx.x & 31;
+    const long long id = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (id >= cells) return;
+    const unsigned b0 = ptr0[id], b1 = ptr1[id];
+    const unsigned cat1 = ptr0[cells];                            // level 1 follows all of level 0
+    unsigned n0 = 0, n1 = 0;
+    for (int ch = 0; ch < n_chunks; ++ch) {
+        const uint2 m = masks[id * n_chunks + ch];
+        const unsigned k = 32u * ch + lane;
+        if ((m.x >> lane) & 1u) {
+            const unsigned at = b0 + n0 + __popc(m.x & lanemask_lt());
+            list0[at] = (uint16_t)k;
+            if (cat_list) cat_list[at] = (uint16_t)(4u * k);
+        }
+        if ((m.y >> lane) & 1u) {
+            const unsigned at = b1 + n1 + __popc(m.y & lanemask_lt());
+            list1[at] = (uint16_t)k;
+            if (cat_list) cat_list[cat1 + at] = (uint16_t)(4u * k);
+        }
+        n0 += __popc(m.x); n1 += __popc(m.y);
+    }
+    if (cat_box && lane == 0) {
+        cat_box[id] = make_uint2(b0, n0);
+        cat_box[cells + id] = make_uint2(cat1 + b1, n1);
+    }
+}
+
+cudaError_t launch_grid_static_masks(const Cell& cell, const double* ideal, const double* rmax, int S, int gx, int gy,
+                                     int gz, double margin0, double margin1, uint2* masks, unsigned* count,
                                      cudaStream_t stream) {
     const long long cells = (long long)gx * gy * gz;
     const int wpb = 8;
-    k_grid_static_lists<<<(unsigned)((cells + wpb - 1) / wpb), wpb * 32, 0, stream>>>(cell, ideal, rmax, S, gx, gy, gz, margin,
-                                                                                 ptr, count, list);
+    k_grid_static_masks<<<(unsigned)((cells + wpb - 1) / wpb), wpb * 32, 0, stream>>>(cell, ideal, rmax, S, gx, gy, gz, margin0,
+                                                                                 margin1, masks, count);
     return cudaGetLastError();
 }
 
-cudaError_t launch_grid_lists(const Cell& cell, const double* ideal, const ushort4* va, const double* q64, int L,
-                              int Lpad, int NB, int S, int gx, int gy, int gz, double margin, const unsigned* ptr,
-                              unsigned* count, uint16_t* list, cudaStream_t stream) {
+cudaError_t launch_grid_masks(const Cell& cell, const double* ideal, const ushort4* va, const double* q64, int L,
+                              int Lpad, int NB, int S, int gx, int gy, int gz, double margin0, double margin1, uint2* masks,
+                              unsigned* count, cudaStream_t stream) {
     const long long cells = (long long)gx * gy * gz;
     const int wpb = 8;
-    k_grid_lists<<<(unsigned)((cells + wpb - 1) / wpb), wpb * 32, 0, stream>>>(cell, ideal, va, q64, L, Lpad, NB, S, gx, gy,
-                                                                          gz, margin, ptr, count, list);
+    k_grid_masks<<<(unsigned)((cells + wpb - 1) / wpb), wpb * 32, 0, stream>>>(cell, ideal, va, q64, L, Lpad, NB, S, gx, gy,
+                                                                          gz, margin0, margin1, masks, count);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_grid_lists_from_masks(const uint2* masks, int n_chunks, long long cells, const unsigned* ptr0,
+                                         const unsigned* ptr1, uint16_t* list0, uint16_t* list1, uint16_t* cat_list,
+                                         uint2* cat_box, cudaStream_t stream) {
+    const int wpb = 8;
+    k_grid_lists_from_masks<<<(unsigned)((cells + wpb - 1) / wpb), wpb * 32, 0, stream>>>(masks, n_chunks, cells, ptr0, ptr1,
+                                                                                     list0, list1, cat_list, cat_box);
     return cudaGetLastError();
 }
 
