@@ -134,6 +134,13 @@ int sitb_pass_stats(sitb_ctx* ctx, int64_t frame_begin, int64_t n, uint64_t* dev
 int sitb_pass_stats_cached(sitb_ctx* ctx, int64_t frame_begin, int64_t n, uint64_t* dev_seen, double* dev_gram_upper,
                            uint64_t* dev_row_ptr, uint16_t* dev_pool_k, double* dev_pool_v, uint64_t* dev_cursor,
                            uint64_t capacity);
+/* The same with the rows in row order: a row of at most slot_entries entries is stored at offset
+ * (frame_begin * n_mobile + row) * slot_entries -- fixed slots, so the passes over the cached rows stream them
+ * sequentially (rows scattered over the pool cost a DRAM page each); longer rows take their space from *dev_cursor,
+ * which the caller initialises to (resident frames * n_mobile) * slot_entries.  dev_row_ptr as above. */
+int sitb_pass_stats_slotted(sitb_ctx* ctx, int64_t frame_begin, int64_t n, uint64_t* dev_seen, double* dev_gram_upper,
+                            uint64_t* dev_row_ptr, uint16_t* dev_pool_k, double* dev_pool_v, uint64_t* dev_cursor,
+                            uint64_t capacity, int32_t slot_entries);
 /* The Gram of rows cached by sitb_pass_stats_cached (pass dev_gram_upper = NULL there): dev_gram_upper [L][L] += the
  * upper triangle of sum_rows lv^T lv over the n_frames * n_mobile cached rows, accumulated per (mobile atom, window
  * of consecutive frames) in shared memory before it touches the matrix.  Fails with SITB_E_CUDA

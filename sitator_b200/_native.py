@@ -63,6 +63,7 @@ SIGNATURES = {
     "sitb_fill_dense_frames": (C.c_int, [_P, _P, C.c_int64, _P, C.c_int32]),
     "sitb_pass_stats": (C.c_int, [_P, C.c_int64, C.c_int64, _P, _P]),
     "sitb_pass_stats_cached": (C.c_int, [_P, C.c_int64, C.c_int64, _P, _P, _P, _P, _P, _P, C.c_uint64]),
+    "sitb_pass_stats_slotted": (C.c_int, [_P, C.c_int64, C.c_int64, _P, _P, _P, _P, _P, _P, C.c_uint64, C.c_int32]),
     "sitb_gram_from_cached": (C.c_int, [_P, _P, _P, _P, C.c_int64, _P]),
     "sitb_gram_words_from_cached": (C.c_int, [_P, _P, _P, _P, C.c_int64, _P]),
     "sitb_gram_words_finish": (C.c_int, [C.c_int, _P, C.c_int32, _P, _P]),

@@ -143,6 +143,11 @@ struct sitb_ctx {
     unsigned long long* d_two_tier = nullptr; // [0] list length, [1 .. RECHECK_SLOTS] reason counters
     size_t recheck_rows_cap = 0, recheck_frames_cap = 0;
     int assign_mode = 0;                      // 0 exact, 1 two-tier where the shape allows it
+    // the last sitb_pass_stats_slotted: rows in these buffers live in row-ordered slots of row_slot entries (the passes
+    // over cached rows then load the entries without waiting for the row pointers)
+    const void* slot_pool_k = nullptr;
+    const void* slot_row_ptr = nullptr;       // row 0 of the shard
+    int row_slot = 0;
 };
 
 static void free_ctx(sitb_ctx* c) {
@@ -988,28 +993,47 @@ cudaError_t launch_assign_sparse(const unsigned long long* row_ptr, const uint16
                                  long long n_rows, long long row0, int L, const int* cid, const double* cw,
                                  int n_clusters, double thr, long long* labels, double* confs,
                                  unsigned long long* counts, unsigned long long* best, double* rep, double* rep_w,
-                                 unsigned long long* site_best, int n_sms, cudaStream_t st, const long long* row_list = nullptr,
-                                 const unsigned long long* n_list = nullptr);
+                                 unsigned long long* site_best, int n_sms, cudaStream_t st, const long long* row_list,
+                                 const unsigned long long* n_list, int slot);
 cudaError_t launch_relabel_select(long long* labels, long long n_rows, const int* remap, long long* row_list,
                                   unsigned long long* n_list, int n_sms, cudaStream_t st);
 cudaError_t launch_sparse_row_norm2(const unsigned long long* row_ptr, const double* pv, long long n_rows,
                                     const long long* rows, int n, double* out, cudaStream_t st);
 }
 
-extern "C" int sitb_pass_stats_cached(sitb_ctx* c, int64_t begin, int64_t n, uint64_t* dev_seen, double* dev_gram,
-                                      uint64_t* dev_row_ptr, uint16_t* dev_pool_k, double* dev_pool_v,
-                                      uint64_t* dev_cursor, uint64_t capacity) {
+static int pass_stats_cached(sitb_ctx* c, int64_t begin, int64_t n, uint64_t* dev_seen, double* dev_gram,
+                             uint64_t* dev_row_ptr, uint16_t* dev_pool_k, double* dev_pool_v,
+                             uint64_t* dev_cursor, uint64_t capacity, int32_t slot, const char* who) {
     FillParams p;
-    int rc = base_params(c, begin, n, p, "sitb_pass_stats_cached");
+    int rc = base_params(c, begin, n, p, who);
     if (rc) return rc;
     if (!dev_seen || !dev_row_ptr || !dev_pool_k || !dev_pool_v || !dev_cursor)      // dev_gram may be null
-        return fail(SITB_E_INVALID, "sitb_pass_stats_cached: null output");
+        return fail(SITB_E_INVALID, "%s: null output", who);
+    if (slot < 0 || slot > ENTRY_CAP) return fail(SITB_E_INVALID, "%s: slot_entries %d outside [0, %d]", who, slot, ENTRY_CAP);
     CK(cudaSetDevice(c->device));
     p.seen = (unsigned long long*)dev_seen; p.gram = dev_gram;
     p.sparse_ptr = (unsigned long long*)dev_row_ptr; p.sparse_k = dev_pool_k; p.sparse_v = dev_pool_v;
     p.sparse_cursor = (unsigned long long*)dev_cursor; p.sparse_capacity = capacity;
+    p.sparse_slot = (unsigned)slot; p.sparse_row_base = (long long)begin * c->M;
+    c->row_slot = slot;
+    c->slot_pool_k = slot ? dev_pool_k : nullptr;
+    c->slot_row_ptr = slot ? dev_row_ptr - (size_t)begin * c->M : nullptr;
     CK(launch_fill(p, MODE_STATS, c->n_sms, c->stream));
     return SITB_OK;
+}
+
+extern "C" int sitb_pass_stats_cached(sitb_ctx* c, int64_t begin, int64_t n, uint64_t* dev_seen, double* dev_gram,
+                                      uint64_t* dev_row_ptr, uint16_t* dev_pool_k, double* dev_pool_v,
+                                      uint64_t* dev_cursor, uint64_t capacity) {
+    return pass_stats_cached(c, begin, n, dev_seen, dev_gram, dev_row_ptr, dev_pool_k, dev_pool_v, dev_cursor, capacity, 0,
+                             "sitb_pass_stats_cached");
+}
+
+extern "C" int sitb_pass_stats_slotted(sitb_ctx* c, int64_t begin, int64_t n, uint64_t* dev_seen, double* dev_gram,
+                                       uint64_t* dev_row_ptr, uint16_t* dev_pool_k, double* dev_pool_v,
+                                       uint64_t* dev_cursor, uint64_t capacity, int32_t slot_entries) {
+    return pass_stats_cached(c, begin, n, dev_seen, dev_gram, dev_row_ptr, dev_pool_k, dev_pool_v, dev_cursor, capacity,
+                             slot_entries, "sitb_pass_stats_slotted");
 }
 
 extern "C" int sitb_assign_sparse(sitb_ctx* c, const uint64_t* dev_row_ptr, const uint16_t* dev_pool_k,
@@ -1023,7 +1047,8 @@ extern "C" int sitb_assign_sparse(sitb_ctx* c, const uint64_t* dev_row_ptr, cons
     CK(launch_assign_sparse((const unsigned long long*)dev_row_ptr, dev_pool_k, dev_pool_v, n_rows, row0, c->L,
                             c->d_cid_orig, c->d_cw_orig, c->n_clusters, thr, (long long*)labels, confs,
                             (unsigned long long*)counts, (unsigned long long*)best, rep, rep_w,
-                            (unsigned long long*)site_best, c->n_sms, c->stream));
+                            (unsigned long long*)site_best, c->n_sms, c->stream, nullptr, nullptr,
+                            (dev_pool_k == c->slot_pool_k && dev_row_ptr == c->slot_row_ptr) ? c->row_slot : 0));
     return SITB_OK;
 }
 
@@ -1061,7 +1086,8 @@ extern "C" int sitb_assign_sparse_rows(sitb_ctx* c, const uint64_t* dev_row_ptr,
                             c->d_cid_orig, c->d_cw_orig, c->n_clusters, thr, (long long*)labels, confs,
                             (unsigned long long*)counts, (unsigned long long*)best, rep, rep_w,
                             (unsigned long long*)site_best, c->n_sms, c->stream, (const long long*)dev_row_list,
-                            (const unsigned long long*)dev_n_list));
+                            (const unsigned long long*)dev_n_list,
+                            (dev_pool_k == c->slot_pool_k && dev_row_ptr == c->slot_row_ptr) ? c->row_slot : 0));
     return SITB_OK;
 }
 

@@ -650,7 +650,12 @@ __global__ void __launch_bounds__(DIAG ? SITB_K1_WARPS * 32 : 512) k_fill(const 
                 if ((MODE == MODE_STATS || MODE == MODE_STAGE) && p.sparse_ptr) {
                     // keep the row in compressed form: later passes read ~250 B instead of recomputing it
                     unsigned long long off = 0;
-                    if (lane == 0 && nent > 0) {                   // (an all-zero row needs no space: offset 0, count 0)
+                    const bool slotted = p.sparse_slot && (unsigned)nent <= p.sparse_slot;
+                    if (slotted) {
+                        // row-ordered fixed slots: the later passes stream them in order (rows scattered over the pool cost
+                        // a DRAM page per row: those passes ran at a fifth of the HBM rate)
+                        off = (unsigned long long)(p.sparse_row_base + row_local) * p.sparse_slot;
+                    } else if (lane == 0 && nent > 0) {            // (an all-zero row needs no space: offset 0, count 0)
                         if (*pool_left < (unsigned)nent) {         // next slice (the rest of the old one stays unused)
                             *pool_off = atomicAdd(p.sparse_cursor, (unsigned long long)POOL_SLICE);
                             *pool_left = POOL_SLICE;
@@ -659,7 +664,7 @@ __global__ void __launch_bounds__(DIAG ? SITB_K1_WARPS * 32 : 512) k_fill(const 
                         *pool_off = off + (unsigned long long)nent;
                         *pool_left -= (unsigned)nent;
                     }
-                    off = __shfl_sync(0xffffffffu, off, 0);
+                    if (!slotted) off = __shfl_sync(0xffffffffu, off, 0);
                     if (off + (unsigned long long)nent <= p.sparse_capacity) {
                         for (int e = lane; e < nent; e += 32) { p.sparse_k[off + e] = ek[e]; p.sparse_v[off + e] = ev[e]; }
                         if (lane == 0) p.sparse_ptr[row_local] = (off << 8) | (unsigned long long)nent;

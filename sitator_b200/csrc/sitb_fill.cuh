@@ -102,6 +102,8 @@ struct FillParams {
     double* sparse_v;
     unsigned long long* sparse_cursor;
     unsigned long long sparse_capacity;
+    unsigned sparse_slot;            // > 0: rows of at most this many entries live in fixed slots, row-ordered:
+    long long sparse_row_base;       //   offset (sparse_row_base + row) * sparse_slot; the cursor only serves longer rows
     // MODE_ASSIGN
     const int* cid;              // [L] cluster of landmark (internal numbering), -1 none
     const double* cw;            // [L] centre weight of landmark (internal numbering)

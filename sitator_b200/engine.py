@@ -318,23 +318,30 @@ class LandmarkEngine(object):
         if gram is None and want_gram:
             # gram_words: the deterministic integer form (sitb_gram_words_from_cached), finished by gram_words_finish
             gram = self._zeros((2 * (self.L + 1), self.L), torch.int64) if gram_words else self._zeros((self.L, self.L), torch.float64)
+        # Rows of up to ROW_SLOT entries live in fixed, row-ordered slots (the passes over the cached rows then stream
+        # them; scattered over a pool they cost a DRAM page per row); longer rows take space behind the slots.
+        slot = self.ROW_SLOT
+        overflow_per_row = 0.02 * entries_per_row
         while True:
-            # (warps reserve the pool in slices of 256 entries and leave the tail of a slice unused at the end of a launch)
+            # (warps reserve the overflow space in slices of 256 entries and leave the tail of a slice unused)
             step = self.upload_chunk_frames() or self.n_frames
             n_launches = (self.n_frames + step - 1) // step
-            cap = int(n_rows * entries_per_row) + 1024 + 256 * 32 * self.n_sms * n_launches
+            base = n_rows * slot
+            cap = base + int(n_rows * overflow_per_row) + 1024 + 256 * 32 * self.n_sms * n_launches
+            cursor = self._empty((1,), torch.int64)
+            cursor.fill_(base)
             rows = SparseRows(self._empty((n_rows,), torch.int64), self._empty((cap,), torch.int16),
-                              self._empty((cap,), torch.float64), self._zeros((1,), torch.int64), cap, n_rows,
+                              self._empty((cap,), torch.float64), cursor, cap, n_rows,
                               self.frame0 * self.M)
             seen_try = seen.clone()
             gram_try = None if gram_from_rows else gram.clone()
             # launched per upload chunk: each launch waits only for its own chunk of the host -> device copy
             for b in range(0, self.n_frames, step):
                 nb = min(step, self.n_frames - b)
-                _native.check(self._lib.sitb_pass_stats_cached(
+                _native.check(self._lib.sitb_pass_stats_slotted(
                     self._ctx, b, nb, self._ptr(seen_try), self._ptr(gram_try),
                     C.c_void_p(rows.ptr.data_ptr() + 8 * b * self.M), self._ptr(rows.k), self._ptr(rows.v),
-                    self._ptr(rows.cursor), cap))
+                    self._ptr(rows.cursor), cap, slot))
             used = int(rows.cursor.item())
             if used <= cap:
                 seen.copy_(seen_try)
@@ -348,7 +355,7 @@ class LandmarkEngine(object):
                     gram.copy_(gram_try)
                 rows.used = used
                 return seen, gram, rows
-            entries_per_row = used / float(n_rows) * 1.05 + 1     # exact requirement is known now
+            overflow_per_row = (used - base) / float(n_rows) * 1.05 + 1     # exact requirement is known now
             self.reset_status()
 
     def assign_sparse(self, rows, threshold, labels=None, confs=None, counts=None, best=None, rep=None, rep_w=None,
@@ -380,6 +387,8 @@ class LandmarkEngine(object):
         assert cid.shape == (self.L,) and w.shape == (self.L,)
         _native.check(self._lib.sitb_set_centers(self._ctx, cid.ctypes.data, w.ctypes.data, int(n_clusters)))
         self.n_clusters = int(n_clusters)
+
+    ROW_SLOT = 32          # entries per fixed slot of a cached row (pass_stats_cached)
 
     TWO_TIER_REASONS = ("frame", "support", "margin", "threshold", "long", "rows")
 
