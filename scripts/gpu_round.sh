@@ -30,7 +30,8 @@ timeout 600 ncu --set full --clock-control none --import-source on -k regex:k_as
 ncu -i $OUT/${TAG}_k1_full.ncu-rep --page raw --csv > $OUT/${TAG}_k1_ncu_full.csv 2>/dev/null || true
 
 echo "== 5. other shapes + dotprod report"
-timeout 600 python scripts/config_sweep.py > $OUT/${TAG}_config_sweep.json 2> $OUT/${TAG}_config_sweep.err || true
+timeout 600 python scripts/config_sweep.py > $OUT/${TAG}_config_sweep.log 2> $OUT/${TAG}_config_sweep.err || true
+cp $OUT/config_sweep.json $OUT/${TAG}_config_sweep.json 2>/dev/null || true      # (stdout is one JSON line per shape; the file is the list)
 timeout 300 python scripts/dotprod_report.py > $OUT/${TAG}_dotprod.json 2> $OUT/${TAG}_dotprod.err || true
 timeout 120 python scripts/e2e_phases.py 100000 $OUT/${TAG}_e2e_1gpu_phases.json > $OUT/${TAG}_e2e_1gpu_phases.txt 2>&1 || true
 ls -la $OUT | tail -n 20
