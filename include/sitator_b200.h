@@ -160,7 +160,9 @@ int sitb_gram_words_from_cached(sitb_ctx* ctx, const uint64_t* dev_row_ptr, cons
                                 const double* dev_pool_v, int64_t n_frames, int64_t* dev_gram_words);
 int sitb_gram_words_finish(int device, const int64_t* dev_gram_words, int32_t n_landmarks, double* dev_gram_upper,
                            void* cuda_stream);
-/* sitb_pass_assign over rows cached by sitb_pass_stats_cached (same outputs, same semantics); row0 = global
+/* sitb_pass_assign over rows cached by sitb_pass_stats_cached / sitb_pass_stats_slotted (same outputs, same
+ * semantics; given the buffers of the context's last sitb_pass_stats_slotted call with dev_row_ptr = the shard's row 0,
+ * the entry loads use the slot layout and do not wait for the row pointers); row0 = global
  * index of the first row.  The later passes of the clustering plugin (cluster/mcl.py:81-83, :98-122) stream the
  * compressed rows instead of recomputing them. */
 int sitb_assign_sparse(sitb_ctx* ctx, const uint64_t* dev_row_ptr, const uint16_t* dev_pool_k, const double* dev_pool_v,

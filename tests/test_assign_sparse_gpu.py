@@ -126,3 +126,57 @@ def test_assign_sparse_against_numpy(case):
             want_w[c] = confs[mine].sum()
         assert np.max(np.abs(rep.cpu().numpy() - want_rep)) < 1e-9
         assert np.max(np.abs(rep_w.cpu().numpy() - want_w)) < 1e-9
+
+
+def test_slot_layout_path_equals_pool_path():
+    """Rows written by the slotted fill pass are read through the slot path (vector loads at 32 * row, entries beyond
+    the row's count masked); the same buffers under other addresses go through the generic path (offset from the row
+    pointer).  The two paths deal the entries to the lanes differently, so sums may differ in the last bits: labels, counts
+    and the rows of the tables must agree, values to rounding."""
+    import torch
+    from sitator_b200.engine import SparseRows, new_best_table
+    system, cfg = syn.make_config("llzo")
+    eng = U.engine_for(system)
+    frames = system.trajectory(300, seed=11)
+    eng.set_frames(frames)
+    eng.reset_status()
+    seen, gram, rows = eng.pass_stats_cached(want_gram=False)
+    L = eng.L
+    rng = np.random.default_rng(5)
+    n_c = 40
+    cid = rng.integers(-1, n_c, size=L).astype(np.int32)
+    w = rng.standard_normal(L)
+    w[cid < 0] = 0.0
+    eng.set_centers(cid, w, n_c)
+    ptr = rows.ptr.cpu().numpy().view(np.uint64)
+    cnt = (ptr & np.uint64(0xFF)).astype(np.int64)
+    off = (ptr >> np.uint64(8)).astype(np.int64)
+    short = cnt <= eng.ROW_SLOT
+    assert np.array_equal(off[short], np.arange(rows.n_rows)[short] * eng.ROW_SLOT)       # the slot layout itself
+    assert np.all(off[~short] >= rows.n_rows * eng.ROW_SLOT)
+    # poison what lies beyond every short row's count: the slot path must not let it through
+    k_h = rows.k.cpu().numpy().copy(); v_h = rows.v.cpu().numpy().copy()
+    for r in np.nonzero(short)[0][:2000]:
+        k_h[off[r] + cnt[r]: off[r] + eng.ROW_SLOT] = -1            # landmark 65535
+        v_h[off[r] + cnt[r]: off[r] + eng.ROW_SLOT] = np.nan
+    rows.k.copy_(torch.as_tensor(k_h, device=eng.device)); rows.v.copy_(torch.as_tensor(v_h, device=eng.device))
+    clone = SparseRows(rows.ptr.clone(), rows.k.clone(), rows.v.clone(), None, rows.capacity, rows.n_rows, rows.row0)
+
+    def run(rr):
+        out = dict(labels=torch.full((rr.n_rows,), -7, dtype=torch.int64, device=eng.device),
+                   confs=torch.full((rr.n_rows,), -7.0, dtype=torch.float64, device=eng.device),
+                   counts=torch.zeros((n_c,), dtype=torch.int64, device=eng.device), best=new_best_table(n_c, eng.device),
+                   site_best=new_best_table(n_c, eng.device), rep=torch.zeros((n_c, L), dtype=torch.float64, device=eng.device),
+                   rep_w=torch.zeros((n_c,), dtype=torch.float64, device=eng.device))
+        eng.assign_sparse(rr, 0.3, **out)
+        return {k: v.cpu().numpy() for k, v in out.items()}
+
+    a, b = run(rows), run(clone)
+    assert (a["labels"] >= 0).sum() > 100 and (a["labels"] < 0).sum() > 0
+    assert np.array_equal(a["labels"], b["labels"]) and np.array_equal(a["counts"], b["counts"])
+    assert np.allclose(a["confs"], b["confs"], rtol=1e-13, atol=0.0)
+    for key in ("best", "site_best"):
+        va, vb = a[key][:n_c].view(np.float64), b[key][:n_c].view(np.float64)
+        assert np.allclose(va, vb, rtol=1e-13, atol=0.0), key
+        assert np.array_equal(a[key][n_c:2 * n_c], b[key][n_c:2 * n_c]), key
+    assert np.allclose(a["rep"], b["rep"], rtol=1e-12, atol=1e-12) and np.allclose(a["rep_w"], b["rep_w"], rtol=1e-12)
