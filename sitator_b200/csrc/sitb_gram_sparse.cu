@@ -10,7 +10,8 @@
 //     3. X^T X on the FP64 tensor cores (mma.sync m8n8k4.f64, 8x8 tiles of the upper triangle, K = the 16 frames)
 //     4. add the non-zero entries of the tiles into G straight from the accumulator registers:
 //        ~35 atomics per row instead of 253, and ~50 instructions per row instead of ~300
-//   windows whose union exceeds GW_CAP slots (an atom in transit through many sites) add directly.
+//   a window whose union exceeds GW_CAP slots (an atom in transit through many sites: 11 % of the LLZO windows) is
+//   split into halves, recursively, each handled the same way; only a single row beyond GW_CAP entries adds directly.
 // The sums are the same FP64 products in a different association; G is exact to rounding either way.
 //
 // Deterministic accumulation (EXACT = true, the default of the clustering plugin): FP64 atomics add in arrival
@@ -131,10 +132,7 @@ k_gram_windows(const unsigned long long* __restrict__ row_ptr, const uint16_t* _
             my_off = e >> 8; my_n = (int)(e & 0xFFull);
         }
         const bool long_rows = __any_sync(0xffffffffu, my_n > 32);
-        // 1. union bitmap (the first 32 entries of all rows are fetched together; longer rows are rare)
-        for (int w = lane; w < words; w += 32) bits[w] = 0u;
-        for (int i = lane; i < GW_T * GW_STRIDE; i += 32) X[i] = 0.0;
-        __syncwarp();
+        // the first 32 entries of all rows are fetched together (longer rows are rare)
         unsigned kk[GW_T];
 #pragma unroll
         for (int i = 0; i < GW_T; ++i) {
@@ -142,96 +140,114 @@ k_gram_windows(const unsigned long long* __restrict__ row_ptr, const uint16_t* _
             const int n = __shfl_sync(0xffffffffu, my_n, i);
             kk[i] = (lane < n) ? (unsigned)pk[off + lane] : 0xFFFFFFFFu;
         }
+        // Segments of the window, depth first: the whole window if its landmarks fit GW_CAP slots, else its halves, their
+        // halves, ... (an atom in transit between sites: 11 % of the 16-frame windows at the LLZO shape exceed 48 slots,
+        // 1 % of the 4-frame ones).  Adding such a window's rows pair by pair instead cost 253 atomics per row and was a
+        // third of the kernel's atomics.  The partition depends on the window's data alone.
+        int lo = 0, len = GW_T;
+        while (lo < nf) {
+            const int hi = lo + len;
+            // 1. union bitmap of the segment's rows
+            for (int w = lane; w < words; w += 32) bits[w] = 0u;
+            __syncwarp();
 #pragma unroll
-        for (int i = 0; i < GW_T; ++i)
-            if (kk[i] != 0xFFFFFFFFu) atomicOr(&bits[kk[i] >> 5], 1u << (kk[i] & 31u));
-        if (long_rows) {
-            for (int i = 0; i < nf; ++i) {
-                const unsigned long long off = __shfl_sync(0xffffffffu, my_off, i);
-                const int n = __shfl_sync(0xffffffffu, my_n, i);
-                for (int e = 32 + lane; e < n; e += 32) {
-                    const unsigned k = pk[off + e];
-                    atomicOr(&bits[k >> 5], 1u << (k & 31u));
-                }
-            }
-        }
-        __syncwarp();
-        // slot offsets: exclusive prefix of the words' popcounts
-        int carry = 0;
-        for (int w0 = 0; w0 < words; w0 += 32) {
-            const int w = w0 + lane;
-            const int c = (w < words) ? __popc(bits[w]) : 0;
-            int incl = c;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const int v = __shfl_up_sync(0xffffffffu, incl, o);
-                if (lane >= o) incl += v;
-            }
-            if (w < words) wofs[w] = (uint16_t)(carry + incl - c);
-            carry += __shfl_sync(0xffffffffu, incl, 31);
-        }
-        const int u = carry;
-        __syncwarp();
-        if (u > GW_CAP) {
-            for (int i = 0; i < nf; ++i)
-                gram_row_direct<EXACT>(pk, pv, __shfl_sync(0xffffffffu, my_off, i), __shfl_sync(0xffffffffu, my_n, i), lane, L, gram);
-            continue;
-        }
-        for (int w = lane; w < words; w += 32) {
-            unsigned b = bits[w];
-            int s = wofs[w];
-            while (b) { ids[s++] = (uint16_t)(w * 32 + __ffs(b) - 1); b &= b - 1u; }
-        }
-        // 2. X[row][slot] = value
-#pragma unroll
-        for (int i = 0; i < GW_T; ++i) {
-            const unsigned long long off = __shfl_sync(0xffffffffu, my_off, i);
-            if (kk[i] != 0xFFFFFFFFu) {
-                const unsigned k = kk[i];
-                const int s = wofs[k >> 5] + __popc(bits[k >> 5] & ((1u << (k & 31u)) - 1u));
-                X[i * GW_STRIDE + s] = pv[off + lane];
-            }
-        }
-        if (long_rows) {
-            for (int i = 0; i < nf; ++i) {
-                const unsigned long long off = __shfl_sync(0xffffffffu, my_off, i);
-                const int n = __shfl_sync(0xffffffffu, my_n, i);
-                for (int e = 32 + lane; e < n; e += 32) {
-                    const unsigned k = pk[off + e];
-                    const int s = wofs[k >> 5] + __popc(bits[k >> 5] & ((1u << (k & 31u)) - 1u));
-                    X[i * GW_STRIDE + s] = pv[off + e];
-                }
-            }
-        }
-        __syncwarp();
-        // 3. + 4. upper-triangular tiles of X^T X, flushed from the accumulators
-        const int nt = (u + 7) >> 3;
-        for (int ti = 0; ti < nt; ++ti) {
-            double acc[GW_NT][2];
-#pragma unroll
-            for (int d = 0; d < GW_NT; ++d) acc[d][0] = acc[d][1] = 0.0;
-#pragma unroll
-            for (int ks = 0; ks < GW_T / 4; ++ks) {
-                const double* xr = X + (ks * 4 + r4) * GW_STRIDE + c8;
-                const double a = xr[ti * 8];
-#pragma unroll
-                for (int d = 0; d < GW_NT; ++d)
-                    if (ti + d < nt) dmma(acc[d], a, xr[(ti + d) * 8]);
-            }
-            const int r = ti * 8 + c8;                    // accumulator row (slot)
-            if (r < u) {
-#pragma unroll
-                for (int d = 0; d < GW_NT; ++d) {
-                    if (ti + d >= nt) break;
-#pragma unroll
-                    for (int q = 0; q < 2; ++q) {
-                        const int c = (ti + d) * 8 + r4 * 2 + q;
-                        if (c < u && c >= r && acc[d][q] != 0.0) gram_add<EXACT>(gram, L, ids[r], ids[c], acc[d][q]);
+            for (int i = 0; i < GW_T; ++i)
+                if (i >= lo && i < hi && kk[i] != 0xFFFFFFFFu) atomicOr(&bits[kk[i] >> 5], 1u << (kk[i] & 31u));
+            if (long_rows) {
+                for (int i = lo; i < hi && i < nf; ++i) {
+                    const unsigned long long off = __shfl_sync(0xffffffffu, my_off, i);
+                    const int n = __shfl_sync(0xffffffffu, my_n, i);
+                    for (int e = 32 + lane; e < n; e += 32) {
+                        const unsigned k = pk[off + e];
+                        atomicOr(&bits[k >> 5], 1u << (k & 31u));
                     }
                 }
             }
+            __syncwarp();
+            // slot offsets: exclusive prefix of the words' popcounts
+            int carry = 0;
+            for (int w0 = 0; w0 < words; w0 += 32) {
+                const int w = w0 + lane;
+                const int c = (w < words) ? __popc(bits[w]) : 0;
+                int incl = c;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const int v = __shfl_up_sync(0xffffffffu, incl, o);
+                    if (lane >= o) incl += v;
+                }
+                if (w < words) wofs[w] = (uint16_t)(carry + incl - c);
+                carry += __shfl_sync(0xffffffffu, incl, 31);
+            }
+            const int u = carry;
+            __syncwarp();
+            if (u > GW_CAP && len > 1) { len >>= 1; continue; }            // descend into the left half
+            if (u > GW_CAP) {
+                // a single row with more than GW_CAP entries: pair by pair
+                gram_row_direct<EXACT>(pk, pv, __shfl_sync(0xffffffffu, my_off, lo), __shfl_sync(0xffffffffu, my_n, lo), lane, L, gram);
+            } else if (u > 0) {
+                for (int w = lane; w < words; w += 32) {
+                    unsigned b = bits[w];
+                    int s = wofs[w];
+                    while (b) { ids[s++] = (uint16_t)(w * 32 + __ffs(b) - 1); b &= b - 1u; }
+                }
+                // 2. X[row][slot] = value for the segment's rows; the rows of its k-steps are cleared first (a k-step is
+                // four rows: a segment of one or two rows shares its k-step with rows of earlier segments)
+                const int r_lo = lo & ~3, r_hi = (hi + 3) & ~3;
+                for (int i = r_lo * GW_STRIDE + lane; i < r_hi * GW_STRIDE; i += 32) X[i] = 0.0;
+                __syncwarp();
+#pragma unroll
+                for (int i = 0; i < GW_T; ++i) {
+                    const unsigned long long off = __shfl_sync(0xffffffffu, my_off, i);
+                    if (i >= lo && i < hi && kk[i] != 0xFFFFFFFFu) {
+                        const unsigned k = kk[i];
+                        const int s = wofs[k >> 5] + __popc(bits[k >> 5] & ((1u << (k & 31u)) - 1u));
+                        X[i * GW_STRIDE + s] = pv[off + lane];
+                    }
+                }
+                if (long_rows) {
+                    for (int i = lo; i < hi && i < nf; ++i) {
+                        const unsigned long long off = __shfl_sync(0xffffffffu, my_off, i);
+                        const int n = __shfl_sync(0xffffffffu, my_n, i);
+                        for (int e = 32 + lane; e < n; e += 32) {
+                            const unsigned k = pk[off + e];
+                            const int s = wofs[k >> 5] + __popc(bits[k >> 5] & ((1u << (k & 31u)) - 1u));
+                            X[i * GW_STRIDE + s] = pv[off + e];
+                        }
+                    }
+                }
+                __syncwarp();
+                // 3. + 4. upper-triangular tiles of X^T X over the segment's k-steps, flushed from the accumulators
+                const int nt = (u + 7) >> 3;
+                const int ks_lo = r_lo >> 2, ks_hi = r_hi >> 2;
+                for (int ti = 0; ti < nt; ++ti) {
+                    double acc[GW_NT][2];
+#pragma unroll
+                    for (int d = 0; d < GW_NT; ++d) acc[d][0] = acc[d][1] = 0.0;
+                    for (int ks = ks_lo; ks < ks_hi; ++ks) {
+                        const double* xr = X + (ks * 4 + r4) * GW_STRIDE + c8;
+                        const double a = xr[ti * 8];
+#pragma unroll
+                        for (int d = 0; d < GW_NT; ++d)
+                            if (ti + d < nt) dmma(acc[d], a, xr[(ti + d) * 8]);
+                    }
+                    const int r = ti * 8 + c8;                    // accumulator row (slot)
+                    if (r < u) {
+#pragma unroll
+                        for (int d = 0; d < GW_NT; ++d) {
+                            if (ti + d >= nt) break;
+#pragma unroll
+                            for (int q = 0; q < 2; ++q) {
+                                const int c = (ti + d) * 8 + r4 * 2 + q;
+                                if (c < u && c >= r && acc[d][q] != 0.0) gram_add<EXACT>(gram, L, ids[r], ids[c], acc[d][q]);
+                            }
+                        }
+                    }
+                }
+                __syncwarp();
+            }
+            lo = hi;
+            len = lo & -lo;                                       // the largest aligned segment that starts here
         }
-        __syncwarp();
     }
 }
 
