@@ -38,8 +38,11 @@ namespace sitb {
 #define SITB_GW_WARPS 14
 #endif
 constexpr int GW_T = SITB_GW_T;  // frames per window = K of the local product (mma k-steps of 4)
-constexpr int GW_CAP = 48;       // landmark slots per window (6 tiles of 8)
-constexpr int GW_STRIDE = 52;    // row stride of X in doubles: = 4 mod 16, so the 4 x 8 fragment loads are conflict-free
+#ifndef SITB_GW_CAP
+#define SITB_GW_CAP 48
+#endif
+constexpr int GW_CAP = SITB_GW_CAP;        // landmark slots per window (6 tiles of 8)
+constexpr int GW_STRIDE = GW_CAP + 4;      // row stride of X in doubles: = 4 mod 16, so the 4 x 8 fragment loads are conflict-free
 constexpr int GW_WARPS = SITB_GW_WARPS;   // warps per CTA (two CTAs per SM; X is GW_T x GW_STRIDE doubles per warp)
 constexpr int GW_NT = GW_CAP / 8;
 
