@@ -40,7 +40,8 @@ for rep in range(REPS):
     clusters = gm._clusters_on_device(m2); t = tick("clusters from m2", t)
     clusters = [list(c) for c in clusters if seen_n[c[0]] > 0]
     vectors = gm.principal_vectors(gm._covariance_blocks(cov, clusters)); t = tick("eigh host", t)
-    cid, w = gm._centre_tables(clusters, vectors, eng.L); eng.set_centers(cid, w, len(clusters))
+    flat = gm._FlatClusters(clusters, eng.L); flat.weights = np.concatenate(vectors)
+    cid, w = flat.tables(); eng.set_centers(cid, w, len(clusters))
     best = new_best_table(len(clusters), eng.device); src.assign(float('nan'), best=best); t = tick("pass B", t)
     _, rows = read_best_table(best); lv = src.rows(rows); t = tick("best rows refill", t)
     N = F * system.n_mobile

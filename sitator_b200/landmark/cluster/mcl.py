@@ -116,13 +116,20 @@ def landmark_graph(source, gram_method='sparse'):
 
 
 def _clusters_on_device(m2):
-    """util/mcl.py:52-60 with only the attractor rows leaving the device."""
+    """util/mcl.py:52-60 with only the attractor rows leaving the device.  Same construct as the reference (a ``set`` of
+    tuples of column indices, in attractor order), so the clusters come out in the reference's order under the same
+    interpreter; the tuples are cut from one ``nonzero`` of the whole block instead of one call per row."""
     import torch
     attractors = torch.nonzero(torch.diagonal(m2) != 0).reshape(-1)
     rows = (m2.index_select(0, attractors) != 0).cpu().numpy()
+    ri, ci = rows.nonzero()                                   # row-major: ascending columns within each row
+    ends = np.cumsum(np.bincount(ri, minlength=rows.shape[0]))
+    cols = ci.tolist()
     clusters = set()
-    for r in rows:
-        clusters.add(tuple(r.nonzero()[0]))
+    beg = 0
+    for end in ends.tolist():
+        clusters.add(tuple(cols[beg:end]))
+        beg = end
     return list(clusters)
 
 
@@ -145,32 +152,80 @@ def _covariance_blocks(cov, clusters):
     return out
 
 
-def principal_vectors_device(cov, clusters, L):
+class _FlatClusters(object):
+    """The landmark clusters as flat arrays (members, sizes, one weight per member): the per-landmark centre tables the
+    kernels read, the good-site and min_samples filters and the rescaling are then a few vector operations instead of
+    Python loops over the clusters (which took longer than the device passes between them)."""
+
+    def __init__(self, clusters, L):
+        import itertools
+        self.clusters = clusters
+        self.L = L
+        self.sizes = np.fromiter((len(c) for c in clusters), dtype=np.int64, count=len(clusters))
+        self.members = np.fromiter(itertools.chain.from_iterable(clusters), dtype=np.int64, count=int(self.sizes.sum()))
+        if len(self.members) and np.bincount(self.members, minlength=L).max() > 1:
+            raise ValueError("landmark clusters overlap; the sparse centre representation needs disjoint clusters")
+        self.weights = np.zeros(len(self.members), dtype=np.float64)
+
+    def __len__(self):
+        return len(self.clusters)
+
+    def offsets(self):
+        out = np.zeros(len(self.sizes) + 1, dtype=np.int64)
+        np.cumsum(self.sizes, out=out[1:])
+        return out
+
+    def tables(self):
+        """(cluster of landmark (L,) int32 with -1 = none, centre weight (L,) float64)."""
+        cid = np.full(self.L, -1, dtype=np.int32)
+        w = np.zeros(self.L, dtype=np.float64)
+        cid[self.members] = np.repeat(np.arange(len(self.sizes), dtype=np.int32), self.sizes)
+        w[self.members] = self.weights
+        return cid, w
+
+    def keep(self, mask, scale=None):
+        """The clusters where ``mask``; weights divided by ``scale`` (per cluster) first if given."""
+        mask = np.asarray(mask, dtype=bool)
+        out = _FlatClusters.__new__(_FlatClusters)
+        out.L = self.L
+        out.clusters = [c for c, m in zip(self.clusters, mask.tolist()) if m]
+        member_mask = np.repeat(mask, self.sizes)
+        weights = self.weights if scale is None else self.weights / np.repeat(np.asarray(scale, dtype=np.float64), self.sizes)
+        out.sizes = self.sizes[mask]
+        out.members = self.members[member_mask]
+        out.weights = weights[member_mask]
+        return out
+
+
+def principal_vectors_device(cov, clusters, L, flat=None):
     """mcl.py:73-80 on the device (csrc/sitb_eig.cu): per-landmark centre weights (L,) float64 numpy -- each cluster's
-    unit principal eigenvector scattered onto its landmarks.  Blocks larger than the kernel's limit use LAPACK."""
+    unit principal eigenvector scattered onto its landmarks (``flat.weights`` is set too if ``flat`` is given).  Blocks
+    larger than the kernel's limit use LAPACK."""
     import torch
     lib = _native.load()
-    members = np.concatenate([np.asarray(c, dtype=np.int32) for c in clusters])
-    offsets = np.zeros(len(clusters) + 1, dtype=np.int32)
-    offsets[1:] = np.cumsum([len(c) for c in clusters])
+    if flat is None:
+        flat = _FlatClusters([list(c) for c in clusters], L)
+    n_c = len(flat)
+    offsets = flat.offsets().astype(np.int32)
     dev = cov.device
-    packed = torch.as_tensor(np.concatenate([offsets, members]), device=dev)
+    packed = torch.as_tensor(np.concatenate([offsets, flat.members.astype(np.int32)]), device=dev)
     w = torch.zeros((L,), dtype=torch.float64, device=dev)
-    sweeps = torch.zeros((len(clusters),), dtype=torch.int32, device=dev)
+    sweeps = torch.zeros((n_c,), dtype=torch.int32, device=dev)
     stream = torch.cuda.current_stream(dev).cuda_stream
     _native.check(lib.sitb_principal_vectors(dev.index, C.c_void_p(cov.data_ptr()), L,
                                              C.c_void_p(packed.data_ptr() + 4 * len(offsets)), C.c_void_p(packed.data_ptr()),
-                                             len(clusters), C.c_void_p(w.data_ptr()), C.c_void_p(sweeps.data_ptr()),
+                                             n_c, C.c_void_p(w.data_ptr()), C.c_void_p(sweeps.data_ptr()),
                                              C.c_void_p(stream)))
-    out = torch.empty((L + len(clusters),), dtype=torch.float64, device=dev)
+    out = torch.empty((L + n_c,), dtype=torch.float64, device=dev)
     out[:L] = w
     out[L:] = sweeps.to(torch.float64)
     h = out.cpu().numpy()                       # one small device -> host copy
     w_h, sw = h[:L].copy(), h[L:]
     for i in np.nonzero(sw < 0)[0]:             # blocks beyond the kernel's size limit
-        cl = np.asarray(clusters[i], dtype=np.int64)
+        cl = np.asarray(flat.clusters[i], dtype=np.int64)
         blk = cov[torch.as_tensor(cl, device=dev)][:, torch.as_tensor(cl, device=dev)].cpu().numpy()
         w_h[cl] = principal_vector(blk)
+    flat.weights = w_h[flat.members]
     return w_h
 
 
@@ -211,18 +266,6 @@ def _to_host_async(tensors):
     return [h.numpy() for h in outs], done
 
 
-def _centre_tables(clusters, vectors, L):
-    cid = np.full(L, -1, dtype=np.int32)
-    w = np.zeros(L, dtype=np.float64)
-    for i, (cl, vec) in enumerate(zip(clusters, vectors)):
-        cl = np.asarray(cl, dtype=np.int64)
-        if np.any(cid[cl] != -1):
-            raise ValueError("landmark clusters overlap; the sparse centre representation needs disjoint clusters")
-        cid[cl] = i
-        w[cl] = vec
-    return cid, w
-
-
 def do_landmark_clustering(landmark_vectors, clustering_params, min_samples, verbose):
     import torch
     from ...util.phases import PhaseTimer
@@ -256,12 +299,13 @@ def do_landmark_clustering(landmark_vectors, clustering_params, min_samples, ver
 
     # -- centres: principal eigenvector of each cluster's covariance block (mcl.py:73-80)
     with timer.phase("  centres: eigenvectors of the covariance blocks"):
+        flat = _FlatClusters(clusters, L)
         if eig_where == 'host':
             vectors = principal_vectors(_covariance_blocks(cov, clusters))
+            flat.weights = np.concatenate(vectors) if len(vectors) else np.zeros(0)
         else:
-            w_all = principal_vectors_device(cov, clusters, L)
-            vectors = [w_all[np.asarray(cl, dtype=np.int64)] for cl in clusters]
-        cid, w = _centre_tables(clusters, vectors, L)
+            principal_vectors_device(cov, clusters, L, flat=flat)
+        cid, w = flat.tables()
 
     # -- pass B: best matching landmark vector per cluster (mcl.py:81-89)
     with timer.phase("  pass B: best row per cluster (collective)"):
@@ -272,19 +316,16 @@ def do_landmark_clustering(landmark_vectors, clustering_params, min_samples, ver
     with timer.phase("  best rows: norms (collective)"):
         # best_vals[i] = |best lvec . centre| (mcl.py:84-85) came out of the pass; only the row's norm (:86) is missing
         best_norms = np.sqrt(source.row_norms2(best_rows))
-    good = np.zeros(n_clusters, dtype=bool)
-    scale = np.ones(n_clusters)
-    for i, cl in enumerate(clusters):
-        best_match_dot = float(best_vals[i])
-        with np.errstate(divide='ignore', invalid='ignore'):
-            best_match_dot_norm = best_match_dot / best_norms[i]
-        good[i] = (best_match_dot_norm >= good_site_normed_threshold) and (best_match_dot >= good_site_project_thresh)
-        scale[i] = best_match_dot
+    best_match_dot = np.asarray(best_vals, dtype=np.float64)
+    with np.errstate(divide='ignore', invalid='ignore'):
+        best_match_dot_norm = best_match_dot / best_norms
+    good = (best_match_dot_norm >= good_site_normed_threshold) & (best_match_dot >= good_site_project_thresh)
     logger.debug("Kept %i/%i landmark clusters as good sites" % (int(np.sum(good)), len(good)))
 
-    # -- keep the good sites (mcl.py:94-96)
-    clusters = [c for i, c in enumerate(clusters) if good[i]]
-    vectors = [vectors[i] / scale[i] for i in range(n_clusters) if good[i]]
+    # -- keep the good sites, centres scaled by their best match (mcl.py:94-96)
+    with np.errstate(divide='ignore', invalid='ignore'):
+        flat = flat.keep(good, scale=best_match_dot)
+    clusters = flat.clusters
     n_clusters = len(clusters)
     if n_clusters == 0:
         raise ValueError("`min_samples` too large; all 0 clusters under threshold.")
@@ -292,7 +333,7 @@ def do_landmark_clustering(landmark_vectors, clustering_params, min_samples, ver
     # -- pass C: predict + bincount, then the min_samples filter (DotProdClassifier.pyx:86-115).  The pass also
     # writes everything the final predict needs: when the filter removes no cluster (the usual case) the
     # centres of pass D are the same and its outputs would be bit-identical, so pass D is skipped.
-    cid, w = _centre_tables(clusters, vectors, L)
+    cid, w = flat.tables()
     eng.set_centers(cid, w, n_clusters)
     N = source.n_local
 
@@ -324,15 +365,15 @@ def do_landmark_clustering(landmark_vectors, clustering_params, min_samples, ver
         raise ValueError("`min_samples` too large; all %i clusters under threshold." % len(count_mask))
     logger.info("DotProdClassifier: %i/%i assignment counts below threshold %s (%s); %i clusters remain." %
                 (int(np.sum(~count_mask)), len(count_mask), min_samples, ms, int(np.sum(count_mask))))
-    clusters = [c for i, c in enumerate(clusters) if count_mask[i]]
-    vectors = [v for i, v in enumerate(vectors) if count_mask[i]]
+    flat = flat.keep(count_mask)
+    clusters = flat.clusters
     kept_counts = cluster_counts[count_mask]
     n_sites = len(clusters)
 
     # -- pass D: final predict + representative landmark vectors (mcl.py:114-122) + per-site best row
     if not np.all(count_mask):
         with timer.phase("  pass D: predict with the kept centres"):
-            cid, w = _centre_tables(clusters, vectors, L)
+            cid, w = flat.tables()
             eng.set_centers(cid, w, n_sites)
             if source.sparse is not None:
                 # the surviving centres are unchanged: rows of surviving clusters keep arg-max and confidence, only
