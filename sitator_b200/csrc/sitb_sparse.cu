@@ -133,7 +133,7 @@ __device__ __noinline__ void assign_row_hard(
 // scattered into a small shared-memory accumulator per row.  Sums are formed in an order that depends on the row alone.
 // Rows with more than 32 entries are "hard" and handled by the whole warp afterwards (assign_row).
 template <bool TS, bool SLOT>
-__global__ void __launch_bounds__(256, 4) k_assign_sparse8(
+__global__ void __launch_bounds__(512, 2) k_assign_sparse8(
     const unsigned long long* __restrict__ row_ptr, const uint16_t* __restrict__ pk, const double* __restrict__ pv,
     long long n_rows, long long row0, int L, const int* __restrict__ cid, const double* __restrict__ cw,
     int n_clusters, double thr, long long* __restrict__ labels, double* __restrict__ confs,
@@ -410,8 +410,17 @@ cudaError_t launch_assign_sparse(const unsigned long long* row_ptr, const uint16
         const bool ts = (size_t)L * 12 <= 40 * 1024;      // centre tables in shared memory (L <= ~3400)
         const size_t table_bytes = ts ? (size_t)L * 12 + 8 : 0;
         auto smem_for = [&](int w) { return (size_t)w * (16 * (size_t)C * tables + 32 * (size_t)C) + 8 * (size_t)((C + 1) / 2) + 8 * (size_t)C + table_bytes + 16; };
-        warps = 8;
-        while (warps > 1 && smem_for(warps) > 56 * 1024) warps >>= 1;
+        // warps per CTA: the most resident warps per SM (64 registers: at most 32) within 227 KB of shared memory; the
+        // centre tables are per CTA, the accumulators and best-row tables per warp
+        warps = 1;
+        int best_resident = 0;
+        for (int w = 16; w >= 1; w = (w > 2 ? w - 2 : w - 1)) {
+            const size_t b = smem_for(w) + 1024;
+            if (b > 200 * 1024) continue;
+            int r = (int)((227 * 1024) / b) * w;
+            if (r > 32) r = 32;
+            if (r > best_resident) { best_resident = r; warps = w; }
+        }
         smem = smem_for(warps);
         if (smem > 200 * 1024) return cudaErrorInvalidConfiguration;
         const bool slotted = slot == 32;
