@@ -121,9 +121,11 @@ def _clusters_on_device(m2):
     interpreter; the tuples are cut from one ``nonzero`` of the whole block instead of one call per row."""
     import torch
     attractors = torch.nonzero(torch.diagonal(m2) != 0).reshape(-1)
-    rows = (m2.index_select(0, attractors) != 0).cpu().numpy()
-    ri, ci = rows.nonzero()                                   # row-major: ascending columns within each row
-    ends = np.cumsum(np.bincount(ri, minlength=rows.shape[0]))
+    # (row, column) of every non-zero of the attractor rows, row-major: ascending columns within each row.  Found on the
+    # device: a few KB cross PCIe instead of the rows, and NumPy's 2-D nonzero alone took 0.8 ms here.
+    nz = torch.nonzero(m2.index_select(0, attractors)).cpu().numpy()
+    ri, ci = nz[:, 0], nz[:, 1]
+    ends = np.cumsum(np.bincount(ri, minlength=int(attractors.shape[0])))
     cols = ci.tolist()
     clusters = set()
     beg = 0
