@@ -56,7 +56,7 @@ def parse_args():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--frames", type=int, default=None, help="frames per GPU (default: the config's 100000)")
-    ap.add_argument("--e2e-steps", type=int, default=2)
+    ap.add_argument("--e2e-steps", type=int, default=5)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-frames", type=int, default=400)
     ap.add_argument("--strong-frames", type=int, default=1000000,
@@ -434,7 +434,8 @@ def run_ours(args):
     up_max = max_over_ranks(up_ms)
     up_min = -max_over_ranks(-up_ms)
     e2e = {"value": F * A * world / e2e_t, "unit": UNIT, "h2d_bytes_per_step": int(frames.nbytes),
-           "d2h_bytes_per_step": int(F * M * 16), "ms": e2e_t * 1e3, "steps": len(e2e_ms), "n_sites": int(n_sites),
+           "d2h_bytes_per_step": int(F * M * 16), "ms": e2e_t * 1e3, "steps": len(e2e_ms),
+           "ms_each_step": [round(x, 3) for x in e2e_ms], "n_sites": int(n_sites),
            "upload_alone_ms_slowest_rank": up_max, "upload_alone_ms_fastest_rank": up_min,
            "upload_gbs_slowest_rank": frames.nbytes / (up_max * 1e-3) / 1e9,
            "what": "LandmarkAnalysis(clustering_algorithm='mcl').run(sn, frames) with frames in pinned host memory"}
