@@ -29,6 +29,13 @@ def test_library_exports_every_declared_symbol():
     assert lib.sitb_version() >= 100
 
 
+def test_every_declared_entry_point_is_documented_in_the_integration_guide():
+    """INTEGRATION.md says which reference lines each ABI entry replaces; a new entry point must get its row."""
+    doc = open(os.path.join(ROOT, "INTEGRATION.md")).read()
+    missing = [n for n in _declared() if n not in doc]
+    assert not missing, "not mentioned in INTEGRATION.md: %s" % missing
+
+
 def test_no_cpu_fallback():
     import torch
     if torch.cuda.is_available():
